@@ -1,0 +1,127 @@
+// api.cu — context lifetime, error strings, and the host-buffer entry point.
+#include "common.cuh"
+#include <new>
+
+extern "C" int da3s_version(void) { return DA3S_VERSION; }
+
+extern "C" const char* da3s_strerror(int code) {
+    switch (code) {
+        case DA3S_OK: return "ok";
+        case DA3S_EINVAL: return "invalid argument";
+        case DA3S_EALIGN: return "pointer not 16-byte aligned";
+        case DA3S_ENOMEM: return "context workspace too small";
+        case DA3S_ECUDA: return "CUDA runtime error";
+        case DA3S_ETOOFEW: return "too few usable points";
+        default: return "unknown da3s error";
+    }
+}
+
+extern "C" int da3s_create(int device, size_t workspace_bytes, da3s_ctx** out) {
+    if (!out) return DA3S_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return DA3S_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return DA3S_ECUDA;
+    da3s_ctx* c = new (std::nothrow) da3s_ctx();
+    if (!c) return DA3S_ENOMEM;
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return DA3S_ECUDA; }
+    c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : DA3S_SM_COUNT_FALLBACK;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    if (workspace_bytes < (1u << 20)) workspace_bytes = (1u << 20);
+    c->ws_bytes = workspace_bytes;
+    c->ws = nullptr;
+    cudaError_t e = cudaMalloc((void**)&c->ws, workspace_bytes);
+    if (e != cudaSuccess) { int rc = (e == cudaErrorMemoryAllocation) ? DA3S_ENOMEM : DA3S_ECUDA; cudaGetLastError(); delete c; return rc; }
+    c->ws_top = 0; c->last_cuda_error = 0; c->launches = 0;
+    c->vox_keys = nullptr; c->vox_acc = nullptr; c->vox_rgbn = nullptr; c->vox_slots = 0; c->vox_dropped = nullptr; c->vox_bytes = 0;
+    *out = c;
+    return DA3S_OK;
+}
+
+extern "C" int da3s_destroy(da3s_ctx* ctx) {
+    if (!ctx) return DA3S_EINVAL;
+    cudaSetDevice(ctx->device);
+    if (ctx->ws) cudaFree(ctx->ws);
+    delete ctx;
+    return DA3S_OK;
+}
+
+extern "C" int da3s_last_cuda_error(const da3s_ctx* ctx) { return ctx ? ctx->last_cuda_error : 0; }
+extern "C" unsigned long long da3s_launch_count(const da3s_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+// ---------------------------------------------------------------------------------
+// host-buffer path: H2D copies, the device pipeline, D2H of the rows, one synchronise.
+// ---------------------------------------------------------------------------------
+__global__ void fill_pairs_kernel(da3s_pair* pairs, int n_pairs, long long M, int overlap,
+                                  const float* dA, const float* cA, const float* dB, const float* cB,
+                                  const da3s_cam* camA, const da3s_cam* camB) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    da3s_pair p;
+    p.depth_a = dA + (size_t)i * M; p.conf_a = cA + (size_t)i * M;
+    p.depth_b = dB + (size_t)i * M; p.conf_b = cB + (size_t)i * M;
+    p.cam_a = camA + (size_t)i * overlap; p.cam_b = camB + (size_t)i * overlap;
+    pairs[i] = p;
+}
+
+extern "C" int da3s_align_pairs_host(da3s_ctx* ctx, int n_pairs, int overlap, int H, int W,
+                                     const float* depth_a, const float* conf_a, const float* K_a, const float* E_a,
+                                     const float* depth_b, const float* conf_b, const float* K_b, const float* E_b,
+                                     const da3s_align_opts* opts, const int32_t* sample_idx,
+                                     double* sim3_rows, void* stream) {
+    if (!ctx || !depth_a || !conf_a || !K_a || !E_a || !depth_b || !conf_b || !K_b || !E_b || !opts || !sim3_rows)
+        return DA3S_EINVAL;
+    if (n_pairs <= 0 || overlap <= 0 || H <= 0 || W <= 0) return DA3S_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long M = (long long)overlap * H * W;
+    if ((M * 4) % 16 != 0) return DA3S_EALIGN;             // packed pairs must keep 16-byte alignment
+    const size_t map_bytes = sizeof(float) * (size_t)n_pairs * M;
+    const size_t nf = (size_t)n_pairs * overlap;
+    // input staging lives at the start of the workspace; da3s_align_pairs resets the bump
+    // pointer, so reserve the staging area by sub-allocating from a temporary context view
+    ws_reset(ctx);
+    WS_ALLOC(ctx, float, d_dA, (size_t)n_pairs * M);
+    WS_ALLOC(ctx, float, d_cA, (size_t)n_pairs * M);
+    WS_ALLOC(ctx, float, d_dB, (size_t)n_pairs * M);
+    WS_ALLOC(ctx, float, d_cB, (size_t)n_pairs * M);
+    WS_ALLOC(ctx, float, d_K, nf * 9 * 2);
+    WS_ALLOC(ctx, float, d_E, nf * 12 * 2);
+    WS_ALLOC(ctx, da3s_cam, d_cam, nf * 2);
+    WS_ALLOC(ctx, da3s_pair, d_pairs, n_pairs);
+    WS_ALLOC(ctx, double, d_rows, (size_t)n_pairs * DA3S_ROW_LEN);
+    int32_t* d_idx = nullptr;
+    if (opts->n_hyp > 0) {
+        if (!sample_idx) return DA3S_EINVAL;
+        WS_ALLOC(ctx, int32_t, tmp, (size_t)n_pairs * opts->n_hyp * 3);
+        d_idx = tmp;
+    }
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dA, depth_a, map_bytes, cudaMemcpyHostToDevice, st));
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(d_cA, conf_a, map_bytes, cudaMemcpyHostToDevice, st));
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dB, depth_b, map_bytes, cudaMemcpyHostToDevice, st));
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(d_cB, conf_b, map_bytes, cudaMemcpyHostToDevice, st));
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(d_K, K_a, sizeof(float) * nf * 9, cudaMemcpyHostToDevice, st));
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(d_K + nf * 9, K_b, sizeof(float) * nf * 9, cudaMemcpyHostToDevice, st));
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(d_E, E_a, sizeof(float) * nf * 12, cudaMemcpyHostToDevice, st));
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(d_E + nf * 12, E_b, sizeof(float) * nf * 12, cudaMemcpyHostToDevice, st));
+    if (d_idx)
+        DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(d_idx, sample_idx, sizeof(int32_t) * (size_t)n_pairs * opts->n_hyp * 3,
+                                             cudaMemcpyHostToDevice, st));
+    int rc = da3s_build_cams(ctx, d_K, d_E, (int)(2 * nf), DA3S_CAM_CLOSED_FORM, d_cam, stream);
+    if (rc != DA3S_OK) return rc;
+    fill_pairs_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(d_pairs, n_pairs, M, overlap, d_dA, d_cA, d_dB, d_cB,
+                                                             d_cam, d_cam + nf);
+    DA3S_LAUNCH_CHECK(ctx);
+    // run the device pipeline on the remainder of the workspace
+    unsigned char* ws_save = ctx->ws; size_t bytes_save = ctx->ws_bytes;
+    size_t used = (ctx->ws_top + 255) & ~(size_t)255;
+    ctx->ws += used; ctx->ws_bytes -= used;
+    rc = da3s_align_pairs(ctx, d_pairs, n_pairs, overlap, H, W, opts, d_idx, d_rows, nullptr, nullptr, stream);
+    ctx->ws = ws_save; ctx->ws_bytes = bytes_save;
+    if (rc != DA3S_OK) return rc;
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(sim3_rows, d_rows, sizeof(double) * (size_t)n_pairs * DA3S_ROW_LEN,
+                                         cudaMemcpyDeviceToHost, st));
+    DA3S_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    return DA3S_OK;
+}

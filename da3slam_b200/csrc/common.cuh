@@ -1,0 +1,111 @@
+// common.cuh — context, error plumbing and device helpers shared by every kernel file.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+
+#include "../../include/da3s.h"
+
+#define DA3S_SM_COUNT_FALLBACK 148
+
+struct da3s_ctx {
+    int device;
+    int sm_count;
+    size_t l2_bytes;
+    unsigned char* ws;          // workspace base (cudaMalloc, 256-byte aligned)
+    size_t ws_bytes;
+    size_t ws_top;              // bump pointer for the current call
+    int last_cuda_error;
+    unsigned long long launches;
+    // voxel hash-table state (lives at the END of the workspace between begin/finish)
+    unsigned long long* vox_keys;
+    unsigned long long* vox_acc;    // [slots][4]: sum_qx, sum_qy, sum_qz, (count | rgb sums packed separately)
+    unsigned int* vox_rgbn;         // [slots][4]: count, sum_r, sum_g, sum_b
+    long long vox_slots;
+    unsigned long long* vox_dropped;
+    size_t vox_bytes;
+};
+
+#define DA3S_CHECK_CUDA(ctx, expr)                                   \
+    do {                                                             \
+        cudaError_t _e = (expr);                                     \
+        if (_e != cudaSuccess) {                                     \
+            (ctx)->last_cuda_error = (int)_e;                        \
+            return DA3S_ECUDA;                                       \
+        }                                                            \
+    } while (0)
+
+#define DA3S_LAUNCH_CHECK(ctx)                                       \
+    do {                                                             \
+        (ctx)->launches++;                                           \
+        cudaError_t _e = cudaGetLastError();                         \
+        if (_e != cudaSuccess) {                                     \
+            (ctx)->last_cuda_error = (int)_e;                        \
+            return DA3S_ECUDA;                                       \
+        }                                                            \
+    } while (0)
+
+// ---- workspace bump allocator (per call; nothing is allocated after create) -------
+static inline void ws_reset(da3s_ctx* c) { c->ws_top = 0; }
+static inline void* ws_alloc(da3s_ctx* c, size_t bytes) {
+    size_t start = (c->ws_top + 255) & ~(size_t)255;
+    size_t limit = c->ws_bytes - c->vox_bytes;      // the voxel table owns the tail while active
+    if (start + bytes > limit) return nullptr;
+    c->ws_top = start + bytes;
+    return c->ws + start;
+}
+#define WS_ALLOC(ctx, T, var, count)                                             \
+    T* var = (T*)ws_alloc((ctx), sizeof(T) * (size_t)(count));                   \
+    if (!(var)) return DA3S_ENOMEM
+
+__host__ __device__ static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+// ---- device helpers ----------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming 128-bit load that does not allocate in L1 (data is touched once per pass)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// order-preserving float32 <-> uint32 key (total order: -inf < ... < -0 < +0 < ... < +inf < NaN+)
+__device__ __forceinline__ unsigned int f32_to_key(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_f32(unsigned int k) {
+    unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+// SPEC 1 (oracle/SPEC.md): float32 camera-frame unprojection, every op rounded once.
+__device__ __forceinline__ void cam_fast(float u, float v, float d, float cu, float cv,
+                                         float inv_fu, float inv_fv, float& x, float& y) {
+    x = __fmul_rn(__fmul_rn(__fsub_rn(u, cu), d), inv_fu);
+    y = __fmul_rn(__fmul_rn(__fsub_rn(v, cv), d), inv_fv);
+}
+
+__device__ __forceinline__ bool is_finite_f(float x) { return fabsf(x) <= 3.402823466e+38f; }

@@ -1,0 +1,1043 @@
+// pair_align.cu — the submap-pair alignment hot path.
+//
+//   thresholds   exact medians (select.cu) -> conf threshold, depth scale        (device only)
+//   K4 RANSAC    3-point hypotheses, float32-FMA inlier counts, winner           (ALU bound)
+//   K2/K3 IRLS   fused unproject + joint mask + conf/Huber weight + 20 float64 moments,
+//                warp-shuffle -> shared -> per-block partials -> fixed-order final sum and
+//                closed-form Umeyama by the LAST block of each pair (ticket)      (HBM bound)
+//
+// One launch covers every pair of the batch: grid = (overlap * tiles_per_frame, n_pairs).
+// Reductions use no floating-point atomics and a tiling that depends only on H*W, so the
+// rows are bit-identical from run to run and for any sharding of the pairs over GPUs.
+//
+// Algorithmic bytes per correspondence and pass: 16 B read (depth+conf of both sides),
+// 0 B written.  Moments are accumulated in each overlap frame's CAMERA coordinates and
+// moved to world coordinates once per (pair, frame) — the transform is linear in the
+// moments — so world mode costs nothing per pixel.
+#include "common.cuh"
+#include "sim3_math.cuh"
+
+int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, long long max_n,
+                     da3s_select_out* out, cudaStream_t st);
+
+#define PA_THREADS 256
+#define PA_GROUPS_PER_BLOCK 2048            // 8192 pixels per block; depends on nothing but this constant
+
+struct PairState {
+    double s, R[9], t[3];
+    double change, mean_res, n_valid;
+    int iters, done, status, gate_on;
+};
+
+struct PairArgs {
+    const da3s_pair* pairs;
+    int n_pairs, overlap, H, W;
+    long long P;
+    int tiles_per_frame;
+    int world, valid_depth, huber, variant;
+    float depth_eps;
+    const float* thr;                       // [n_pairs]
+    const float* dscale;                    // [n_pairs] (nullable = 1)
+    PairState* state;                       // [n_pairs]
+    double* eff;                            // [n_pairs][overlap][12]  camera-frame (A | b) of the current estimate
+    const float* gate;                      // [n_pairs][12] winning hypothesis (nullable)
+    float gate_thr2;
+    double* partials;                       // [n_pairs][overlap*tiles][MOM_LEN]
+    unsigned int* tickets;                  // [n_pairs]
+    double huber_delta, tol;
+    int max_iterations, min_points;
+    double* rows;                           // [n_pairs][16]
+    da3s_pair_aux* aux;
+};
+
+struct FrameConst {
+    float cuA, cvA, ifuA, ifvA, cuB, cvB, ifuB, ifvB;
+    float MfA[12], MfB[12];                 // float32 c2w (RANSAC world points, SPEC 4)
+    float gate[12];
+    double effA[9], effb[3];
+    float thr, ds;
+    int gate_on;
+};
+
+__device__ __forceinline__ void load_frame_const(FrameConst& fc, const da3s_pair& pr, int frame, const PairArgs& a, int pair) {
+    const da3s_cam& ca = pr.cam_a[frame];
+    const da3s_cam& cb = pr.cam_b[frame];
+    fc.cuA = ca.cu; fc.cvA = ca.cv; fc.ifuA = ca.inv_fu; fc.ifvA = ca.inv_fv;
+    fc.cuB = cb.cu; fc.cvB = cb.cv; fc.ifuB = cb.inv_fu; fc.ifvB = cb.inv_fv;
+    for (int k = 0; k < 12; ++k) { fc.MfA[k] = (float)ca.c2w[k]; fc.MfB[k] = (float)cb.c2w[k]; }
+    fc.thr = a.thr[pair];
+    fc.ds = a.dscale ? a.dscale[pair] : 1.0f;
+    fc.gate_on = 0;
+    if (a.gate && a.state && a.state[pair].gate_on) {
+        fc.gate_on = 1;
+        for (int k = 0; k < 12; ++k) fc.gate[k] = a.gate[12 * (size_t)pair + k];
+    }
+    if (a.eff) {
+        const double* e = a.eff + ((size_t)pair * a.overlap + frame) * 12;
+        for (int k = 0; k < 9; ++k) fc.effA[k] = e[k];
+        for (int k = 0; k < 3; ++k) fc.effb[k] = e[9 + k];
+    }
+}
+
+// One correspondence: joint mask, float32 camera-frame points of both sides (SPEC 1, 2).
+__device__ __forceinline__ bool corr_points(const FrameConst& fc, bool valid_depth, float eps, int u, int v,
+                                            float dA, float cA, float dB, float cB,
+                                            float* x /* source = B */, float* y /* target = A */, float& dBs) {
+    dBs = __fmul_rn(dB, fc.ds);             // solver.py:126: depth * s_depth in float32
+    bool keep = (cA > fc.thr) && (cB > fc.thr);
+    if (valid_depth) keep = keep && (dA > eps) && (dBs > eps) && is_finite_f(dA) && is_finite_f(dBs);
+    float uf = (float)u, vf = (float)v;
+    cam_fast(uf, vf, dA, fc.cuA, fc.cvA, fc.ifuA, fc.ifvA, y[0], y[1]);
+    y[2] = dA;
+    cam_fast(uf, vf, dBs, fc.cuB, fc.cvB, fc.ifuB, fc.ifvB, x[0], x[1]);
+    x[2] = dBs;
+    return keep;
+}
+
+__device__ __forceinline__ void to_world_f32(const float* M, const float* p, float* w) {
+    w[0] = fmaf(M[0], p[0], fmaf(M[1], p[1], fmaf(M[2], p[2], M[3])));
+    w[1] = fmaf(M[4], p[0], fmaf(M[5], p[1], fmaf(M[6], p[2], M[7])));
+    w[2] = fmaf(M[8], p[0], fmaf(M[9], p[1], fmaf(M[10], p[2], M[11])));
+}
+
+// SPEC 4 residual: p_i = fma(A_i0,x0, fma(A_i1,x1, fma(A_i2,x2, t_i))); d = p - y; r2 = fma(d0,d0, fma(d1,d1, d2*d2))
+__device__ __forceinline__ float residual2_f32(const float* A /* 9 + t 3 */, const float* x, const float* y) {
+    float d0 = __fsub_rn(fmaf(A[0], x[0], fmaf(A[1], x[1], fmaf(A[2], x[2], A[9]))), y[0]);
+    float d1 = __fsub_rn(fmaf(A[3], x[0], fmaf(A[4], x[1], fmaf(A[5], x[2], A[10]))), y[1]);
+    float d2 = __fsub_rn(fmaf(A[6], x[0], fmaf(A[7], x[1], fmaf(A[8], x[2], A[11]))), y[2]);
+    return fmaf(d0, d0, fmaf(d1, d1, __fmul_rn(d2, d2)));
+}
+
+// RANSAC points of a correspondence (camera or float32-world), written to xs/ys
+__device__ __forceinline__ void ransac_points(const FrameConst& fc, int world, const float* x, const float* y, float* xs, float* ys) {
+    if (world) { to_world_f32(fc.MfB, x, xs); to_world_f32(fc.MfA, y, ys); }
+    else { for (int k = 0; k < 3; ++k) { xs[k] = x[k]; ys[k] = y[k]; } }
+}
+
+// ---------------------------------------------------------------------------------
+// per-pair solve, run by one thread of the last block
+// ---------------------------------------------------------------------------------
+__device__ __noinline__ void write_row(const PairArgs& a, int pair, const PairState& st) {
+    double* r = a.rows + (size_t)pair * DA3S_ROW_LEN;
+    r[DA3S_ROW_S] = st.s;
+    for (int k = 0; k < 9; ++k) r[DA3S_ROW_R + k] = st.R[k];
+    for (int k = 0; k < 3; ++k) r[DA3S_ROW_T + k] = st.t[k];
+    r[DA3S_ROW_NVALID] = st.n_valid;
+    r[DA3S_ROW_ITERS] = (double)st.iters;
+    r[DA3S_ROW_STATUS] = (double)st.status;
+    if (a.aux) { a.aux[pair].mean_residual = st.mean_res; a.aux[pair].last_change = st.change; }
+}
+
+__device__ __noinline__ void set_effective(const PairArgs& a, int pair, const PairState& st) {
+    for (int f = 0; f < a.overlap; ++f) {
+        double* e = a.eff + ((size_t)pair * a.overlap + f) * 12;
+        if (a.world) {
+            const da3s_pair pr = a.pairs[pair];
+            effective_cam_transform(st.s, st.R, st.t, pr.cam_b[f].c2w, pr.cam_a[f].c2w, e, e + 9);
+        } else {
+            for (int k = 0; k < 9; ++k) e[k] = st.s * st.R[k];
+            for (int k = 0; k < 3; ++k) e[9 + k] = st.t[k];
+        }
+    }
+}
+
+__device__ __noinline__ void solve_pair(const PairArgs& a, int pair, const double* mom /* world or camera moments */) {
+    PairState st = a.state[pair];
+    const double n = mom[MOM_N];
+    st.n_valid = n;
+    if (n < (double)a.min_points) {                         // utils/align.py:154-156
+        st.s = 1.0;
+        for (int k = 0; k < 9; ++k) st.R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+        st.t[0] = st.t[1] = st.t[2] = 0.0;
+        st.status = 1; st.done = 1; st.change = 0.0;
+        a.state[pair] = st;
+        write_row(a, pair, st);
+        return;
+    }
+    double s, R[9], t[3];
+    double wscale = a.huber ? (mom[MOM_WMAX] + 1e-8) : 1.0; // utils/align.py:194
+    umeyama_from_moments(mom, wscale, a.variant, &s, R, t);
+    double dR = 0, dt = 0;
+    for (int k = 0; k < 9; ++k) dR += (R[k] - st.R[k]) * (R[k] - st.R[k]);
+    for (int k = 0; k < 3; ++k) dt += (t[k] - st.t[k]) * (t[k] - st.t[k]);
+    st.change = fabs(s - st.s) + sqrt(dR) + sqrt(dt);       // utils/align.py:200
+    st.s = s;
+    for (int k = 0; k < 9; ++k) st.R[k] = R[k];
+    for (int k = 0; k < 3; ++k) st.t[k] = t[k];
+    st.iters += 1;
+    st.mean_res = mom[MOM_SR] / n;
+    if (!a.huber || st.change < a.tol || st.iters >= a.max_iterations) st.done = 1;
+    a.state[pair] = st;
+    if (st.done) write_row(a, pair, st);
+    else set_effective(a, pair, st);
+}
+
+// ---------------------------------------------------------------------------------
+// K2 / K3: fused moments (one IRLS iteration, or the single weighted solve)
+// ---------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(PA_THREADS, 2)
+pair_moments_kernel(PairArgs a) {
+    __shared__ FrameConst fc;
+    __shared__ double red[PA_THREADS / 32][MOM_LEN];
+    __shared__ double fmom[MOM_LEN];
+    __shared__ bool is_last;
+    const int pair = blockIdx.y;
+    if (a.state[pair].done) return;                          // block-uniform: converged pairs cost nothing
+    const da3s_pair pr = a.pairs[pair];
+    const int frame = blockIdx.x / a.tiles_per_frame;
+    const int tile = blockIdx.x - frame * a.tiles_per_frame;
+    if (threadIdx.x == 0) load_frame_const(fc, pr, frame, a, pair);
+    __syncthreads();
+
+    double acc[MOM_LEN];
+#pragma unroll
+    for (int k = 0; k < MOM_LEN; ++k) acc[k] = 0.0;
+
+    const size_t foff = (size_t)frame * (size_t)a.P;
+    const float* dA = pr.depth_a + foff; const float* cA = pr.conf_a + foff;
+    const float* dB = pr.depth_b + foff; const float* cB = pr.conf_b + foff;
+    const bool huber = a.huber;
+    const double delta = a.huber_delta;
+
+    auto accumulate = [&](int u, int v, float da, float ca, float db, float cb) {
+        float x[3], y[3], dbs;
+        bool keep = corr_points(fc, a.valid_depth, a.depth_eps, u, v, da, ca, db, cb, x, y, dbs);
+        if (keep && fc.gate_on) {
+            float xs[3], ys[3];
+            ransac_points(fc, a.world, x, y, xs, ys);
+            keep = residual2_f32(fc.gate, xs, ys) < a.gate_thr2;
+        }
+        if (!keep) return;
+        double w = (double)__fsqrt_rn(__fmul_rn(ca, cb));    // utils/align.py:166 in float32
+        const double X0 = x[0], X1 = x[1], X2 = x[2], Y0 = y[0], Y1 = y[1], Y2 = y[2];
+        if (huber) {
+            double r0 = Y0 - (fc.effA[0] * X0 + fc.effA[1] * X1 + fc.effA[2] * X2 + fc.effb[0]);
+            double r1 = Y1 - (fc.effA[3] * X0 + fc.effA[4] * X1 + fc.effA[5] * X2 + fc.effb[1]);
+            double r2 = Y2 - (fc.effA[6] * X0 + fc.effA[7] * X1 + fc.effA[8] * X2 + fc.effb[2]);
+            double r = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+            if (r > delta) w *= delta / r;                   // utils/align.py:94-109, :186-191
+            acc[MOM_SR] += r;
+        }
+        const double wx0 = w * X0, wx1 = w * X1, wx2 = w * X2;
+        const double wy0 = w * Y0, wy1 = w * Y1, wy2 = w * Y2;
+        acc[MOM_S0] += w;
+        acc[MOM_SX] += wx0; acc[MOM_SX + 1] += wx1; acc[MOM_SX + 2] += wx2;
+        acc[MOM_SY] += wy0; acc[MOM_SY + 1] += wy1; acc[MOM_SY + 2] += wy2;
+        acc[MOM_SYX + 0] += wy0 * X0; acc[MOM_SYX + 1] += wy0 * X1; acc[MOM_SYX + 2] += wy0 * X2;
+        acc[MOM_SYX + 3] += wy1 * X0; acc[MOM_SYX + 4] += wy1 * X1; acc[MOM_SYX + 5] += wy1 * X2;
+        acc[MOM_SYX + 6] += wy2 * X0; acc[MOM_SYX + 7] += wy2 * X1; acc[MOM_SYX + 8] += wy2 * X2;
+        acc[MOM_SXX] += wx0 * X0 + wx1 * X1 + wx2 * X2;
+        acc[MOM_WMAX] = fmax(acc[MOM_WMAX], w);
+        acc[MOM_N] += 1.0;
+    };
+
+    if (VEC) {
+        const long long n_groups = a.P >> 2;
+        const long long g_begin = (long long)tile * PA_GROUPS_PER_BLOCK;
+        long long g_end = g_begin + PA_GROUPS_PER_BLOCK;
+        if (g_end > n_groups) g_end = n_groups;
+        const float4* dA4 = reinterpret_cast<const float4*>(dA); const float4* cA4 = reinterpret_cast<const float4*>(cA);
+        const float4* dB4 = reinterpret_cast<const float4*>(dB); const float4* cB4 = reinterpret_cast<const float4*>(cB);
+#pragma unroll 2
+        for (long long g = g_begin + threadIdx.x; g < g_end; g += PA_THREADS) {
+            const float4 da = ldg_stream(dA4 + g), ca = ldg_stream(cA4 + g);
+            const float4 db = ldg_stream(dB4 + g), cb = ldg_stream(cB4 + g);
+            long long pix = g << 2;
+            int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+            accumulate(u, v, da.x, ca.x, db.x, cb.x); if (++u == a.W) { u = 0; ++v; }
+            accumulate(u, v, da.y, ca.y, db.y, cb.y); if (++u == a.W) { u = 0; ++v; }
+            accumulate(u, v, da.z, ca.z, db.z, cb.z); if (++u == a.W) { u = 0; ++v; }
+            accumulate(u, v, da.w, ca.w, db.w, cb.w);
+        }
+    } else {
+        const long long p_begin = (long long)tile * PA_GROUPS_PER_BLOCK * 4;
+        long long p_end = p_begin + (long long)PA_GROUPS_PER_BLOCK * 4;
+        if (p_end > a.P) p_end = a.P;
+        for (long long pix = p_begin + threadIdx.x; pix < p_end; pix += PA_THREADS) {
+            int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+            accumulate(u, v, dA[pix], cA[pix], dB[pix], cB[pix]);
+        }
+    }
+
+    // ---- block reduction: shuffle -> shared -> one partial row, fixed order ----
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < MOM_LEN; ++k) {
+        double v = (k == MOM_WMAX) ? warp_max(acc[k]) : warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    const int n_tiles = a.overlap * a.tiles_per_frame;
+    double* prow = a.partials + ((size_t)pair * n_tiles + blockIdx.x) * MOM_LEN;
+    if (threadIdx.x < MOM_LEN) {
+        double v = red[0][threadIdx.x];
+        for (int w = 1; w < PA_THREADS / 32; ++w)
+            v = (threadIdx.x == MOM_WMAX) ? fmax(v, red[w][threadIdx.x]) : v + red[w][threadIdx.x];
+        prow[threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(&a.tickets[pair], 1u);
+        is_last = (t == (unsigned int)n_tiles - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // ---- last block of the pair: sum partials frame by frame (tile order), to world, solve ----
+    __shared__ double wmom[MOM_LEN];
+    if (threadIdx.x < MOM_LEN) wmom[threadIdx.x] = 0.0;
+    __syncthreads();
+    for (int f = 0; f < a.overlap; ++f) {
+        if (threadIdx.x < MOM_LEN) {
+            const double* src = a.partials + ((size_t)pair * n_tiles + (size_t)f * a.tiles_per_frame) * MOM_LEN + threadIdx.x;
+            double v = 0.0;
+            for (int t = 0; t < a.tiles_per_frame; ++t) {
+                double p = __ldcg(src + (size_t)t * MOM_LEN);
+                v = (threadIdx.x == MOM_WMAX) ? fmax(v, p) : v + p;
+            }
+            fmom[threadIdx.x] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (a.world) {
+                double m[MOM_LEN], acc2[MOM_LEN];
+                for (int k = 0; k < MOM_LEN; ++k) { m[k] = fmom[k]; acc2[k] = wmom[k]; }
+                moments_to_world_add(m, pr.cam_b[f].c2w, pr.cam_a[f].c2w, acc2);
+                for (int k = 0; k < MOM_LEN; ++k) wmom[k] = acc2[k];
+            } else {
+                for (int k = 0; k < MOM_LEN; ++k)
+                    wmom[k] = (k == MOM_WMAX) ? fmax(wmom[k], fmom[k]) : wmom[k] + fmom[k];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double m[MOM_LEN];
+        for (int k = 0; k < MOM_LEN; ++k) m[k] = wmom[k];
+        solve_pair(a, pair, m);
+        a.tickets[pair] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// state initialisation / thresholds
+// ---------------------------------------------------------------------------------
+__global__ void pair_state_init_kernel(PairArgs a) {
+    int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= a.n_pairs) return;
+    PairState st;
+    st.s = 1.0;
+    for (int k = 0; k < 9; ++k) st.R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    st.t[0] = st.t[1] = st.t[2] = 0.0;
+    st.change = 0.0; st.mean_res = 0.0; st.n_valid = 0.0;
+    st.iters = 0; st.done = 0; st.status = 0; st.gate_on = 0;
+    a.state[pair] = st;
+    a.tickets[pair] = 0;
+    set_effective(a, pair, st);
+}
+
+__global__ void make_pair_segs_kernel(const da3s_pair* pairs, int n_pairs, long long M, int depth_mode,
+                                      float conf_th, float eps, da3s_select_seg* segs) {
+    int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    const da3s_pair pr = pairs[pair];
+    da3s_select_seg s;
+    s.b = nullptr; s.ca = nullptr; s.cb = nullptr; s.n = M; s.kind = DA3S_SEL_VALUES; s.stat = DA3S_SEL_MEDIAN;
+    s.percent = 50.0f; s.conf_th = 0.0f; s.eps = 0.0f; s.reserved = 0.0f;
+    s.a = pr.conf_a; segs[3 * pair + 0] = s;
+    s.a = pr.conf_b; segs[3 * pair + 1] = s;
+    // depth-scale median over the single overlap frame prev[-1] / cur[0] (align_geometry.py:319-329):
+    // A's LAST overlap frame and B's FIRST overlap frame
+    s.kind = DA3S_SEL_RATIO;
+    s.n = depth_mode ? M : 0;
+    s.a = pr.depth_a; s.b = pr.depth_b; s.ca = pr.conf_a; s.cb = pr.conf_b; s.conf_th = conf_th; s.eps = eps;
+    segs[3 * pair + 2] = s;
+}
+
+__global__ void pair_prepare_kernel(const da3s_select_out* sel, int n_pairs, int depth_mode, float thr_override,
+                                    float* thr, float* dscale, da3s_pair_aux* aux) {
+    int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    float ma = sel[3 * pair].value, mb = sel[3 * pair + 1].value;
+    // utils/align.py:142: min(median1, median2) * 0.1 in float32 (NumPy >= 2 weak scalar)
+    float t = __fmul_rn(fminf(ma, mb), 0.1f);
+    if (!isnan(thr_override)) t = thr_override;
+    thr[pair] = t;
+    float ds = 1.0f;
+    if (depth_mode) {
+        const da3s_select_out r = sel[3 * pair + 2];
+        ds = r.value;
+        if (depth_mode == 1) {                               // utils/align_geometry_single.py:42-48
+            if (r.n_valid < 50) ds = 1.0f;
+            else if (!is_finite_f(ds) || ds <= 0.0f) ds = 1.0f;
+        }
+    }
+    dscale[pair] = ds;
+    if (aux) {
+        aux[pair].conf_thr = t; aux[pair].depth_scale = ds; aux[pair].median_a = ma; aux[pair].median_b = mb;
+        aux[pair].best_hyp = -1.0; aux[pair].best_count = 0.0; aux[pair].mean_residual = 0.0; aux[pair].last_change = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K4: RANSAC
+// ---------------------------------------------------------------------------------
+struct RansacArgs {
+    const da3s_pair* pairs;
+    int n_pairs, overlap, H, W;
+    long long P;
+    int tiles_per_frame, world, valid_depth, n_hyp, hyp_base;
+    float depth_eps, thr2;
+    const float* thr; const float* dscale;
+    const int32_t* sample_idx;
+    float* hyp_A; float* hyp_t; uint8_t* hyp_ok; double* hyp_sim3;
+    int32_t* counts;
+};
+
+__device__ __forceinline__ void frame_const_basic(FrameConst& fc, const da3s_pair& pr, int frame, const float* thr,
+                                                  const float* dscale, int pair) {
+    const da3s_cam& ca = pr.cam_a[frame];
+    const da3s_cam& cb = pr.cam_b[frame];
+    fc.cuA = ca.cu; fc.cvA = ca.cv; fc.ifuA = ca.inv_fu; fc.ifvA = ca.inv_fv;
+    fc.cuB = cb.cu; fc.cvB = cb.cv; fc.ifuB = cb.inv_fu; fc.ifvB = cb.inv_fv;
+    for (int k = 0; k < 12; ++k) { fc.MfA[k] = (float)ca.c2w[k]; fc.MfB[k] = (float)cb.c2w[k]; }
+    fc.thr = thr[pair];
+    fc.ds = dscale ? dscale[pair] : 1.0f;
+    fc.gate_on = 0;
+}
+
+__global__ void ransac_hyp_kernel(RansacArgs a) {
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    int pair = blockIdx.y;
+    if (h >= a.n_hyp) return;
+    const da3s_pair pr = a.pairs[pair];
+    const int32_t* si = a.sample_idx + ((size_t)pair * a.n_hyp + h) * 3;
+    const long long M = a.P * a.overlap;
+    bool ok = true;
+    double X[3][3], Y[3][3];
+    long long idx[3];
+    for (int j = 0; j < 3; ++j) {
+        idx[j] = si[j];
+        if (idx[j] < 0 || idx[j] >= M) { ok = false; idx[j] = 0; }
+        int frame = (int)(idx[j] / a.P);
+        long long pix = idx[j] - (long long)frame * a.P;
+        int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+        FrameConst fc;
+        frame_const_basic(fc, pr, frame, a.thr, a.dscale, pair);
+        float x[3], y[3], xs[3], ys[3], dbs;
+        bool keep = corr_points(fc, a.valid_depth, a.depth_eps, u, v, pr.depth_a[idx[j]], pr.conf_a[idx[j]],
+                                pr.depth_b[idx[j]], pr.conf_b[idx[j]], x, y, dbs);
+        ok = ok && keep;
+        ransac_points(fc, a.world, x, y, xs, ys);
+        for (int k = 0; k < 3; ++k) { X[j][k] = xs[k]; Y[j][k] = ys[k]; }
+    }
+    if (idx[0] == idx[1] || idx[0] == idx[2] || idx[1] == idx[2]) ok = false;
+    double s = 1.0, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
+    if (ok) {
+        // align_geometry.py:59-82 on three pairs, centred exactly as the reference does
+        double mx[3], my[3];
+        for (int k = 0; k < 3; ++k) { mx[k] = (X[0][k] + X[1][k] + X[2][k]) / 3.0; my[k] = (Y[0][k] + Y[1][k] + Y[2][k]) / 3.0; }
+        double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, var = 0.0;
+        for (int j = 0; j < 3; ++j) {
+            double xc[3], yc[3];
+            for (int k = 0; k < 3; ++k) { xc[k] = X[j][k] - mx[k]; yc[k] = Y[j][k] - my[k]; }
+            for (int i = 0; i < 3; ++i)
+                for (int k = 0; k < 3; ++k) cov[3 * i + k] += yc[i] * xc[k];
+            var += xc[0] * xc[0] + xc[1] * xc[1] + xc[2] * xc[2];
+        }
+        for (int k = 0; k < 9; ++k) cov[k] /= 3.0;
+        var /= 3.0;
+        double U[9], Sg[3], V[9];
+        svd3(cov, U, Sg, V);
+        double dsign = (det3(U) * det3(V) < 0) ? -1.0 : 1.0;
+        double Ud[9];
+        for (int i = 0; i < 3; ++i) { Ud[3 * i] = U[3 * i]; Ud[3 * i + 1] = U[3 * i + 1]; Ud[3 * i + 2] = U[3 * i + 2] * dsign; }
+        mat3_mul_bt(Ud, V, R);
+        s = (Sg[0] + Sg[1] + dsign * Sg[2]) / (var + 1e-12);
+        double Rm[3];
+        mat3_vec(R, mx, Rm);
+        for (int k = 0; k < 3; ++k) t[k] = my[k] - s * Rm[k];
+        bool fin = fabs(s) < INFINITY;
+        for (int k = 0; k < 9; ++k) fin = fin && (fabs(R[k]) < INFINITY);
+        for (int k = 0; k < 3; ++k) fin = fin && (fabs(t[k]) < INFINITY);
+        ok = fin;
+    }
+    size_t o = (size_t)pair * a.n_hyp + h;
+    for (int k = 0; k < 9; ++k) a.hyp_A[o * 9 + k] = ok ? (float)(s * R[k]) : 0.0f;
+    for (int k = 0; k < 3; ++k) a.hyp_t[o * 3 + k] = ok ? (float)t[k] : 0.0f;
+    a.hyp_ok[o] = ok ? 1 : 0;
+    if (a.hyp_sim3) {
+        double* r = a.hyp_sim3 + o * 13;
+        r[0] = ok ? s : 0.0;
+        for (int k = 0; k < 9; ++k) r[1 + k] = ok ? R[k] : 0.0;
+        for (int k = 0; k < 3; ++k) r[10 + k] = ok ? t[k] : 0.0;
+    }
+}
+
+#define RS_THREADS 256
+#define RS_SUB 1024                         // correspondences staged per shared-memory sub-tile
+#define RS_HPT 4                            // hypotheses per thread -> 1024 per launch slice
+
+// Threads own hypotheses (coefficients in registers), points are broadcast from shared
+// memory: the inner loop is 15 FFMA/FADD/FMUL + compare + add per (point, hypothesis), with
+// two LDS.128 per point amortised over RS_HPT hypotheses.
+__global__ void __launch_bounds__(RS_THREADS)
+ransac_score_kernel(RansacArgs a) {
+    __shared__ FrameConst fc;
+    __shared__ float4 pts[RS_SUB][2];       // (x0,x1,x2,y0) (y1,y2,-,-)
+    const int pair = blockIdx.y;
+    const da3s_pair pr = a.pairs[pair];
+    const int frame = blockIdx.x / a.tiles_per_frame;
+    const int tile = blockIdx.x - frame * a.tiles_per_frame;
+    if (threadIdx.x == 0) frame_const_basic(fc, pr, frame, a.thr, a.dscale, pair);
+    __syncthreads();
+
+    float A[RS_HPT][12];
+    int cnt[RS_HPT];
+    bool hok[RS_HPT];
+#pragma unroll
+    for (int m = 0; m < RS_HPT; ++m) {
+        int h = a.hyp_base + m * RS_THREADS + threadIdx.x;
+        cnt[m] = 0;
+        hok[m] = h < a.n_hyp && a.hyp_ok[(size_t)pair * a.n_hyp + h];
+        const float* hA = a.hyp_A + ((size_t)pair * a.n_hyp + (hok[m] ? h : 0)) * 9;
+        const float* ht = a.hyp_t + ((size_t)pair * a.n_hyp + (hok[m] ? h : 0)) * 3;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) A[m][k] = hA[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) A[m][9 + k] = ht[k];
+    }
+
+    const size_t foff = (size_t)frame * (size_t)a.P;
+    const long long p_begin = (long long)tile * PA_GROUPS_PER_BLOCK * 4;
+    long long p_end = p_begin + (long long)PA_GROUPS_PER_BLOCK * 4;
+    if (p_end > a.P) p_end = a.P;
+    const float inf = __int_as_float(0x7f800000);
+    for (long long sb = p_begin; sb < p_end; sb += RS_SUB) {
+        // stage RS_SUB correspondences (4 per thread)
+#pragma unroll
+        for (int j = 0; j < RS_SUB / RS_THREADS; ++j) {
+            int slot = j * RS_THREADS + threadIdx.x;
+            long long pix = sb + slot;
+            float xs[3] = {0, 0, 0}, ys[3] = {inf, inf, inf};
+            if (pix < p_end) {
+                int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+                float x[3], y[3], dbs;
+                bool keep = corr_points(fc, a.valid_depth, a.depth_eps, u, v,
+                                        ldg_stream1(pr.depth_a + foff + pix), ldg_stream1(pr.conf_a + foff + pix),
+                                        ldg_stream1(pr.depth_b + foff + pix), ldg_stream1(pr.conf_b + foff + pix), x, y, dbs);
+                if (keep) ransac_points(fc, a.world, x, y, xs, ys);
+            }
+            pts[slot][0] = make_float4(xs[0], xs[1], xs[2], ys[0]);
+            pts[slot][1] = make_float4(ys[1], ys[2], 0.0f, 0.0f);
+        }
+        __syncthreads();
+        long long rem = p_end - sb;
+        const int n_here = rem < RS_SUB ? (int)rem : RS_SUB;
+#pragma unroll 4
+        for (int i = 0; i < n_here; ++i) {
+            const float4 p0 = pts[i][0], p1 = pts[i][1];
+            const float x[3] = {p0.x, p0.y, p0.z}, y[3] = {p0.w, p1.x, p1.y};
+#pragma unroll
+            for (int m = 0; m < RS_HPT; ++m) cnt[m] += (residual2_f32(A[m], x, y) < a.thr2) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < RS_HPT; ++m) {
+        int h = a.hyp_base + m * RS_THREADS + threadIdx.x;
+        if (hok[m] && cnt[m]) atomicAdd(&a.counts[(size_t)pair * a.n_hyp + h], cnt[m]);
+    }
+}
+
+// winner per pair: max count, ties to the lowest index; fewer than min_inliers -> no model
+__global__ void __launch_bounds__(256)
+ransac_best_kernel(const int32_t* counts, const uint8_t* hyp_ok, const float* hyp_A, const float* hyp_t, int n_hyp,
+                   int min_inliers, PairState* state, float* gate, double* rows, da3s_pair_aux* aux) {
+    __shared__ unsigned long long best[256];
+    const int pair = blockIdx.x;
+    unsigned long long b = 0;
+    for (int h = threadIdx.x; h < n_hyp; h += 256) {
+        size_t o = (size_t)pair * n_hyp + h;
+        if (!hyp_ok[o]) continue;
+        unsigned long long key = ((unsigned long long)(unsigned int)(counts[o] + 1) << 32) | (unsigned int)(0x7fffffff - h);
+        if (key > b) b = key;
+    }
+    best[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s && best[threadIdx.x + s] > best[threadIdx.x]) best[threadIdx.x] = best[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long k = best[0];
+        int cnt = (int)(k >> 32) - 1;
+        int h = k ? (int)(0x7fffffff - (unsigned int)(k & 0xffffffffu)) : -1;
+        PairState st = state[pair];
+        if (h < 0 || cnt < min_inliers) {                    // align_geometry.py:124
+            st.done = 1; st.status = 2; st.gate_on = 0; st.n_valid = 0.0;
+            state[pair] = st;
+            double* r = rows + (size_t)pair * DA3S_ROW_LEN;
+            r[DA3S_ROW_S] = 1.0;
+            for (int q = 0; q < 9; ++q) r[DA3S_ROW_R + q] = (q % 4 == 0) ? 1.0 : 0.0;
+            for (int q = 0; q < 3; ++q) r[DA3S_ROW_T + q] = 0.0;
+            r[DA3S_ROW_NVALID] = 0.0; r[DA3S_ROW_ITERS] = 0.0; r[DA3S_ROW_STATUS] = 2.0;
+            if (aux) { aux[pair].best_hyp = -1.0; aux[pair].best_count = cnt < 0 ? 0.0 : (double)cnt; }
+        } else {
+            st.gate_on = 1;
+            state[pair] = st;
+            size_t o = (size_t)pair * n_hyp + h;
+            for (int q = 0; q < 9; ++q) gate[12 * (size_t)pair + q] = hyp_A[o * 9 + q];
+            for (int q = 0; q < 3; ++q) gate[12 * (size_t)pair + 9 + q] = hyp_t[o * 3 + q];
+            if (aux) { aux[pair].best_hyp = (double)h; aux[pair].best_count = (double)cnt; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ransac_mask_kernel(RansacArgs a, const float* best_A, const float* best_t, const uint8_t* best_ok, uint8_t* mask_out) {
+    __shared__ FrameConst fc;
+    __shared__ float g[12];
+    const int pair = blockIdx.y;
+    const da3s_pair pr = a.pairs[pair];
+    const int frame = blockIdx.x / a.tiles_per_frame;
+    const int tile = blockIdx.x - frame * a.tiles_per_frame;
+    if (threadIdx.x == 0) {
+        frame_const_basic(fc, pr, frame, a.thr, a.dscale, pair);
+        for (int k = 0; k < 9; ++k) g[k] = best_A[9 * (size_t)pair + k];
+        for (int k = 0; k < 3; ++k) g[9 + k] = best_t[3 * (size_t)pair + k];
+    }
+    __syncthreads();
+    const bool ok = best_ok[pair];
+    const size_t foff = (size_t)frame * (size_t)a.P;
+    const long long p_begin = (long long)tile * PA_GROUPS_PER_BLOCK * 4;
+    long long p_end = p_begin + (long long)PA_GROUPS_PER_BLOCK * 4;
+    if (p_end > a.P) p_end = a.P;
+    for (long long pix = p_begin + threadIdx.x; pix < p_end; pix += 256) {
+        int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+        float x[3], y[3], xs[3], ys[3], dbs;
+        bool keep = corr_points(fc, a.valid_depth, a.depth_eps, u, v, pr.depth_a[foff + pix], pr.conf_a[foff + pix],
+                                pr.depth_b[foff + pix], pr.conf_b[foff + pix], x, y, dbs);
+        if (keep && ok) {
+            ransac_points(fc, a.world, x, y, xs, ys);
+            keep = residual2_f32(g, xs, ys) < a.thr2;
+        }
+        mask_out[(size_t)pair * a.P * a.overlap + foff + pix] = (keep && ok) ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host-side orchestration
+// ---------------------------------------------------------------------------------
+static bool pair_geometry(int overlap, int H, int W, long long& P, int& tiles_per_frame) {
+    if (overlap <= 0 || H <= 0 || W <= 0) return false;
+    P = (long long)H * W;
+    long long groups = (P + 3) / 4;
+    tiles_per_frame = (int)((groups + PA_GROUPS_PER_BLOCK - 1) / PA_GROUPS_PER_BLOCK);
+    return (long long)tiles_per_frame * overlap <= 2147483647LL;
+}
+
+extern "C" void da3s_align_opts_default(da3s_align_opts* o) {
+    if (!o) return;
+    o->world = 1; o->depth_scale_mode = 0; o->depth_conf_th = 0.2f; o->depth_eps = 1e-6f; o->valid_depth = 1;
+    o->conf_thr_override = nanf(""); o->huber = 1; o->huber_delta = 1.0; o->max_iterations = 20; o->tol = 1e-6;
+    o->min_points = 100; o->n_hyp = 0; o->ransac_thr = 0.05f; o->ransac_min_inliers = 20;
+}
+
+static int thresholds_impl(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
+                           const da3s_align_opts* opts, float* thr, float* dscale, da3s_pair_aux* aux, cudaStream_t st) {
+    long long P; int tpf;
+    if (!pair_geometry(overlap, H, W, P, tpf)) return DA3S_EINVAL;
+    size_t save_top = ctx->ws_top;
+    WS_ALLOC(ctx, da3s_select_seg, segs, 3 * (size_t)n_pairs);
+    WS_ALLOC(ctx, da3s_select_out, sel, 3 * (size_t)n_pairs);
+    int threads = 128, blocks = (n_pairs + threads - 1) / threads;
+    // the confidence medians run over ALL overlap frames (utils/align.py:136-141); the depth
+    // ratio over ONE frame: A's last overlap frame vs B's first (align_geometry.py:319-320)
+    make_pair_segs_kernel<<<blocks, threads, 0, st>>>(pairs, n_pairs, P * overlap, opts->depth_scale_mode,
+                                                      opts->depth_conf_th, opts->depth_eps, segs);
+    DA3S_LAUNCH_CHECK(ctx);
+    int rc = da3s_select_impl(ctx, segs, 3 * n_pairs, P * overlap, sel, st);
+    if (rc != DA3S_OK) return rc;
+    pair_prepare_kernel<<<blocks, threads, 0, st>>>(sel, n_pairs, opts->depth_scale_mode, opts->conf_thr_override, thr, dscale, aux);
+    DA3S_LAUNCH_CHECK(ctx);
+    ctx->ws_top = save_top;
+    return DA3S_OK;
+}
+
+extern "C" int da3s_pair_thresholds(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
+                                    const da3s_align_opts* opts, float* conf_thr, float* depth_scale,
+                                    da3s_pair_aux* aux, void* stream) {
+    if (!ctx || !pairs || !opts || !conf_thr || !depth_scale || n_pairs <= 0) return DA3S_EINVAL;
+    if (opts->depth_scale_mode && overlap != 1) return DA3S_EINVAL;
+    ws_reset(ctx);
+    return thresholds_impl(ctx, pairs, n_pairs, overlap, H, W, opts, conf_thr, depth_scale, aux, (cudaStream_t)stream);
+}
+
+static void fill_ransac_args(RansacArgs& r, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W, long long P,
+                             int tpf, int world, int valid_depth, float depth_eps, const float* thr, const float* dscale,
+                             int n_hyp, float ransac_thr) {
+    r.pairs = pairs; r.n_pairs = n_pairs; r.overlap = overlap; r.H = H; r.W = W; r.P = P; r.tiles_per_frame = tpf;
+    r.world = world; r.valid_depth = valid_depth; r.n_hyp = n_hyp; r.hyp_base = 0; r.depth_eps = depth_eps;
+    r.thr2 = (float)((double)ransac_thr * (double)ransac_thr);
+    r.thr = thr; r.dscale = dscale; r.sample_idx = nullptr; r.hyp_A = nullptr; r.hyp_t = nullptr; r.hyp_ok = nullptr;
+    r.hyp_sim3 = nullptr; r.counts = nullptr;
+}
+
+extern "C" int da3s_ransac_hypotheses(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
+                                      int world, int valid_depth, float depth_eps, const float* conf_thr, const float* depth_scale,
+                                      const int32_t* sample_idx, int n_hyp, float* hyp_A, float* hyp_t, uint8_t* hyp_ok,
+                                      double* hyp_sim3, void* stream) {
+    if (!ctx || !pairs || !conf_thr || !sample_idx || !hyp_A || !hyp_t || !hyp_ok || n_pairs <= 0 || n_hyp <= 0) return DA3S_EINVAL;
+    if (n_pairs > 65535) return DA3S_EINVAL;
+    long long P; int tpf;
+    if (!pair_geometry(overlap, H, W, P, tpf)) return DA3S_EINVAL;
+    RansacArgs r;
+    fill_ransac_args(r, pairs, n_pairs, overlap, H, W, P, tpf, world, valid_depth, depth_eps, conf_thr, depth_scale, n_hyp, 0.0f);
+    r.sample_idx = sample_idx; r.hyp_A = hyp_A; r.hyp_t = hyp_t; r.hyp_ok = hyp_ok; r.hyp_sim3 = hyp_sim3;
+    dim3 grid((n_hyp + 127) / 128, n_pairs);
+    ransac_hyp_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(r);
+    DA3S_LAUNCH_CHECK(ctx);
+    return DA3S_OK;
+}
+
+extern "C" int da3s_ransac_score(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
+                                 int world, int valid_depth, float depth_eps, const float* conf_thr, const float* depth_scale,
+                                 const float* hyp_A, const float* hyp_t, const uint8_t* hyp_ok, int n_hyp,
+                                 float ransac_thr, int32_t* counts, void* stream) {
+    if (!ctx || !pairs || !conf_thr || !hyp_A || !hyp_t || !hyp_ok || !counts || n_pairs <= 0 || n_hyp <= 0) return DA3S_EINVAL;
+    if (n_pairs > 65535) return DA3S_EINVAL;
+    long long P; int tpf;
+    if (!pair_geometry(overlap, H, W, P, tpf)) return DA3S_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    RansacArgs r;
+    fill_ransac_args(r, pairs, n_pairs, overlap, H, W, P, tpf, world, valid_depth, depth_eps, conf_thr, depth_scale, n_hyp, ransac_thr);
+    r.hyp_A = const_cast<float*>(hyp_A); r.hyp_t = const_cast<float*>(hyp_t); r.hyp_ok = const_cast<uint8_t*>(hyp_ok); r.counts = counts;
+    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_pairs * n_hyp, st));
+    dim3 grid(tpf * overlap, n_pairs);
+    for (int base = 0; base < n_hyp; base += RS_THREADS * RS_HPT) {
+        r.hyp_base = base;
+        ransac_score_kernel<<<grid, RS_THREADS, 0, st>>>(r);
+        DA3S_LAUNCH_CHECK(ctx);
+    }
+    return DA3S_OK;
+}
+
+extern "C" int da3s_ransac_inlier_mask(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
+                                       int world, int valid_depth, float depth_eps, const float* conf_thr, const float* depth_scale,
+                                       const float* best_A, const float* best_t, const uint8_t* best_ok, float ransac_thr,
+                                       uint8_t* mask_out, void* stream) {
+    if (!ctx || !pairs || !conf_thr || !best_A || !best_t || !best_ok || !mask_out || n_pairs <= 0) return DA3S_EINVAL;
+    if (n_pairs > 65535) return DA3S_EINVAL;
+    long long P; int tpf;
+    if (!pair_geometry(overlap, H, W, P, tpf)) return DA3S_EINVAL;
+    RansacArgs r;
+    fill_ransac_args(r, pairs, n_pairs, overlap, H, W, P, tpf, world, valid_depth, depth_eps, conf_thr, depth_scale, 1, ransac_thr);
+    dim3 grid(tpf * overlap, n_pairs);
+    ransac_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r, best_A, best_t, best_ok, mask_out);
+    DA3S_LAUNCH_CHECK(ctx);
+    return DA3S_OK;
+}
+
+extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
+                                const da3s_align_opts* opts, const int32_t* sample_idx, double* sim3_rows,
+                                da3s_pair_aux* aux, int32_t* hyp_counts_out, void* stream) {
+    if (!ctx || !pairs || !opts || !sim3_rows || n_pairs <= 0) return DA3S_EINVAL;
+    if (n_pairs > 65535) return DA3S_EINVAL;
+    if (opts->n_hyp < 0 || (opts->n_hyp > 0 && !sample_idx)) return DA3S_EINVAL;
+    if (opts->max_iterations <= 0 || opts->min_points < 0) return DA3S_EINVAL;
+    if (opts->depth_scale_mode < 0 || opts->depth_scale_mode > 2) return DA3S_EINVAL;
+    if (opts->depth_scale_mode && overlap != 1) return DA3S_EINVAL;
+    long long P; int tpf;
+    if (!pair_geometry(overlap, H, W, P, tpf)) return DA3S_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    ws_reset(ctx);
+    const int n_tiles = tpf * overlap;
+    WS_ALLOC(ctx, float, thr, n_pairs);
+    WS_ALLOC(ctx, float, dscale, n_pairs);
+    WS_ALLOC(ctx, PairState, state, n_pairs);
+    WS_ALLOC(ctx, double, eff, (size_t)n_pairs * overlap * 12);
+    WS_ALLOC(ctx, float, gate, (size_t)n_pairs * 12);
+    WS_ALLOC(ctx, double, partials, (size_t)n_pairs * n_tiles * MOM_LEN);
+    WS_ALLOC(ctx, unsigned int, tickets, n_pairs);
+
+    int rc = thresholds_impl(ctx, pairs, n_pairs, overlap, H, W, opts, thr, dscale, aux, st);
+    if (rc != DA3S_OK) return rc;
+
+    PairArgs a;
+    a.pairs = pairs; a.n_pairs = n_pairs; a.overlap = overlap; a.H = H; a.W = W; a.P = P; a.tiles_per_frame = tpf;
+    a.world = opts->world; a.valid_depth = opts->valid_depth; a.huber = opts->huber; a.variant = SOLVE_WEIGHTED;
+    a.depth_eps = opts->depth_eps; a.thr = thr; a.dscale = dscale; a.state = state; a.eff = eff;
+    a.gate = opts->n_hyp > 0 ? gate : nullptr;
+    a.gate_thr2 = (float)((double)opts->ransac_thr * (double)opts->ransac_thr);
+    a.partials = partials; a.tickets = tickets; a.huber_delta = opts->huber_delta; a.tol = opts->tol;
+    a.max_iterations = opts->max_iterations; a.min_points = opts->min_points; a.rows = sim3_rows; a.aux = aux;
+
+    int threads = 128, blocks = (n_pairs + threads - 1) / threads;
+    pair_state_init_kernel<<<blocks, threads, 0, st>>>(a);
+    DA3S_LAUNCH_CHECK(ctx);
+
+    if (opts->n_hyp > 0) {
+        const int nh = opts->n_hyp;
+        WS_ALLOC(ctx, float, hyp_A, (size_t)n_pairs * nh * 9);
+        WS_ALLOC(ctx, float, hyp_t, (size_t)n_pairs * nh * 3);
+        WS_ALLOC(ctx, uint8_t, hyp_ok, (size_t)n_pairs * nh);
+        int32_t* counts = hyp_counts_out;
+        if (!counts) { WS_ALLOC(ctx, int32_t, c2, (size_t)n_pairs * nh); counts = c2; }
+        rc = da3s_ransac_hypotheses(ctx, pairs, n_pairs, overlap, H, W, opts->world, opts->valid_depth, opts->depth_eps,
+                                    thr, dscale, sample_idx, nh, hyp_A, hyp_t, hyp_ok, nullptr, stream);
+        if (rc != DA3S_OK) return rc;
+        rc = da3s_ransac_score(ctx, pairs, n_pairs, overlap, H, W, opts->world, opts->valid_depth, opts->depth_eps,
+                               thr, dscale, hyp_A, hyp_t, hyp_ok, nh, opts->ransac_thr, counts, stream);
+        if (rc != DA3S_OK) return rc;
+        ransac_best_kernel<<<n_pairs, 256, 0, st>>>(counts, hyp_ok, hyp_A, hyp_t, nh, opts->ransac_min_inliers, state, gate,
+                                                    sim3_rows, aux);
+        DA3S_LAUNCH_CHECK(ctx);
+    }
+
+    const bool vec = (P % 4 == 0);          // per-pair pointer alignment is the caller's contract (EALIGN documented)
+    dim3 grid(n_tiles, n_pairs);
+    const int iters = opts->huber ? opts->max_iterations : 1;
+    for (int it = 0; it < iters; ++it) {
+        if (vec) pair_moments_kernel<true><<<grid, PA_THREADS, 0, st>>>(a);
+        else     pair_moments_kernel<false><<<grid, PA_THREADS, 0, st>>>(a);
+        DA3S_LAUNCH_CHECK(ctx);
+    }
+    return DA3S_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Umeyama / IRLS on MATERIALISED correspondences (the reference's array-level API:
+// utils/align.py:14-40, :111-218, :224-276; align_geometry.py:59-82).  Same reduction and
+// solve as above with one "pair", camera mode, and optional gather lists.
+// Algorithmic bytes: 12+12+4 = 28 B per point pair (float32), 56 B (float64).
+// ---------------------------------------------------------------------------------
+#define PT_THREADS 256
+#define PT_PER_BLOCK 4096
+
+struct PointsArgs {
+    const void* src; const void* dst;
+    const void* weights; int weights_f64;
+    const float* conf_src; const float* conf_dst;
+    long long n; const long long* idx_src; const long long* idx_dst; long long count;
+    int irls;
+    double* norm_state;                     // [8]: mx[3], my[3], n, unused  (NORMRATIO)
+    PairArgs pa;
+};
+
+template <typename T>
+__device__ __forceinline__ void load_pt(const void* base, long long i, double* p) {
+    const T* q = (const T*)base + 3 * i;
+    p[0] = (double)q[0]; p[1] = (double)q[1]; p[2] = (double)q[2];
+}
+
+template <typename T, int STAGE>            // STAGE 0: moments (+solve); 1: centred norm sums (NORMRATIO pass 2)
+__global__ void __launch_bounds__(PT_THREADS)
+points_moments_kernel(PointsArgs a) {
+    __shared__ double red[PT_THREADS / 32][MOM_LEN];
+    __shared__ bool is_last;
+    __shared__ double eff[12];
+    __shared__ double cen[6];
+    PairArgs& pa = a.pa;
+    if (STAGE == 0 && pa.state[0].done) return;
+    if (threadIdx.x < 12 && pa.eff) eff[threadIdx.x] = pa.eff[threadIdx.x];
+    if (STAGE == 1 && threadIdx.x < 6) cen[threadIdx.x] = a.norm_state[threadIdx.x];
+    __syncthreads();
+    double acc[MOM_LEN];
+#pragma unroll
+    for (int k = 0; k < MOM_LEN; ++k) acc[k] = 0.0;
+    const long long begin = (long long)blockIdx.x * PT_PER_BLOCK;
+    long long end = begin + PT_PER_BLOCK;
+    if (end > a.count) end = a.count;
+    for (long long i = begin + threadIdx.x; i < end; i += PT_THREADS) {
+        const long long is = a.idx_src ? a.idx_src[i] : i;
+        const long long id = a.idx_dst ? a.idx_dst[i] : i;
+        double X[3], Y[3];
+        load_pt<T>(a.src, is, X);
+        load_pt<T>(a.dst, id, Y);
+        if (STAGE == 1) {
+            double dx0 = X[0] - cen[0], dx1 = X[1] - cen[1], dx2 = X[2] - cen[2];
+            double dy0 = Y[0] - cen[3], dy1 = Y[1] - cen[4], dy2 = Y[2] - cen[5];
+            acc[0] += sqrt(dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+            acc[1] += sqrt(dy0 * dy0 + dy1 * dy1 + dy2 * dy2);
+            continue;
+        }
+        double w = 1.0;
+        if (a.weights) w = a.weights_f64 ? ((const double*)a.weights)[i] : (double)((const float*)a.weights)[i];
+        if (a.irls) {
+            w = (double)__fsqrt_rn(__fmul_rn(a.conf_dst[id], a.conf_src[is]));       // utils/align.py:166
+            double r0 = Y[0] - (eff[0] * X[0] + eff[1] * X[1] + eff[2] * X[2] + eff[9]);
+            double r1 = Y[1] - (eff[3] * X[0] + eff[4] * X[1] + eff[5] * X[2] + eff[10]);
+            double r2 = Y[2] - (eff[6] * X[0] + eff[7] * X[1] + eff[8] * X[2] + eff[11]);
+            double r = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+            if (r > pa.huber_delta) w *= pa.huber_delta / r;
+            acc[MOM_SR] += r;
+        }
+        const double wx0 = w * X[0], wx1 = w * X[1], wx2 = w * X[2];
+        const double wy0 = w * Y[0], wy1 = w * Y[1], wy2 = w * Y[2];
+        acc[MOM_S0] += w;
+        acc[MOM_SX] += wx0; acc[MOM_SX + 1] += wx1; acc[MOM_SX + 2] += wx2;
+        acc[MOM_SY] += wy0; acc[MOM_SY + 1] += wy1; acc[MOM_SY + 2] += wy2;
+        acc[MOM_SYX + 0] += wy0 * X[0]; acc[MOM_SYX + 1] += wy0 * X[1]; acc[MOM_SYX + 2] += wy0 * X[2];
+        acc[MOM_SYX + 3] += wy1 * X[0]; acc[MOM_SYX + 4] += wy1 * X[1]; acc[MOM_SYX + 5] += wy1 * X[2];
+        acc[MOM_SYX + 6] += wy2 * X[0]; acc[MOM_SYX + 7] += wy2 * X[1]; acc[MOM_SYX + 8] += wy2 * X[2];
+        acc[MOM_SXX] += wx0 * X[0] + wx1 * X[1] + wx2 * X[2];
+        acc[MOM_WMAX] = fmax(acc[MOM_WMAX], w);
+        acc[MOM_N] += 1.0;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < MOM_LEN; ++k) {
+        double v = (k == MOM_WMAX) ? warp_max(acc[k]) : warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    double* prow = pa.partials + (size_t)blockIdx.x * MOM_LEN;
+    if (threadIdx.x < MOM_LEN) {
+        double v = red[0][threadIdx.x];
+        for (int w = 1; w < PT_THREADS / 32; ++w)
+            v = (threadIdx.x == MOM_WMAX) ? fmax(v, red[w][threadIdx.x]) : v + red[w][threadIdx.x];
+        prow[threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(&pa.tickets[0], 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    __shared__ double tot[MOM_LEN];
+    if (threadIdx.x < MOM_LEN) {
+        double v = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) {
+            double p = __ldcg(pa.partials + (size_t)b * MOM_LEN + threadIdx.x);
+            v = (threadIdx.x == MOM_WMAX) ? fmax(v, p) : v + p;
+        }
+        tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    pa.tickets[0] = 0;
+    double m[MOM_LEN];
+    for (int k = 0; k < MOM_LEN; ++k) m[k] = tot[k];
+    if (STAGE == 1) {
+        // utils/align.py:250-276: s = sum|y-cy| / sum|x-cx|; Kabsch on H = s Xc^T Yc; R = V S U^T
+        PairState st = pa.state[0];
+        const double* ns = a.norm_state;
+        double mx[3] = {ns[0], ns[1], ns[2]}, my[3] = {ns[3], ns[4], ns[5]};
+        double s = m[0] > 0 ? m[1] / m[0] : 1.0;
+        double Hm[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Hm[3 * i + j] = s * ns[8 + 3 * j + i];          // (C^T)[i][j], C = centred sum y x^T
+        double U[9], Sg[3], V[9], VUt[9];
+        svd3(Hm, U, Sg, V);
+        mat3_mul_bt(V, U, VUt);
+        double dsign = det3(VUt) < 0 ? -1.0 : 1.0;
+        double Vd[9];
+        for (int i = 0; i < 3; ++i) { Vd[3 * i] = V[3 * i]; Vd[3 * i + 1] = V[3 * i + 1]; Vd[3 * i + 2] = V[3 * i + 2] * dsign; }
+        mat3_mul_bt(Vd, U, st.R);
+        double Rm[3];
+        mat3_vec(st.R, mx, Rm);
+        for (int k = 0; k < 3; ++k) st.t[k] = my[k] - s * Rm[k];
+        st.s = s; st.iters = 1; st.done = 1; st.n_valid = ns[6];
+        pa.state[0] = st;
+        write_row(pa, 0, st);
+        return;
+    }
+    if (a.norm_state) {
+        // NORMRATIO pass 1: centroids (utils/align.py:242-243) and the centred cross sums
+        double n = m[MOM_N];
+        double* ns = a.norm_state;
+        for (int k = 0; k < 3; ++k) { ns[k] = m[MOM_SX + k] / n; ns[3 + k] = m[MOM_SY + k] / n; }
+        ns[6] = n; ns[7] = 0.0;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) ns[8 + 3 * i + j] = m[MOM_SYX + 3 * i + j] - n * ns[3 + i] * ns[j];
+        return;
+    }
+    solve_pair(pa, 0, m);
+}
+
+static int points_common(da3s_ctx* ctx, PointsArgs& a, long long count, int huber, int variant, double delta,
+                         int max_it, double tol, int min_points, double* row) {
+    WS_ALLOC(ctx, PairState, state, 1);
+    WS_ALLOC(ctx, double, eff, 12);
+    WS_ALLOC(ctx, unsigned int, tickets, 1);
+    long long nb = (count + PT_PER_BLOCK - 1) / PT_PER_BLOCK;
+    if (nb < 1) nb = 1;
+    if (nb > 2147483647LL) return DA3S_EINVAL;
+    WS_ALLOC(ctx, double, partials, (size_t)nb * MOM_LEN);
+    PairArgs& pa = a.pa;
+    pa.pairs = nullptr; pa.n_pairs = 1; pa.overlap = 1; pa.H = 1; pa.W = 1; pa.P = 1; pa.tiles_per_frame = (int)nb;
+    pa.world = 0; pa.valid_depth = 0; pa.huber = huber; pa.variant = variant; pa.depth_eps = 0; pa.thr = nullptr;
+    pa.dscale = nullptr; pa.state = state; pa.eff = eff; pa.gate = nullptr; pa.gate_thr2 = 0; pa.partials = partials;
+    pa.tickets = tickets; pa.huber_delta = delta; pa.tol = tol; pa.max_iterations = max_it; pa.min_points = min_points;
+    pa.rows = row; pa.aux = nullptr;
+    a.count = count;
+    return (int)nb;
+}
+
+extern "C" int da3s_umeyama_points(da3s_ctx* ctx, const void* src, const void* dst, int points_f64,
+                                   const void* weights, int weights_f64, long long n,
+                                   const long long* idx_src, const long long* idx_dst, long long n_idx,
+                                   int variant, double* sim3_row, void* stream) {
+    if (!ctx || !src || !dst || !sim3_row || n <= 0) return DA3S_EINVAL;
+    if ((idx_src == nullptr) != (idx_dst == nullptr)) return DA3S_EINVAL;
+    if (variant < 0 || variant > 2) return DA3S_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    ws_reset(ctx);
+    PointsArgs a;
+    a.src = src; a.dst = dst; a.weights = (variant == DA3S_UMEYAMA_WEIGHTED) ? weights : nullptr; a.weights_f64 = weights_f64;
+    a.conf_src = nullptr; a.conf_dst = nullptr; a.n = n; a.idx_src = idx_src; a.idx_dst = idx_dst; a.irls = 0;
+    a.norm_state = nullptr;
+    long long count = idx_src ? n_idx : n;
+    if (count <= 0) return DA3S_EINVAL;
+    int nb = points_common(ctx, a, count, 0, variant == DA3S_UMEYAMA_WEIGHTED ? SOLVE_WEIGHTED : SOLVE_MEAN, 1.0, 1, 0.0, 0, sim3_row);
+    if (nb < 0) return nb;
+    pair_state_init_kernel<<<1, 32, 0, st>>>(a.pa);
+    DA3S_LAUNCH_CHECK(ctx);
+    if (variant == DA3S_UMEYAMA_NORMRATIO) {
+        WS_ALLOC(ctx, double, ns, 17);
+        a.norm_state = ns;
+        if (points_f64) points_moments_kernel<double, 0><<<nb, PT_THREADS, 0, st>>>(a);
+        else            points_moments_kernel<float, 0><<<nb, PT_THREADS, 0, st>>>(a);
+        DA3S_LAUNCH_CHECK(ctx);
+        if (points_f64) points_moments_kernel<double, 1><<<nb, PT_THREADS, 0, st>>>(a);
+        else            points_moments_kernel<float, 1><<<nb, PT_THREADS, 0, st>>>(a);
+        DA3S_LAUNCH_CHECK(ctx);
+        return DA3S_OK;
+    }
+    if (points_f64) points_moments_kernel<double, 0><<<nb, PT_THREADS, 0, st>>>(a);
+    else            points_moments_kernel<float, 0><<<nb, PT_THREADS, 0, st>>>(a);
+    DA3S_LAUNCH_CHECK(ctx);
+    return DA3S_OK;
+}
+
+extern "C" int da3s_irls_points(da3s_ctx* ctx, const void* src, const void* dst, int points_f64,
+                                const float* conf_src, const float* conf_dst, long long n,
+                                const long long* idx_src, const long long* idx_dst, long long n_idx,
+                                double huber_delta, int max_iterations, double tol, double* sim3_row, void* stream) {
+    if (!ctx || !src || !dst || !conf_src || !conf_dst || !sim3_row || n <= 0 || max_iterations <= 0) return DA3S_EINVAL;
+    if ((idx_src == nullptr) != (idx_dst == nullptr)) return DA3S_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    ws_reset(ctx);
+    PointsArgs a;
+    a.src = src; a.dst = dst; a.weights = nullptr; a.weights_f64 = 0; a.conf_src = conf_src; a.conf_dst = conf_dst;
+    a.n = n; a.idx_src = idx_src; a.idx_dst = idx_dst; a.irls = 1; a.norm_state = nullptr;
+    long long count = idx_src ? n_idx : n;
+    if (count <= 0) return DA3S_EINVAL;
+    int nb = points_common(ctx, a, count, 1, SOLVE_WEIGHTED, huber_delta, max_iterations, tol, 0, sim3_row);
+    if (nb < 0) return nb;
+    pair_state_init_kernel<<<1, 32, 0, st>>>(a.pa);
+    DA3S_LAUNCH_CHECK(ctx);
+    for (int it = 0; it < max_iterations; ++it) {
+        if (points_f64) points_moments_kernel<double, 0><<<nb, PT_THREADS, 0, st>>>(a);
+        else            points_moments_kernel<float, 0><<<nb, PT_THREADS, 0, st>>>(a);
+        DA3S_LAUNCH_CHECK(ctx);
+    }
+    return DA3S_OK;
+}

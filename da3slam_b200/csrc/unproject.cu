@@ -1,0 +1,390 @@
+// unproject.cu — camera table, K1 (depth -> xyz fused with filtering and an optional
+// Sim(3)), K5 (apply Sim(3)).  HBM-bound streaming kernels: 128-bit coalesced loads,
+// xyz staged through shared memory so that every store instruction of a warp writes
+// 512 contiguous bytes, grid = (tiles per frame, frames).
+//
+// Algorithmic bytes: K1 = 4 (depth) + 4 (conf) read + 12 (xyz f32) + 1 (mask) write
+// = 21 B / pixel; K5 = 12 + 12 = 24 B / point.
+#include "common.cuh"
+#include "sim3_math.cuh"
+
+// ---------------------------------------------------------------------------------
+// camera table
+// ---------------------------------------------------------------------------------
+__global__ void build_cams_kernel(const float* __restrict__ K9, const float* __restrict__ E12, int n,
+                                  int inverse_mode, da3s_cam* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* K = K9 + 9 * (size_t)i;
+    const float* E = E12 + 12 * (size_t)i;
+    da3s_cam c;
+    c.fu = K[0]; c.fv = K[4]; c.cu = K[2]; c.cv = K[5];
+    c.inv_fu = __fdiv_rn(1.0f, c.fu);
+    c.inv_fv = __fdiv_rn(1.0f, c.fv);
+    c.skew_flag = (K[1] != 0.0f || K[3] != 0.0f) ? 1.0f : 0.0f;
+    c.reserved = 0.0f;
+    double Kd[9], Ki[9];
+    for (int k = 0; k < 9; ++k) Kd[k] = (double)K[k];
+    if (!mat3_inv(Kd, Ki))
+        for (int k = 0; k < 9; ++k) Ki[k] = nan("");
+    for (int k = 0; k < 9; ++k) c.kinv[k] = Ki[k];
+    double R[9], t[3], Rinv[9];
+    for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) R[3 * r + k] = (double)E[4 * r + k];
+        t[r] = (double)E[4 * r + 3];
+    }
+    if (inverse_mode == DA3S_CAM_GENERAL_INV) {
+        if (!mat3_inv(R, Rinv))
+            for (int k = 0; k < 9; ++k) Rinv[k] = nan("");
+    } else {
+        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < 3; ++k) Rinv[3 * r + k] = R[3 * k + r];
+    }
+    double ti[3];
+    mat3_vec(Rinv, t, ti);
+    for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) c.c2w[4 * r + k] = Rinv[3 * r + k];
+        c.c2w[4 * r + 3] = -ti[r];
+    }
+    out[i] = c;
+}
+
+extern "C" int da3s_build_cams(da3s_ctx* ctx, const float* K9, const float* E12, int n_frames, int inverse_mode,
+                               da3s_cam* cams_out, void* stream) {
+    if (!ctx || !K9 || !E12 || !cams_out || n_frames <= 0) return DA3S_EINVAL;
+    if (inverse_mode != DA3S_CAM_CLOSED_FORM && inverse_mode != DA3S_CAM_GENERAL_INV) return DA3S_EINVAL;
+    int threads = 128;
+    build_cams_kernel<<<(n_frames + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+        K9, E12, n_frames, inverse_mode, cams_out);
+    DA3S_LAUNCH_CHECK(ctx);
+    return DA3S_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------
+struct UnprojFrame {            // per-frame constants, staged in shared memory
+    double fu, fv, cu, cv;      // closed form
+    double kinv[9];             // general
+    double M[9], m[3];          // output transform: identity, c2w, or sim3 o c2w
+    float cuf, cvf, ifu, ifv;   // fast float32 path
+    float Mf[9], mf[3];
+};
+
+template <int MODE>             // DA3S_UNPROJ_CLOSED / KINV / FAST
+__device__ __forceinline__ void unproject_pixel(const UnprojFrame& f, int u, int v, float d, bool xform,
+                                                double& X, double& Y, double& Z) {
+    if (MODE == DA3S_UNPROJ_FAST) {
+        float x, y;
+        cam_fast((float)u, (float)v, d, f.cuf, f.cvf, f.ifu, f.ifv, x, y);
+        if (xform) {
+            X = (double)fmaf(f.Mf[0], x, fmaf(f.Mf[1], y, fmaf(f.Mf[2], d, f.mf[0])));
+            Y = (double)fmaf(f.Mf[3], x, fmaf(f.Mf[4], y, fmaf(f.Mf[5], d, f.mf[1])));
+            Z = (double)fmaf(f.Mf[6], x, fmaf(f.Mf[7], y, fmaf(f.Mf[8], d, f.mf[2])));
+        } else {
+            X = x; Y = y; Z = d;
+        }
+        return;
+    }
+    double x, y, z;
+    if (MODE == DA3S_UNPROJ_CLOSED) {
+        // src/vggt/utils/geometry.py:109-114: float64 sub, mul, div (each rounded once), then float32
+        double dd = (double)d;
+        x = (double)__double2float_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)u, f.cu), dd), f.fu));
+        y = (double)__double2float_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)v, f.cv), dd), f.fv));
+        z = dd;
+    } else {
+        // utils/geometry.py:26-28: K^-1 [u, v, 1] then * depth, float64 throughout
+        double uu = (double)u, vv = (double)v, dd = (double)d;
+        x = (f.kinv[0] * uu + f.kinv[1] * vv + f.kinv[2]) * dd;
+        y = (f.kinv[3] * uu + f.kinv[4] * vv + f.kinv[5]) * dd;
+        z = (f.kinv[6] * uu + f.kinv[7] * vv + f.kinv[8]) * dd;
+    }
+    if (xform) {
+        X = f.M[0] * x + f.M[1] * y + f.M[2] * z + f.m[0];
+        Y = f.M[3] * x + f.M[4] * y + f.M[5] * z + f.m[1];
+        Z = f.M[6] * x + f.M[7] * y + f.M[8] * z + f.m[2];
+    } else {
+        X = x; Y = y; Z = z;
+    }
+}
+
+#define K1_THREADS 256
+#define K1_PIX_PER_THREAD 4
+
+struct K1Args {
+    const float* depth; const float* conf; const da3s_cam* cams;
+    int H, W; long long P;      // P = H*W
+    int flags;
+    float conf_thr; const float* conf_thr_dev; float conf_floor; float depth_eps;
+    const double* sim3;
+    void* xyz; uint8_t* mask; unsigned long long* n_kept;
+    int groups_per_block;       // float4 groups handled by one block (multiple of K1_THREADS)
+};
+
+template <int MODE, typename OutT, bool VEC>
+__global__ void __launch_bounds__(K1_THREADS)
+unproject_filter_kernel(K1Args a) {
+    __shared__ UnprojFrame fr;
+    __shared__ float stage[VEC ? (K1_THREADS / 32) * 32 * 12 : 1];     // per-warp staging for f32 xyz
+    __shared__ unsigned int blk_kept;
+    const int frame = blockIdx.y;
+    const bool world = a.flags & DA3S_UNPROJ_WORLD;
+    const bool xform = world || a.sim3 != nullptr;
+    if (threadIdx.x == 0) {
+        const da3s_cam& c = a.cams[frame];
+        fr.fu = c.fu; fr.fv = c.fv; fr.cu = c.cu; fr.cv = c.cv;
+        for (int k = 0; k < 9; ++k) fr.kinv[k] = c.kinv[k];
+        fr.cuf = c.cu; fr.cvf = c.cv; fr.ifu = c.inv_fu; fr.ifv = c.inv_fv;
+        double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, m[3] = {0, 0, 0};
+        if (world) {
+            for (int r = 0; r < 3; ++r) {
+                for (int k = 0; k < 3; ++k) M[3 * r + k] = c.c2w[4 * r + k];
+                m[r] = c.c2w[4 * r + 3];
+            }
+        }
+        if (a.sim3) {
+            const double* s3 = a.sim3 + ((a.flags & DA3S_SIM3_PER_FRAME) ? 13 * (size_t)frame : 0);
+            double s = s3[0];
+            double sR[9], M2[9], m2[3];
+            for (int k = 0; k < 9; ++k) sR[k] = s * s3[1 + k];
+            mat3_mul(sR, M, M2);
+            mat3_vec(sR, m, m2);
+            for (int k = 0; k < 9; ++k) M[k] = M2[k];
+            for (int k = 0; k < 3; ++k) m[k] = m2[k] + s3[10 + k];
+        }
+        for (int k = 0; k < 9; ++k) { fr.M[k] = M[k]; fr.Mf[k] = (float)M[k]; }
+        for (int k = 0; k < 3; ++k) { fr.m[k] = m[k]; fr.mf[k] = (float)m[k]; }
+        blk_kept = 0;
+    }
+    __syncthreads();
+
+    const float thr = a.conf_thr_dev ? *a.conf_thr_dev : a.conf_thr;
+    const size_t frame_off = (size_t)frame * (size_t)a.P;
+    const float* depth = a.depth + frame_off;
+    const float* conf = a.conf ? a.conf + frame_off : nullptr;
+    unsigned int kept = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    auto keep_of = [&](float d, float c, double X, double Y, double Z) -> bool {
+        bool k = true;
+        if (conf) {
+            if (a.flags & DA3S_MASK_CONF_GT) k = k && (c > thr);
+            if (a.flags & DA3S_MASK_CONF_GE) k = k && (c >= thr);
+            if (a.flags & DA3S_MASK_CONF_FLOOR) k = k && (c > a.conf_floor);
+        }
+        if (a.flags & DA3S_MASK_DEPTH) k = k && (d > a.depth_eps) && is_finite_f(d);
+        if (a.flags & DA3S_MASK_WORLD_Z)
+            k = k && (Z > 0.1) && (Z < 50.0) && (fabs(X) < INFINITY) && (fabs(Y) < INFINITY) && (fabs(Z) < INFINITY);
+        return k;
+    };
+
+    if (VEC) {
+        const long long n_groups = a.P >> 2;
+        const long long g_begin = (long long)blockIdx.x * a.groups_per_block;
+        long long g_end = g_begin + a.groups_per_block;
+        if (g_end > n_groups) g_end = n_groups;
+        const float4* d4 = reinterpret_cast<const float4*>(depth);
+        const float4* c4 = reinterpret_cast<const float4*>(conf);
+        for (long long gb = g_begin; gb < g_end; gb += K1_THREADS) {      // block-uniform loop
+            const long long g = gb + threadIdx.x;
+            const bool active = g < g_end;
+            float dv[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0};
+            if (active) {
+                float4 t = ldg_stream(d4 + g);
+                dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w;
+                if (conf) { float4 q = ldg_stream(c4 + g); cv[0] = q.x; cv[1] = q.y; cv[2] = q.z; cv[3] = q.w; }
+            }
+            long long pix = g << 2;
+            int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+            unsigned int mbits = 0;
+            OutT o[12];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double X, Y, Z;
+                unproject_pixel<MODE>(fr, u, v, dv[j], xform, X, Y, Z);
+                o[3 * j] = (OutT)X; o[3 * j + 1] = (OutT)Y; o[3 * j + 2] = (OutT)Z;
+                if (active && keep_of(dv[j], cv[j], X, Y, Z)) mbits |= (1u << (8 * j));
+                if (++u == a.W) { u = 0; ++v; }
+            }
+            kept += __popc(mbits);
+            if (a.mask && active) reinterpret_cast<unsigned int*>(a.mask + frame_off)[g] = mbits;
+            if (sizeof(OutT) == 4) {
+                // stage this warp's 32 x 12 floats, then store 3 x 512 contiguous bytes per warp
+                float* ws = stage + warp * (32 * 12);
+                float4* ws4 = reinterpret_cast<float4*>(ws);
+                ws4[lane * 3 + 0] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+                ws4[lane * 3 + 1] = make_float4((float)o[4], (float)o[5], (float)o[6], (float)o[7]);
+                ws4[lane * 3 + 2] = make_float4((float)o[8], (float)o[9], (float)o[10], (float)o[11]);
+                __syncwarp();
+                const long long warp_g0 = gb + warp * 32;                  // first group of this warp
+                float4* out4 = reinterpret_cast<float4*>((float*)a.xyz + frame_off * 3) + warp_g0 * 3;
+                long long warp_groups = g_end - warp_g0;                   // groups this warp really owns
+                if (warp_groups > 32) warp_groups = 32;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    int idx = j * 32 + lane;
+                    if (idx < warp_groups * 3) stg_stream(out4 + idx, ws4[idx]);
+                }
+                __syncwarp();
+            } else if (active) {
+                double* out = (double*)a.xyz + (frame_off + (size_t)pix) * 3;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) out[j] = (double)o[j];
+            }
+        }
+    } else {
+        const long long p_begin = (long long)blockIdx.x * a.groups_per_block * 4;
+        long long p_end = p_begin + (long long)a.groups_per_block * 4;
+        if (p_end > a.P) p_end = a.P;
+        for (long long pix = p_begin + threadIdx.x; pix < p_end; pix += K1_THREADS) {
+            float d = depth[pix], c = conf ? conf[pix] : 0.0f;
+            int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+            double X, Y, Z;
+            unproject_pixel<MODE>(fr, u, v, d, xform, X, Y, Z);
+            bool k = keep_of(d, c, X, Y, Z);
+            kept += k;
+            if (a.mask) a.mask[frame_off + pix] = k ? 1 : 0;
+            OutT* out = (OutT*)a.xyz + (frame_off + (size_t)pix) * 3;
+            out[0] = (OutT)X; out[1] = (OutT)Y; out[2] = (OutT)Z;
+        }
+    }
+    if (a.n_kept) {
+        unsigned int wk = __reduce_add_sync(0xffffffffu, kept);
+        if (lane == 0 && wk) atomicAdd(&blk_kept, wk);
+        __syncthreads();
+        if (threadIdx.x == 0 && blk_kept) atomicAdd(a.n_kept, (unsigned long long)blk_kept);
+    }
+}
+
+template <int MODE, typename OutT>
+static int launch_k1(da3s_ctx* ctx, const K1Args& a0, int n_frames, bool vec, cudaStream_t st) {
+    K1Args a = a0;
+    // tile: 8192 pixels per block (2048 float4 groups = 8 iterations of 256 threads)
+    a.groups_per_block = 2048;
+    long long groups = (a.P + 3) / 4;
+    int tiles = (int)((groups + a.groups_per_block - 1) / a.groups_per_block);
+    dim3 grid(tiles, n_frames);
+    if (vec) unproject_filter_kernel<MODE, OutT, true><<<grid, K1_THREADS, 0, st>>>(a);
+    else     unproject_filter_kernel<MODE, OutT, false><<<grid, K1_THREADS, 0, st>>>(a);
+    DA3S_LAUNCH_CHECK(ctx);
+    return DA3S_OK;
+}
+
+extern "C" int da3s_unproject_filter(da3s_ctx* ctx, const float* depth, const float* conf, const da3s_cam* cams,
+                                     int n_frames, int H, int W, int flags,
+                                     float conf_thr, const float* conf_thr_dev, float conf_floor, float depth_eps,
+                                     const double* sim3, void* xyz_out, uint8_t* mask_out,
+                                     unsigned long long* n_kept, void* stream) {
+    if (!ctx || !depth || !cams || !xyz_out || n_frames <= 0 || H <= 0 || W <= 0) return DA3S_EINVAL;
+    if ((flags & DA3S_MASK_CONF_GT) && (flags & DA3S_MASK_CONF_GE)) return DA3S_EINVAL;
+    int mode = flags & DA3S_UNPROJ_MODEMASK;
+    if (mode == 3) return DA3S_EINVAL;
+    if (n_frames > 65535) return DA3S_EINVAL;
+    K1Args a;
+    a.depth = depth; a.conf = conf; a.cams = cams; a.H = H; a.W = W; a.P = (long long)H * W;
+    a.flags = flags; a.conf_thr = conf_thr; a.conf_thr_dev = conf_thr_dev; a.conf_floor = conf_floor;
+    a.depth_eps = depth_eps; a.sim3 = sim3; a.xyz = xyz_out; a.mask = mask_out; a.n_kept = n_kept;
+    a.groups_per_block = 0;
+    const bool f64 = flags & DA3S_UNPROJ_OUT_F64;
+    // the vector path needs 16-byte aligned frames: P % 4 == 0 and aligned bases
+    bool vec = (a.P % 4 == 0) && aligned16(depth) && (!conf || aligned16(conf)) && aligned16(xyz_out) &&
+               (!mask_out || ((uintptr_t)mask_out & 3) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+#define K1_DISPATCH(M)                                                        \
+    return f64 ? launch_k1<M, double>(ctx, a, n_frames, vec, st)              \
+               : launch_k1<M, float>(ctx, a, n_frames, vec, st)
+    if (mode == DA3S_UNPROJ_CLOSED) { K1_DISPATCH(DA3S_UNPROJ_CLOSED); }
+    if (mode == DA3S_UNPROJ_KINV)   { K1_DISPATCH(DA3S_UNPROJ_KINV); }
+    K1_DISPATCH(DA3S_UNPROJ_FAST);
+#undef K1_DISPATCH
+}
+
+// ---------------------------------------------------------------------------------
+// K5: apply Sim(3):  out = s * (p R^T) + t   (utils/geometry.py:60-62, same operation order:
+// rotate, scale, translate — not pre-multiplied — so float64 results track numpy's)
+// ---------------------------------------------------------------------------------
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256)
+apply_sim3_kernel(const InT* __restrict__ in, long long n, const double* __restrict__ sim3, OutT* __restrict__ out) {
+    __shared__ double sm[13];
+    if (threadIdx.x < 13) sm[threadIdx.x] = sim3[threadIdx.x];
+    __syncthreads();
+    const double s = sm[0];
+    const double* R = sm + 1;
+    const double* t = sm + 10;
+    const bool f32io = sizeof(InT) == 4 && sizeof(OutT) == 4;
+    if (f32io) {
+        // 4 points = 3 float4 per thread; loads and stores both coalesced through shared memory
+        __shared__ float4 stg[256 * 3];
+        const long long n_groups = n >> 2;                         // full groups of 4 points
+        const float4* in4 = reinterpret_cast<const float4*>(in);
+        float4* out4 = reinterpret_cast<float4*>(out);
+        const long long per_block = 256;
+        for (long long gb = (long long)blockIdx.x * per_block; gb < n_groups; gb += (long long)gridDim.x * per_block) {
+            long long gcount = n_groups - gb; if (gcount > per_block) gcount = per_block;
+            const long long f4_count = gcount * 3;
+            for (int j = 0; j < 3; ++j) {
+                int idx = j * 256 + threadIdx.x;
+                if (idx < f4_count) stg[idx] = ldg_stream(in4 + gb * 3 + idx);
+            }
+            __syncthreads();
+            if (threadIdx.x < gcount) {
+                float* p = reinterpret_cast<float*>(&stg[threadIdx.x * 3]);
+                float q[12];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double x = p[3 * k], y = p[3 * k + 1], z = p[3 * k + 2];
+                    q[3 * k]     = (float)(s * (x * R[0] + y * R[1] + z * R[2]) + t[0]);
+                    q[3 * k + 1] = (float)(s * (x * R[3] + y * R[4] + z * R[5]) + t[1]);
+                    q[3 * k + 2] = (float)(s * (x * R[6] + y * R[7] + z * R[8]) + t[2]);
+                }
+#pragma unroll
+                for (int k = 0; k < 12; ++k) p[k] = q[k];
+            }
+            __syncthreads();
+            for (int j = 0; j < 3; ++j) {
+                int idx = j * 256 + threadIdx.x;
+                if (idx < f4_count) stg_stream(out4 + gb * 3 + idx, stg[idx]);
+            }
+            __syncthreads();
+        }
+        // tail points (n % 4)
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+            long long i = (n_groups << 2) + threadIdx.x;
+            double x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+            out[3 * i]     = (OutT)(s * (x * R[0] + y * R[1] + z * R[2]) + t[0]);
+            out[3 * i + 1] = (OutT)(s * (x * R[3] + y * R[4] + z * R[5]) + t[1]);
+            out[3 * i + 2] = (OutT)(s * (x * R[6] + y * R[7] + z * R[8]) + t[2]);
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            double x = (double)in[3 * i], y = (double)in[3 * i + 1], z = (double)in[3 * i + 2];
+            out[3 * i]     = (OutT)(s * (x * R[0] + y * R[1] + z * R[2]) + t[0]);
+            out[3 * i + 1] = (OutT)(s * (x * R[3] + y * R[4] + z * R[5]) + t[1]);
+            out[3 * i + 2] = (OutT)(s * (x * R[6] + y * R[7] + z * R[8]) + t[2]);
+        }
+    }
+}
+
+extern "C" int da3s_apply_sim3(da3s_ctx* ctx, const void* xyz_in, int in_f64, long long n_points,
+                               const double* sim3, void* xyz_out, int out_f64, void* stream) {
+    if (!ctx || !xyz_in || !xyz_out || !sim3 || n_points < 0) return DA3S_EINVAL;
+    if (n_points == 0) return DA3S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long work = in_f64 || out_f64 ? (n_points + 255) / 256 : ((n_points >> 2) + 255) / 256;
+    long long cap = (long long)ctx->sm_count * 16;
+    int blocks = (int)(work < 1 ? 1 : (work > cap ? cap : work));
+    if (!in_f64 && !out_f64) {
+        if (!aligned16(xyz_in) || !aligned16(xyz_out)) return DA3S_EALIGN;
+        apply_sim3_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)xyz_in, n_points, sim3, (float*)xyz_out);
+    } else if (!in_f64 && out_f64) {
+        apply_sim3_kernel<float, double><<<blocks, 256, 0, st>>>((const float*)xyz_in, n_points, sim3, (double*)xyz_out);
+    } else if (in_f64 && out_f64) {
+        apply_sim3_kernel<double, double><<<blocks, 256, 0, st>>>((const double*)xyz_in, n_points, sim3, (double*)xyz_out);
+    } else {
+        apply_sim3_kernel<double, float><<<blocks, 256, 0, st>>>((const double*)xyz_in, n_points, sim3, (float*)xyz_out);
+    }
+    DA3S_LAUNCH_CHECK(ctx);
+    return DA3S_OK;
+}

@@ -1,0 +1,390 @@
+"""torch-facing wrappers over the C ABI (include/da3s.h).
+
+torch is plumbing only: it owns device memory and streams; every computation on the
+path is a kernel of libda3s.so launched on torch's current stream.  All functions take
+CUDA tensors and raise on CPU tensors (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_contexts = {}
+
+
+class Context:
+    """One da3s_ctx per device (+ its workspace)."""
+
+    def __init__(self, device: torch.device, workspace_bytes: int):
+        self.lib = L.load()
+        self.device = device
+        h = C.c_void_p()
+        L.check(self.lib.da3s_create(device.index or 0, workspace_bytes, C.byref(h)), "da3s_create")
+        self.h = h
+        self.workspace_bytes = workspace_bytes
+
+    def close(self):
+        if self.h:
+            self.lib.da3s_destroy(self.h)
+            self.h = None
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.da3s_launch_count(self.h))
+
+
+def context(device=None, workspace_bytes: int | None = None) -> Context:
+    if not torch.cuda.is_available():
+        raise RuntimeError("da3slam_b200 needs a CUDA device: the alignment path has no CPU fallback")
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    if device.type != "cuda":
+        raise RuntimeError("da3slam_b200 runs on CUDA devices only")
+    if device.index is None:
+        device = torch.device(f"cuda:{torch.cuda.current_device()}")
+    ctx = _contexts.get(device.index)
+    want = workspace_bytes or (256 << 20)
+    if ctx is None or ctx.workspace_bytes < want:
+        if ctx is not None:
+            torch.cuda.synchronize(device)
+            ctx.close()
+        with torch.cuda.device(device):
+            ctx = Context(device, want)
+        _contexts[device.index] = ctx
+    return ctx
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t, name="tensor", dtype=None):
+    if t is None:
+        return C.c_void_p(0)
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+# ------------------------------------------------------------------------------------------
+# camera table
+# ------------------------------------------------------------------------------------------
+def build_cams(intrinsics: torch.Tensor, extrinsics: torch.Tensor, general_inverse: bool = False) -> torch.Tensor:
+    """[n,3,3] f32, [n,3,4] f32 -> opaque uint8 tensor [n, 200] holding da3s_cam records."""
+    K = intrinsics.to(torch.float32).contiguous()
+    E = extrinsics.to(torch.float32).contiguous()
+    n = K.shape[0]
+    assert K.shape == (n, 3, 3) and E.shape == (n, 3, 4)
+    ctx = context(K.device)
+    cams = torch.empty((n, L.CAM_BYTES), dtype=torch.uint8, device=K.device)
+    rc = ctx.lib.da3s_build_cams(ctx.h, _ptr(K), _ptr(E), n, L.CAM_GENERAL_INV if general_inverse else L.CAM_CLOSED_FORM,
+                                 _ptr(cams), _stream(K))
+    L.check(rc, "da3s_build_cams")
+    return cams
+
+
+# ------------------------------------------------------------------------------------------
+# K1 / K5
+# ------------------------------------------------------------------------------------------
+def unproject_filter(depth, conf, cams, *, mode="closed", world=False, out_f64=False, conf_cmp=None,
+                     conf_thr=0.0, conf_thr_dev=None, conf_floor=None, depth_eps=None, world_z=False,
+                     sim3=None, want_mask=True, want_count=True):
+    """depth [N,H,W] f32 (+ conf) -> (xyz [N,H,W,3], mask [N,H,W] bool or None, n_kept tensor or None)."""
+    depth = depth.contiguous()
+    N, H, W = depth.shape
+    ctx = context(depth.device)
+    flags = {"closed": L.UNPROJ_CLOSED, "kinv": L.UNPROJ_KINV, "fast": L.UNPROJ_FAST}[mode]
+    if world:
+        flags |= L.UNPROJ_WORLD
+    if out_f64:
+        flags |= L.UNPROJ_OUT_F64
+    if conf_cmp == ">":
+        flags |= L.MASK_CONF_GT
+    elif conf_cmp == ">=":
+        flags |= L.MASK_CONF_GE
+    elif conf_cmp is not None:
+        raise ValueError("conf_cmp must be '>' or '>='")
+    if conf_floor is not None:
+        flags |= L.MASK_CONF_FLOOR
+    if depth_eps is not None:
+        flags |= L.MASK_DEPTH
+    if world_z:
+        flags |= L.MASK_WORLD_Z
+    s3 = None
+    if sim3 is not None:
+        s3 = sim3.to(torch.float64).contiguous()
+        if s3.dim() == 2:
+            assert s3.shape == (N, 13)
+            flags |= L.SIM3_PER_FRAME
+        else:
+            assert s3.shape == (13,)
+    xyz = torch.empty((N, H, W, 3), dtype=torch.float64 if out_f64 else torch.float32, device=depth.device)
+    mask = torch.empty((N, H, W), dtype=torch.uint8, device=depth.device) if want_mask else None
+    cnt = torch.zeros((1,), dtype=torch.int64, device=depth.device) if want_count else None
+    rc = ctx.lib.da3s_unproject_filter(
+        ctx.h, _ptr(depth, "depth", torch.float32), _ptr(conf, "conf", torch.float32), _ptr(cams, "cams"), N, H, W, flags,
+        float(conf_thr), _ptr(conf_thr_dev, "conf_thr_dev", torch.float32), float(conf_floor or 0.0), float(depth_eps or 0.0),
+        _ptr(s3), _ptr(xyz), _ptr(mask), _ptr(cnt), _stream(depth))
+    L.check(rc, "da3s_unproject_filter")
+    return xyz, (mask.view(torch.bool) if mask is not None else None), cnt
+
+
+def sim3_row(s, R, t, device) -> torch.Tensor:
+    row = np.empty(13, np.float64)
+    row[0] = s
+    row[1:10] = np.asarray(R, np.float64).reshape(-1)
+    row[10:13] = np.asarray(t, np.float64).reshape(-1)
+    return torch.from_numpy(row).to(device)
+
+
+def apply_sim3(points: torch.Tensor, sim3: torch.Tensor, out_f64: bool | None = None) -> torch.Tensor:
+    """points [...,3] f32/f64, sim3 [13] f64 (s, R row-major, t) -> s * (p R^T) + t."""
+    points = points.contiguous()
+    assert points.shape[-1] == 3 and points.dtype in (torch.float32, torch.float64)
+    in_f64 = points.dtype == torch.float64
+    if out_f64 is None:
+        out_f64 = True                     # utils/geometry.py:43-70 returns float64 for any input
+    ctx = context(points.device)
+    out = torch.empty(points.shape, dtype=torch.float64 if out_f64 else torch.float32, device=points.device)
+    s3 = sim3.to(torch.float64).contiguous()
+    rc = ctx.lib.da3s_apply_sim3(ctx.h, _ptr(points), int(in_f64), points.numel() // 3, _ptr(s3), _ptr(out), int(out_f64),
+                                 _stream(points))
+    L.check(rc, "da3s_apply_sim3")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# exact selection
+# ------------------------------------------------------------------------------------------
+def select(segments, device):
+    """segments: list of dicts(a=tensor, [b, ca, cb], kind, stat, percent, conf_th, eps).
+    Returns a structured numpy array (n_valid, lo, hi, value, gamma) — this helper
+    synchronises; the pair pipeline uses the device-side entry instead."""
+    ctx = context(device)
+    n = len(segments)
+    segs = (L.SelectSeg * n)()
+    keep = []
+    max_n = 0
+    for i, s in enumerate(segments):
+        a = s["a"].contiguous().view(-1)
+        keep.append(a)
+        segs[i].a = a.data_ptr()
+        for nm in ("b", "ca", "cb"):
+            t = s.get(nm)
+            if t is not None:
+                t = t.contiguous().view(-1)
+                keep.append(t)
+                setattr(segs[i], nm, t.data_ptr())
+        segs[i].n = a.numel()
+        segs[i].kind = s.get("kind", L.SEL_VALUES)
+        segs[i].stat = s.get("stat", L.SEL_MEDIAN)
+        segs[i].percent = s.get("percent", 50.0)
+        segs[i].conf_th = s.get("conf_th", 0.0)
+        segs[i].eps = s.get("eps", 0.0)
+        max_n = max(max_n, a.numel())
+    raw = np.frombuffer(bytes(segs), dtype=np.uint8).copy()
+    d_segs = torch.from_numpy(raw).to(device)
+    d_out = torch.empty((n, C.sizeof(L.SelectOut)), dtype=torch.uint8, device=device)
+    rc = ctx.lib.da3s_select(ctx.h, _ptr(d_segs), n, max_n, _ptr(d_out), _stream(d_segs))
+    L.check(rc, "da3s_select")
+    host = d_out.cpu().numpy()
+    dt = np.dtype([("n_valid", np.int64), ("lo", np.float32), ("hi", np.float32), ("value", np.float32), ("gamma", np.float32)])
+    return host.view(dt).reshape(n)
+
+
+# ------------------------------------------------------------------------------------------
+# pairs
+# ------------------------------------------------------------------------------------------
+def make_pairs(entries, device) -> torch.Tensor:
+    """entries: list of (depth_a, conf_a, depth_b, conf_b, cams_a, cams_b) CUDA tensors (views are
+    fine as long as they are contiguous and 16-byte aligned).  Returns the device pair table."""
+    n = len(entries)
+    arr = (L.Pair * n)()
+    for i, (da, ca, db, cb, cama, camb) in enumerate(entries):
+        for t in (da, ca, db, cb):
+            if not t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32:
+                raise RuntimeError("pair maps must be contiguous float32 CUDA tensors")
+            if t.data_ptr() % 16:
+                raise L.Da3sError(L.EALIGN, "make_pairs", "depth/conf view is not 16-byte aligned")
+        arr[i].depth_a, arr[i].conf_a = da.data_ptr(), ca.data_ptr()
+        arr[i].depth_b, arr[i].conf_b = db.data_ptr(), cb.data_ptr()
+        arr[i].cam_a, arr[i].cam_b = cama.data_ptr(), camb.data_ptr()
+    raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+    return torch.from_numpy(raw).to(device)
+
+
+def align_pairs(pairs: torch.Tensor, n_pairs: int, overlap: int, H: int, W: int, opts: L.AlignOpts,
+                sample_idx: torch.Tensor | None = None, want_aux=False, want_counts=False):
+    """Runs the whole pair pipeline asynchronously; returns (rows [n,16] f64, aux [n,8] f64 or None,
+    counts [n,n_hyp] i32 or None) as CUDA tensors."""
+    dev = pairs.device
+    ctx = context(dev)
+    rows = torch.empty((n_pairs, L.ROW_LEN), dtype=torch.float64, device=dev)
+    aux = torch.zeros((n_pairs, L.AUX_DOUBLES), dtype=torch.float64, device=dev) if want_aux else None
+    counts = None
+    if opts.n_hyp > 0:
+        if sample_idx is None:
+            raise ValueError("n_hyp > 0 needs sample_idx")
+        sample_idx = sample_idx.to(torch.int32).contiguous()
+        assert sample_idx.shape == (n_pairs, opts.n_hyp, 3)
+        if want_counts:
+            counts = torch.empty((n_pairs, opts.n_hyp), dtype=torch.int32, device=dev)
+    rc = ctx.lib.da3s_align_pairs(ctx.h, _ptr(pairs), n_pairs, overlap, H, W, C.byref(opts), _ptr(sample_idx), _ptr(rows),
+                                  _ptr(aux), _ptr(counts), _stream(pairs))
+    L.check(rc, "da3s_align_pairs")
+    return rows, aux, counts
+
+
+def pair_thresholds(pairs, n_pairs, overlap, H, W, opts):
+    dev = pairs.device
+    ctx = context(dev)
+    thr = torch.empty((n_pairs,), dtype=torch.float32, device=dev)
+    ds = torch.empty((n_pairs,), dtype=torch.float32, device=dev)
+    aux = torch.zeros((n_pairs, L.AUX_DOUBLES), dtype=torch.float64, device=dev)
+    rc = ctx.lib.da3s_pair_thresholds(ctx.h, _ptr(pairs), n_pairs, overlap, H, W, C.byref(opts), _ptr(thr), _ptr(ds),
+                                      _ptr(aux), _stream(pairs))
+    L.check(rc, "da3s_pair_thresholds")
+    return thr, ds, aux
+
+
+def ransac_hypotheses(pairs, n_pairs, overlap, H, W, thr, ds, sample_idx, *, world=True, valid_depth=True, depth_eps=1e-6):
+    dev = pairs.device
+    ctx = context(dev)
+    sample_idx = sample_idx.to(torch.int32).contiguous()
+    n_hyp = sample_idx.shape[1]
+    A = torch.empty((n_pairs, n_hyp, 9), dtype=torch.float32, device=dev)
+    t = torch.empty((n_pairs, n_hyp, 3), dtype=torch.float32, device=dev)
+    ok = torch.empty((n_pairs, n_hyp), dtype=torch.uint8, device=dev)
+    s3 = torch.empty((n_pairs, n_hyp, 13), dtype=torch.float64, device=dev)
+    rc = ctx.lib.da3s_ransac_hypotheses(ctx.h, _ptr(pairs), n_pairs, overlap, H, W, int(world), int(valid_depth), depth_eps,
+                                        _ptr(thr), _ptr(ds), _ptr(sample_idx), n_hyp, _ptr(A), _ptr(t), _ptr(ok), _ptr(s3),
+                                        _stream(pairs))
+    L.check(rc, "da3s_ransac_hypotheses")
+    return A, t, ok, s3
+
+
+def ransac_score(pairs, n_pairs, overlap, H, W, thr, ds, A, t, ok, ransac_thr, *, world=True, valid_depth=True, depth_eps=1e-6):
+    dev = pairs.device
+    ctx = context(dev)
+    n_hyp = A.shape[1]
+    counts = torch.empty((n_pairs, n_hyp), dtype=torch.int32, device=dev)
+    rc = ctx.lib.da3s_ransac_score(ctx.h, _ptr(pairs), n_pairs, overlap, H, W, int(world), int(valid_depth), depth_eps,
+                                   _ptr(thr), _ptr(ds), _ptr(A.contiguous()), _ptr(t.contiguous()), _ptr(ok.contiguous()),
+                                   n_hyp, float(ransac_thr), _ptr(counts), _stream(pairs))
+    L.check(rc, "da3s_ransac_score")
+    return counts
+
+
+def ransac_inlier_mask(pairs, n_pairs, overlap, H, W, thr, ds, best_A, best_t, best_ok, ransac_thr, *, world=True,
+                       valid_depth=True, depth_eps=1e-6):
+    dev = pairs.device
+    ctx = context(dev)
+    mask = torch.empty((n_pairs, overlap * H * W), dtype=torch.uint8, device=dev)
+    rc = ctx.lib.da3s_ransac_inlier_mask(ctx.h, _ptr(pairs), n_pairs, overlap, H, W, int(world), int(valid_depth), depth_eps,
+                                         _ptr(thr), _ptr(ds), _ptr(best_A.contiguous()), _ptr(best_t.contiguous()),
+                                         _ptr(best_ok.contiguous()), float(ransac_thr), _ptr(mask), _stream(pairs))
+    L.check(rc, "da3s_ransac_inlier_mask")
+    return mask.view(torch.bool)
+
+
+# ------------------------------------------------------------------------------------------
+# materialised correspondences
+# ------------------------------------------------------------------------------------------
+def umeyama_points(src, dst, weights=None, variant=L.UMEYAMA_WEIGHTED, idx_src=None, idx_dst=None) -> torch.Tensor:
+    src = src.contiguous()
+    dst = dst.contiguous()
+    assert src.dtype == dst.dtype and src.dtype in (torch.float32, torch.float64)
+    n = src.numel() // 3
+    ctx = context(src.device)
+    row = torch.zeros((L.ROW_LEN,), dtype=torch.float64, device=src.device)
+    w64 = 0
+    if weights is not None:
+        weights = weights.contiguous()
+        assert weights.dtype in (torch.float32, torch.float64)
+        w64 = int(weights.dtype == torch.float64)
+    n_idx = 0
+    if idx_src is not None:
+        idx_src = idx_src.to(torch.int64).contiguous()
+        idx_dst = idx_dst.to(torch.int64).contiguous()
+        n_idx = idx_src.numel()
+    rc = ctx.lib.da3s_umeyama_points(ctx.h, _ptr(src), _ptr(dst), int(src.dtype == torch.float64), _ptr(weights), w64, n,
+                                     _ptr(idx_src), _ptr(idx_dst), n_idx, variant, _ptr(row), _stream(src))
+    L.check(rc, "da3s_umeyama_points")
+    return row
+
+
+def irls_points(src, dst, conf_src, conf_dst, idx_src=None, idx_dst=None, delta=1.0, max_iterations=20, tol=1e-6):
+    src = src.contiguous()
+    dst = dst.contiguous()
+    assert src.dtype == dst.dtype and src.dtype in (torch.float32, torch.float64)
+    n = src.numel() // 3
+    ctx = context(src.device)
+    row = torch.zeros((L.ROW_LEN,), dtype=torch.float64, device=src.device)
+    n_idx = 0
+    if idx_src is not None:
+        idx_src = idx_src.to(torch.int64).contiguous()
+        idx_dst = idx_dst.to(torch.int64).contiguous()
+        n_idx = idx_src.numel()
+    rc = ctx.lib.da3s_irls_points(ctx.h, _ptr(src), _ptr(dst), int(src.dtype == torch.float64),
+                                  _ptr(conf_src.contiguous(), "conf_src", torch.float32),
+                                  _ptr(conf_dst.contiguous(), "conf_dst", torch.float32), n, _ptr(idx_src), _ptr(idx_dst),
+                                  n_idx, float(delta), int(max_iterations), float(tol), _ptr(row), _stream(src))
+    L.check(rc, "da3s_irls_points")
+    return row
+
+
+# ------------------------------------------------------------------------------------------
+# voxel grid
+# ------------------------------------------------------------------------------------------
+def voxel_downsample(clouds, voxel: float, table_slots: int | None = None, max_voxels: int | None = None, sort=True):
+    """clouds: list of (xyz [n,3] f32, rgb [n,3] u8 or None, mask [n] bool/u8 or None) CUDA tensors, all
+    accumulated into one grid.  Returns (xyz [m,3] f32, rgb [m,3] u8 or None, count [m] i32, key [m] i64)."""
+    dev = clouds[0][0].device
+    total = sum(c[0].numel() // 3 for c in clouds)
+    if table_slots is None:
+        table_slots = 1 << max(10, int(math.ceil(math.log2(max(2 * total, 1024)))))
+        table_slots = min(table_slots, 1 << 28)
+    need = table_slots * 64 + (64 << 20)
+    ctx = context(dev, need)
+    if max_voxels is None:
+        max_voxels = min(total, table_slots)
+    has_rgb = clouds[0][1] is not None
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    L.check(ctx.lib.da3s_voxel_begin(ctx.h, table_slots, st), "da3s_voxel_begin")
+    for xyz, rgb, mask in clouds:
+        xyz = xyz.contiguous().view(-1, 3)
+        if mask is not None:
+            mask = mask.contiguous().view(-1).view(torch.uint8)
+        rc = ctx.lib.da3s_voxel_insert(ctx.h, _ptr(xyz, "xyz", torch.float32), _ptr(rgb.contiguous() if rgb is not None else None),
+                                       _ptr(mask), xyz.shape[0], float(voxel), st)
+        L.check(rc, "da3s_voxel_insert")
+    out_xyz = torch.empty((max_voxels, 3), dtype=torch.float32, device=dev)
+    out_rgb = torch.empty((max_voxels, 3), dtype=torch.uint8, device=dev) if has_rgb else None
+    out_cnt = torch.empty((max_voxels,), dtype=torch.int32, device=dev)
+    out_key = torch.empty((max_voxels,), dtype=torch.int64, device=dev)
+    nv = torch.zeros((2,), dtype=torch.int64, device=dev)
+    rc = ctx.lib.da3s_voxel_finish(ctx.h, float(voxel), max_voxels, _ptr(out_xyz), _ptr(out_rgb), _ptr(out_cnt), _ptr(out_key),
+                                   C.c_void_p(nv.data_ptr()), C.c_void_p(nv.data_ptr() + 8), st)
+    L.check(rc, "da3s_voxel_finish")
+    n, dropped = (int(v) for v in nv.cpu())
+    if dropped:
+        raise L.Da3sError(L.ENOMEM, "voxel_downsample", f"hash table full: {dropped} points dropped")
+    if n > max_voxels:
+        raise L.Da3sError(L.ENOMEM, "voxel_downsample", f"{n} voxels > max_voxels {max_voxels}")
+    out_xyz, out_cnt, out_key = out_xyz[:n], out_cnt[:n], out_key[:n]
+    if out_rgb is not None:
+        out_rgb = out_rgb[:n]
+    if sort:
+        order = torch.argsort(out_key)     # canonical order = ascending packed key (glue, not the hot path)
+        out_xyz, out_cnt, out_key = out_xyz[order], out_cnt[order], out_key[order]
+        if out_rgb is not None:
+            out_rgb = out_rgb[order]
+    return out_xyz, out_rgb, out_cnt, out_key

@@ -1,0 +1,128 @@
+"""Submap-level host logic over the kernels: device-resident submaps, batched pair
+alignment of a sequence / of loop candidates, Sim(3) chaining, map export.
+
+Mirrors the shape of the reference's intended long-sequence pipeline
+(utils/da3_streaming.py:523-695: pairwise align -> accumulate -> apply -> export) with
+every per-pixel stage on the GPU and no host synchronisation until the Sim(3) rows are
+read back.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def _field(pred, key):
+    return pred[key] if isinstance(pred, dict) else getattr(pred, key)
+
+
+@dataclass
+class DeviceSubmap:
+    """A DA3 prediction for one chunk of frames, resident in HBM.
+    depth/conf [F,H,W] f32, cams = da3s_cam table [F,200] u8, images [F,H,W,3] u8 or None."""
+    depth: torch.Tensor
+    conf: torch.Tensor
+    cams: torch.Tensor
+    intrinsics: torch.Tensor
+    extrinsics: torch.Tensor
+    images: torch.Tensor | None = None
+
+    @property
+    def shape(self):
+        return tuple(self.depth.shape)
+
+    @staticmethod
+    def from_prediction(pred, device="cuda", general_inverse=False, non_blocking=True) -> "DeviceSubmap":
+        def up(x, dtype):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            return t.to(device=device, dtype=dtype, non_blocking=non_blocking).contiguous()
+        depth = up(_field(pred, "depth"), torch.float32)
+        conf = up(_field(pred, "conf"), torch.float32)
+        K = up(_field(pred, "intrinsics"), torch.float32)
+        E = up(_field(pred, "extrinsics"), torch.float32)
+        img = None
+        has_img = ("processed_images" in pred) if isinstance(pred, dict) else hasattr(pred, "processed_images")
+        if has_img:
+            img = up(_field(pred, "processed_images"), torch.uint8)
+        F, H, W = depth.shape
+        if (H * W) % 4:
+            raise L.Da3sError(L.EALIGN, "DeviceSubmap", "H*W must be a multiple of 4 (16-byte frame alignment)")
+        return DeviceSubmap(depth, conf, ops.build_cams(K, E, general_inverse), K, E, img)
+
+
+def pair_entry(prev: DeviceSubmap, cur: DeviceSubmap, overlap: int):
+    """prev's last `overlap` frames (target, A) vs cur's first `overlap` frames (source, B):
+    utils/align.py:323-335, align_geometry.py:271-285."""
+    F = prev.depth.shape[0]
+    return (prev.depth[F - overlap:], prev.conf[F - overlap:], cur.depth[:overlap], cur.conf[:overlap],
+            prev.cams[F - overlap:], cur.cams[:overlap])
+
+
+def rows_to_sim3(rows: np.ndarray):
+    """[n,16] rows -> list of (s, R, t) exactly as the reference returns them
+    (python float, (3,3) float64, (3,) float64)."""
+    out = []
+    for r in np.asarray(rows):
+        out.append((float(r[0]), r[1:10].reshape(3, 3).copy(), r[10:13].copy()))
+    return out
+
+
+def align_submap_pairs(pairs_list, overlap=1, sample_idx=None, want_aux=False, want_counts=False, **opt_kw):
+    """pairs_list: list of (prev DeviceSubmap, cur DeviceSubmap).  One batched launch
+    sequence for all of them.  Returns CUDA tensors (rows, aux, counts)."""
+    if not pairs_list:
+        raise ValueError("no pairs")
+    dev = pairs_list[0][0].depth.device
+    _, H, W = pairs_list[0][0].depth.shape
+    entries = [pair_entry(a, b, overlap) for a, b in pairs_list]
+    table = ops.make_pairs(entries, dev)
+    opts = L.default_opts(**opt_kw)
+    return ops.align_pairs(table, len(entries), overlap, H, W, opts, sample_idx, want_aux, want_counts)
+
+
+def align_sequence(submaps, overlap=1, **kw):
+    """Consecutive pairs (k, k+1) of a sequence; rows[k] maps submap k+1 into submap k."""
+    return align_submap_pairs([(submaps[k], submaps[k + 1]) for k in range(len(submaps) - 1)], overlap, **kw)
+
+
+def accumulate_sim3(chain):
+    """utils/geometry.py:73-119: identity first, then left-to-right composition
+    (output length = len(chain) + 1).  Host float64: it is len(chain) 3x3 products."""
+    if not chain:
+        return []
+    acc = [(1.0, np.eye(3), np.zeros(3)), (chain[0][0], chain[0][1], chain[0][2])]
+    for i in range(1, len(chain)):
+        s_n, R_n, t_n = chain[i]
+        s_p, R_p, t_p = acc[i]
+        acc.append((s_p * s_n, R_p @ R_n, s_p * (R_p @ t_n) + t_p))
+    return acc
+
+
+def export_map(submaps, cumulative, voxel, conf_percentile=None, conf_thr=None, mode="fast", table_slots=None,
+               max_voxels=None, skip_overlap=0, sort=True):
+    """Unproject every submap to its world frame, move it into submap 0's frame with its
+    cumulative Sim(3) (fused into the unprojection kernel), keep confident pixels and
+    voxel-downsample the union.  conf_percentile follows viewer.py:333-336 per submap
+    (percentile of the positive confidences, keep >=); conf_thr is a fixed '>' threshold."""
+    dev = submaps[0].depth.device
+    clouds = []
+    for k, sm in enumerate(submaps):
+        s, R, t = cumulative[k]
+        row = ops.sim3_row(s, R, t, dev)
+        first = skip_overlap if k > 0 else 0
+        depth, conf, cams = sm.depth[first:], sm.conf[first:], sm.cams[first:]
+        kw = dict(mode=mode, world=True, sim3=row, depth_eps=1e-6, want_count=False)
+        if conf_percentile is not None:
+            sel = ops.select([dict(a=conf, kind=L.SEL_POSITIVE, stat=L.SEL_PERCENTILE, percent=float(min(conf_percentile, 99.9)))], dev)
+            kw.update(conf_cmp=">=", conf_thr=float(sel["value"][0]), conf_floor=0.0)
+        elif conf_thr is not None:
+            kw.update(conf_cmp=">", conf_thr=float(conf_thr))
+        xyz, mask, _ = ops.unproject_filter(depth, conf, cams, **kw)
+        rgb = sm.images[first:].reshape(-1, 3) if sm.images is not None else None
+        clouds.append((xyz.view(-1, 3), rgb, mask.reshape(-1)))
+    return ops.voxel_downsample(clouds, voxel, table_slots, max_voxels, sort=sort)

@@ -335,3 +335,50 @@ def align_pair(prev, cur, overlap=1, world=True, use_depth_scale=False, delta=1.
                                tol, min_points, huber)
     out.update(s=s, R=R, t=t, iters=info["iters"], n_valid=info["n_valid"], status=info["status"])
     return out
+
+
+# --------------------------------------------------------------------------
+# C-backed twins of the SPEC 4 loops (oracle/c/oracle.c, real fmaf): exact and fast
+# enough for full-size inputs; the numpy forms above are the readable statement.
+# --------------------------------------------------------------------------
+def _c_arrays(A, T, ok, xs, ys, mask):
+    A = np.ascontiguousarray(A, F32).reshape(-1, 9)
+    T = np.ascontiguousarray(T, F32).reshape(-1, 3)
+    ok = np.ascontiguousarray(ok, np.uint8)
+    xs = np.ascontiguousarray(xs, F32)
+    ys = np.ascontiguousarray(ys, F32)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    return A, T, ok, xs, ys, mask
+
+
+def ransac_score_c(A, T, ok, xs, ys, mask, thr):
+    from . import build as ob
+    lib = ob.load()
+    A, T, ok, xs, ys, mask = _c_arrays(A, T, ok, xs, ys, mask)
+    counts = np.zeros(A.shape[0], np.int32)
+    lib.oracle_ransac_score(A.ctypes.data, T.ctypes.data, ok.ctypes.data, A.shape[0], xs.ctypes.data, ys.ctypes.data,
+                            mask.ctypes.data, xs.shape[0], F32(float(thr) * float(thr)), counts.ctypes.data)
+    return counts
+
+
+def ransac_inlier_mask_c(A, T, best, xs, ys, mask, thr):
+    from . import build as ob
+    lib = ob.load()
+    if best < 0:
+        return np.zeros(len(mask), bool)
+    A, T, _, xs, ys, mask = _c_arrays(A, T, np.ones(len(np.asarray(A).reshape(-1, 9)), np.uint8), xs, ys, mask)
+    out = np.zeros(xs.shape[0], np.uint8)
+    lib.oracle_ransac_inlier_mask(A[best].ctypes.data, T[best].ctypes.data, xs.ctypes.data, ys.ctypes.data,
+                                  mask.ctypes.data, xs.shape[0], F32(float(thr) * float(thr)), out.ctypes.data)
+    return out.astype(bool)
+
+
+def cam_fast_f32_c(depth, intrinsics):
+    from . import build as ob
+    lib = ob.load()
+    depth = np.ascontiguousarray(depth, F32)
+    K = np.ascontiguousarray(intrinsics, F32)
+    n, H, W = depth.shape
+    out = np.empty((n, H, W, 3), F32)
+    lib.oracle_cam_fast_f32(depth.ctypes.data, n, H, W, K.ctypes.data, out.ctypes.data)
+    return out

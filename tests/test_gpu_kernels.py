@@ -1,0 +1,412 @@
+"""GPU parity tests: every kernel of libda3s.so against the CPU oracle, through the C ABI
+(da3slam_b200.ops is a thin ctypes layer).  Bit-exact for masks / counts / order
+statistics / inliers / voxel keys; 1e-6 relative (stated per test) for floating results.
+"""
+import numpy as np
+import pytest
+import torch
+
+from da3slam_b200 import _lib as L
+from da3slam_b200 import ops, synth
+from da3slam_b200.pipeline import DeviceSubmap
+from oracle import ref_port as rp
+from oracle import spec_port as sp
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6          # north-star tolerance for scale / rotation / translation
+
+
+def dev_t(x, cuda, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(cuda)
+    return t if dtype is None else t.to(dtype)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(1e-30, np.max(np.abs(b))))
+
+
+# ----------------------------------------------------------------------------------------
+# K1 unprojection + filtering
+# ----------------------------------------------------------------------------------------
+def test_unproject_against_reference_golden(golden, cuda):
+    g = golden("unproject")
+    d, c, K, E = (dev_t(g[k], cuda) for k in ("depth", "conf", "K", "E"))
+    cams = ops.build_cams(K, E)
+    # closed form, camera frame: BIT-EXACT vs src/vggt/utils/geometry.py:86-116
+    xyz, _, _ = ops.unproject_filter(d[1:2], None, cams[1:2], mode="closed", world=False, want_mask=False, want_count=False)
+    assert np.array_equal(xyz[0].cpu().numpy(), g["u3_cam_1"])
+    # closed form, world, float64 out vs VGGT world (BLAS order differs -> 1e-6 rel, observed ~1e-16)
+    xyz, _, _ = ops.unproject_filter(d, None, cams, mode="closed", world=True, out_f64=True, want_mask=False, want_count=False)
+    assert rel_err(xyz.cpu().numpy(), g["u3_world"]) < 1e-12
+    # general K^-1 path vs the float64 numpy reference (utils/geometry.py:4-40)
+    cams_g = ops.build_cams(K, E, general_inverse=True)
+    xyz, _, _ = ops.unproject_filter(d, None, cams_g, mode="kinv", world=True, out_f64=True, want_mask=False, want_count=False)
+    assert rel_err(xyz.cpu().numpy(), g["u2_world"]) < REL
+    # float32 outputs vs the float32 torch reference (align_geometry.py:192-256)
+    xyz, _, _ = ops.unproject_filter(d, None, cams, mode="closed", world=False, want_mask=False, want_count=False)
+    assert rel_err(xyz.cpu().numpy(), g["u1_camera"]) < REL
+    xyz, _, _ = ops.unproject_filter(d, None, cams, mode="fast", world=True, want_mask=False, want_count=False)
+    assert rel_err(xyz.cpu().numpy(), g["u1_world"]) < 2e-6
+
+
+@pytest.mark.parametrize("H,W", [(20, 28), (37, 41), (518, 518)])
+def test_unproject_fast_bit_exact_and_masks(cuda, H, W):
+    rng = np.random.default_rng(H * 1000 + W)
+    n = 3
+    depth = synth.smooth_depth(rng, n, H, W)
+    depth[0, 0, :5] = 0.0
+    depth[1, 1, 2] = np.nan
+    depth[2, 2, 3] = np.inf
+    conf = synth.da3_like_conf(rng, n, H, W)
+    K = synth.make_intrinsics(n, H, W)
+    E = synth.trajectory_w2c(rng, n).astype(np.float32)
+    d, c = dev_t(depth, cuda), dev_t(conf, cuda)
+    cams = ops.build_cams(dev_t(K, cuda), dev_t(E, cuda))
+    thr = np.float32(0.37)
+    # SPEC 1: float32 camera points, bit-exact vs the oracle statement
+    xyz, mask, cnt = ops.unproject_filter(d, c, cams, mode="fast", world=False, conf_cmp=">", conf_thr=float(thr), depth_eps=1e-6)
+    ref = sp.cam_fast_f32(depth, K)
+    got = xyz.cpu().numpy()
+    assert np.array_equal(got, ref, equal_nan=True)
+    ref_mask = (conf > thr) & (depth > np.float32(1e-6)) & np.isfinite(depth)
+    assert np.array_equal(mask.cpu().numpy(), ref_mask)
+    assert int(cnt.item()) == int(ref_mask.sum())
+    # '>=' with a positive floor (viewer.py:334-336) and the threshold passed from device memory
+    thr_dev = torch.tensor([float(thr)], dtype=torch.float32, device=cuda)
+    _, mask, cnt = ops.unproject_filter(d, c, cams, mode="fast", conf_cmp=">=", conf_thr_dev=thr_dev, conf_floor=0.0)
+    ref_mask = (conf >= thr) & (conf > 0)
+    assert np.array_equal(mask.cpu().numpy(), ref_mask) and int(cnt.item()) == int(ref_mask.sum())
+    # threshold exactly equal to a data value: '>' and '>=' must differ exactly there
+    v = conf[0, H // 2, W // 2]
+    _, m_gt, _ = ops.unproject_filter(d, c, cams, mode="fast", conf_cmp=">", conf_thr=float(v))
+    _, m_ge, _ = ops.unproject_filter(d, c, cams, mode="fast", conf_cmp=">=", conf_thr=float(v))
+    assert np.array_equal(m_gt.cpu().numpy(), conf > v) and np.array_equal(m_ge.cpu().numpy(), conf >= v)
+    # world mode in float32 (SPEC 4 world points)
+    xyz, _, _ = ops.unproject_filter(d, None, cams, mode="fast", world=True, want_mask=False, want_count=False)
+    finite = np.isfinite(depth)
+    ref_w = sp.world_from_cam_f32(np.where(finite[..., None], ref, 0), E)
+    assert np.array_equal(xyz.cpu().numpy()[finite], ref_w[finite])
+
+
+def test_unproject_fused_sim3_and_viewer_validity(cuda):
+    rng = np.random.default_rng(3)
+    n, H, W = 4, 24, 32
+    depth = synth.smooth_depth(rng, n, H, W)
+    depth[0, :2] = 0.01                                   # z < 0.1 after unprojection with identity-ish pose
+    conf = synth.da3_like_conf(rng, n, H, W)
+    K = synth.make_intrinsics(n, H, W)
+    E = synth.trajectory_w2c(rng, n).astype(np.float32)
+    d, c = dev_t(depth, cuda), dev_t(conf, cuda)
+    cams = ops.build_cams(dev_t(K, cuda), dev_t(E, cuda))
+    world, _, _ = rp.unproject_world_vggt(depth, E, K)
+    # viewer.py:214-218 validity on world z
+    xyz, mask, _ = ops.unproject_filter(d, c, cams, mode="closed", world=True, out_f64=True, world_z=True)
+    ref_mask = (world[..., 2] > 0.1) & (world[..., 2] < 50.0) & np.all(np.isfinite(world), axis=-1)
+    assert rel_err(xyz.cpu().numpy(), world) < 1e-12
+    assert np.array_equal(mask.cpu().numpy(), ref_mask)
+    # one Sim(3) for all frames, and one per frame, fused behind the unprojection
+    s, R, t = synth.random_sim3(rng)
+    row = ops.sim3_row(s, R, t, cuda)
+    xyz, _, _ = ops.unproject_filter(d, None, cams, mode="closed", world=True, out_f64=True, sim3=row, want_mask=False, want_count=False)
+    assert rel_err(xyz.cpu().numpy(), rp.apply_sim3(world, s, R, t)) < 1e-12
+    rows, ref = [], []
+    for f in range(n):
+        s, R, t = synth.random_sim3(rng)
+        rows.append(ops.sim3_row(s, R, t, cuda))
+        ref.append(rp.apply_sim3(world[f], s, R, t))
+    xyz, _, _ = ops.unproject_filter(d, None, cams, mode="closed", world=True, out_f64=True, sim3=torch.stack(rows), want_mask=False, want_count=False)
+    assert rel_err(xyz.cpu().numpy(), np.stack(ref)) < 1e-12
+
+
+def test_apply_sim3_golden_and_sizes(golden, cuda):
+    g = golden("sim3_chain")
+    row = ops.sim3_row(float(g["s"]), g["R"], g["t"], cuda)
+    out = ops.apply_sim3(dev_t(g["P4"], cuda), row)
+    assert out.dtype == torch.float64 and rel_err(out.cpu().numpy(), g["S4"]) < 1e-14
+    out = ops.apply_sim3(dev_t(g["P2"], cuda), row)
+    assert rel_err(out.cpu().numpy(), g["S2"]) < 1e-14
+    rng = np.random.default_rng(0)
+    for n in (1, 3, 4, 5, 1023, 1024, 1025, 100003):
+        p = rng.normal(0, 2, (n, 3)).astype(np.float32)
+        out = ops.apply_sim3(dev_t(p, cuda), row, out_f64=False)
+        ref = rp.apply_sim3(p, float(g["s"]), g["R"], g["t"])
+        assert out.dtype == torch.float32 and np.abs(out.cpu().numpy() - ref).max() < 1e-6 * 8
+
+
+# ----------------------------------------------------------------------------------------
+# exact selection
+# ----------------------------------------------------------------------------------------
+def test_select_median_percentile_bit_exact(cuda):
+    rng = np.random.default_rng(11)
+    segs, refs = [], []
+    for n in (1, 2, 3, 4, 7, 100, 4095, 4096, 4097, 268324):
+        a = (np.exp(rng.normal(0, 0.75, n))).astype(np.float32)
+        if n > 50:
+            a[rng.integers(0, n, n // 20)] = 0.0          # ties and zeros
+            a[rng.integers(0, n, 5)] = -1.5               # negatives
+        t = dev_t(a, cuda)
+        segs.append(dict(a=t, stat=L.SEL_MEDIAN)); refs.append(np.median(a))
+        for p in (0.0, 10.0, 50.0, 65.0, 99.9, 100.0):
+            segs.append(dict(a=t, stat=L.SEL_PERCENTILE, percent=p)); refs.append(np.percentile(a, p))
+        pos = a[a > 0]
+        if len(pos):
+            segs.append(dict(a=t, kind=L.SEL_POSITIVE, stat=L.SEL_PERCENTILE, percent=65.0))
+            refs.append(np.percentile(pos, 65.0))          # viewer.py:334-335
+    out = ops.select(segs, cuda)
+    for i, r in enumerate(refs):
+        assert out["value"][i] == np.float32(r), (i, out[i], r)
+    # all-equal data, and an empty positive set
+    z = dev_t(np.zeros(1000, np.float32), cuda)
+    out = ops.select([dict(a=z, stat=L.SEL_MEDIAN), dict(a=z, kind=L.SEL_POSITIVE, stat=L.SEL_PERCENTILE, percent=65.0)], cuda)
+    assert out["value"][0] == 0 and out["n_valid"][1] == 0 and np.isnan(out["value"][1])
+
+
+def test_select_depth_ratio_median(golden, cuda):
+    g = golden("depth_scale")
+    segs, refs, counts = [], [], []
+    for case in range(4):
+        dA, cA, dB, cB = (g[f"{k}{case}"] for k in ("dA", "cA", "dB", "cB"))
+        segs.append(dict(a=dev_t(dA[-1], cuda), b=dev_t(dB[0], cuda), ca=dev_t(cA[-1], cuda), cb=dev_t(cB[0], cuda),
+                         kind=L.SEL_RATIO, stat=L.SEL_MEDIAN, conf_th=0.2, eps=1e-6))
+        refs.append(g[f"plain{case}"])
+        m = (dA[-1] > 1e-6) & (dB[0] > 1e-6) & np.isfinite(dA[-1]) & np.isfinite(dB[0]) & (cA[-1] > 0.2) & (cB[0] > 0.2)
+        counts.append(int(m.sum()))
+    out = ops.select(segs, cuda)
+    for i in range(4):
+        assert out["n_valid"][i] == counts[i]
+        assert np.float64(out["value"][i]) == refs[i]      # align_geometry.py:329-330, bit-exact
+
+
+# ----------------------------------------------------------------------------------------
+# pair alignment
+# ----------------------------------------------------------------------------------------
+def make_dev_pairs(subs, cuda, overlap):
+    dsubs = [DeviceSubmap.from_prediction(s, cuda) for s in subs]
+    from da3slam_b200.pipeline import pair_entry
+    entries = [pair_entry(dsubs[k], dsubs[k + 1], overlap) for k in range(len(dsubs) - 1)]
+    return dsubs, ops.make_pairs(entries, cuda), len(entries)
+
+
+def check_rows_against_oracle(rows, subs, overlap, tol=REL, **kw):
+    rows = rows.cpu().numpy()
+    for k in range(len(subs) - 1):
+        o = sp.align_pair(subs[k], subs[k + 1], overlap=overlap, **kw)
+        r = rows[k]
+        assert int(r[15]) == o["status"], (k, r[15], o["status"])
+        assert int(r[13]) == o["n_valid"], (k, r[13], o["n_valid"])            # bit-exact mask count
+        if o["status"] == 0:
+            assert int(r[14]) == o["iters"], (k, r[14], o["iters"])
+            assert abs(r[0] - o["s"]) <= tol * abs(o["s"])
+            assert rel_err(r[1:10].reshape(3, 3), o["R"]) <= tol
+            assert np.abs(r[10:13] - o["t"]).max() <= tol * max(1.0, np.abs(o["t"]).max())
+        else:
+            assert r[0] == 1.0 and np.array_equal(r[1:10].reshape(3, 3), np.eye(3)) and not r[10:13].any()
+
+
+@pytest.mark.parametrize("world", [True, False])
+@pytest.mark.parametrize("overlap", [1, 2])
+def test_align_pairs_irls_vs_oracle(cuda, world, overlap):
+    subs, gt = synth.make_sequence(4, 3, 40, 52, overlap=overlap, seed=21 + overlap)
+    _, table, n = make_dev_pairs(subs, cuda, overlap)
+    opts = L.default_opts(world=int(world))
+    rows, aux, _ = ops.align_pairs(table, n, overlap, 40, 52, opts, want_aux=True)
+    check_rows_against_oracle(rows, subs, overlap, world=world)
+    aux = aux.cpu().numpy()
+    for k in range(n):
+        c = sp.pair_correspondences(subs[k], subs[k + 1], overlap, world)
+        assert np.float32(aux[k, 0]) == c["thr"]                               # utils/align.py:142, bit-exact
+    if world:                                                                   # the estimate recovers ground truth
+        r = rows.cpu().numpy()
+        for k in range(n):
+            assert abs(r[k, 0] - gt[k][0]) < 2e-3 and np.abs(r[k, 1:10].reshape(3, 3) - gt[k][1]).max() < 2e-3
+
+
+def test_align_pairs_huber_tail_and_single_solve(cuda):
+    # gross outliers put many residuals above delta so the Huber branch matters
+    subs, _ = synth.make_sequence(3, 2, 48, 64, overlap=1, seed=5, outlier_ratio=0.25)
+    _, table, n = make_dev_pairs(subs, cuda, 1)
+    for delta in (1.0, 0.1):
+        opts = L.default_opts(world=1, huber_delta=delta)
+        rows, _, _ = ops.align_pairs(table, n, 1, 48, 64, opts)
+        check_rows_against_oracle(rows, subs, 1, world=True, delta=delta)
+    opts = L.default_opts(world=1, huber=0)
+    rows, _, _ = ops.align_pairs(table, n, 1, 48, 64, opts)
+    check_rows_against_oracle(rows, subs, 1, world=True, huber=False)
+    # max_iterations cap is honoured
+    opts = L.default_opts(world=1, max_iterations=2, tol=0.0)
+    rows, _, _ = ops.align_pairs(table, n, 1, 48, 64, opts)
+    check_rows_against_oracle(rows, subs, 1, world=True, max_iterations=2, tol=0.0)
+
+
+def test_align_pairs_depth_scale_and_too_few(cuda):
+    subs, _ = synth.make_sequence(3, 2, 36, 44, overlap=1, seed=9)
+    subs[2]["conf"][0] = 0.0                                # pair 1: nothing passes the threshold
+    _, table, n = make_dev_pairs(subs, cuda, 1)
+    opts = L.default_opts(world=0, depth_scale_mode=1)
+    rows, aux, _ = ops.align_pairs(table, n, 1, 36, 44, opts, want_aux=True)
+    check_rows_against_oracle(rows, subs, 1, world=False, use_depth_scale=True)
+    aux = aux.cpu().numpy()
+    assert np.float32(aux[0, 1]) == np.float32(rp.depth_scale_guarded(subs[0], subs[1]))   # bit-exact median ratio
+    assert aux[1, 1] == 1.0                                                                   # < 50 valid -> 1.0
+    assert int(rows[1, 15].item()) == 1
+
+
+def test_align_pairs_batch_order_invariance(cuda):
+    subs, _ = synth.make_sequence(5, 2, 32, 40, overlap=1, seed=2)
+    dsubs = [DeviceSubmap.from_prediction(s, cuda) for s in subs]
+    from da3slam_b200.pipeline import pair_entry
+    entries = [pair_entry(dsubs[k], dsubs[k + 1], 1) for k in range(4)]
+    opts = L.default_opts(world=1)
+    rows_a, _, _ = ops.align_pairs(ops.make_pairs(entries, cuda), 4, 1, 32, 40, opts)
+    perm = [2, 0, 3, 1]
+    rows_b, _, _ = ops.align_pairs(ops.make_pairs([entries[i] for i in perm], cuda), 4, 1, 32, 40, opts)
+    rows_c, _, _ = ops.align_pairs(ops.make_pairs(entries[1:3], cuda), 2, 1, 32, 40, opts)
+    a, b, c = rows_a.cpu().numpy(), rows_b.cpu().numpy(), rows_c.cpu().numpy()
+    assert np.array_equal(a[perm], b)          # bit-identical regardless of batch order ...
+    assert np.array_equal(a[1:3], c)           # ... and of how the batch is sharded (multi-GPU contract)
+
+
+def test_ransac_stages_bit_exact(cuda):
+    H, W, n_hyp = 40, 48, 96
+    subs, gt = synth.make_sequence(3, 2, H, W, overlap=1, seed=31, outlier_ratio=0.3)
+    _, table, n = make_dev_pairs(subs, cuda, 1)
+    rng = np.random.default_rng(7)
+    si = rng.integers(0, H * W, size=(n, n_hyp, 3)).astype(np.int32)
+    si[0, 5] = [3, 3, 9]                                    # repeated pixel -> invalid hypothesis
+    opts = L.default_opts(world=1)
+    thr, ds, _ = ops.pair_thresholds(table, n, 1, H, W, opts)
+    for world in (True, False):
+        A, t, ok, s3 = ops.ransac_hypotheses(table, n, 1, H, W, thr, ds, dev_t(si, cuda), world=world)
+        counts = ops.ransac_score(table, n, 1, H, W, thr, ds, A, t, ok, 0.02, world=world)
+        A_h, t_h, ok_h, s3_h, cnt_h = (x.cpu().numpy() for x in (A, t, ok, s3, counts))
+        for k in range(n):
+            corr = sp.pair_correspondences(subs[k], subs[k + 1], 1, world)
+            xs, ys = sp.ransac_points(corr, world)
+            oA, oT, ook, osim = sp.ransac_hypotheses(xs, ys, corr["mask"], si[k])
+            assert np.array_equal(ok_h[k].astype(bool), ook)                    # validity flags: exact
+            v = ook
+            assert rel_err(s3_h[k][v], osim[v]) < 1e-9                           # 3-point Umeyama vs LAPACK route
+            # scoring: feed the GPU's own float32 hypotheses to the oracle -> counts must be bit-exact
+            ref_counts = sp.ransac_score(A_h[k].reshape(-1, 3, 3), t_h[k], ok_h[k].astype(bool), xs, ys, corr["mask"], 0.02)
+            assert np.array_equal(cnt_h[k], ref_counts)
+            best, nbest = sp.ransac_best(ref_counts, ook, 20)
+            assert best >= 0
+            m = ops.ransac_inlier_mask(table[k * L.PAIR_BYTES:(k + 1) * L.PAIR_BYTES], 1, 1, H, W, thr[k:k + 1], ds[k:k + 1],
+                                       A[k, best:best + 1], t[k, best:best + 1], ok[k, best:best + 1], 0.02, world=world)
+            ref_m = sp.ransac_inlier_mask(A_h[k].reshape(-1, 3, 3), t_h[k], best, xs, ys, corr["mask"], 0.02)
+            assert np.array_equal(m.cpu().numpy()[0], ref_m) and int(ref_m.sum()) == nbest
+
+
+def test_align_pairs_with_ransac_end_to_end(cuda):
+    H, W, n_hyp = 40, 48, 128
+    subs, gt = synth.make_sequence(3, 2, H, W, overlap=1, seed=33, outlier_ratio=0.3)
+    _, table, n = make_dev_pairs(subs, cuda, 1)
+    rng = np.random.default_rng(8)
+    si = rng.integers(0, H * W, size=(n, n_hyp, 3)).astype(np.int32)
+    opts = L.default_opts(world=1, n_hyp=n_hyp, ransac_thr=0.02)
+    rows, aux, counts = ops.align_pairs(table, n, 1, H, W, opts, dev_t(si, cuda), want_aux=True, want_counts=True)
+    rows, aux, counts = rows.cpu().numpy(), aux.cpu().numpy(), counts.cpu().numpy()
+    for k in range(n):
+        o = sp.align_pair(subs[k], subs[k + 1], overlap=1, world=True, ransac=dict(sample_idx=si[k], thr=0.02))
+        # hypothesis tables can differ in the last float32 bit between the device Jacobi SVD and LAPACK, so the
+        # end-to-end check is on the decisions and the refined transform, not on every count
+        assert int(aux[k, 4]) == o["best"] and int(aux[k, 5]) == o["best_count"]
+        assert int(rows[k, 13]) == o["n_valid"]
+        assert abs(rows[k, 0] - o["s"]) <= REL * o["s"] and rel_err(rows[k, 1:10].reshape(3, 3), o["R"]) <= REL
+        assert abs(rows[k, 0] - gt[k][0]) < 5e-3              # RANSAC + IRLS recovers ground truth despite 30 % outliers
+    # no model: threshold so tight that fewer than min_inliers agree
+    opts = L.default_opts(world=1, n_hyp=n_hyp, ransac_thr=1e-7)
+    rows, _, _ = ops.align_pairs(table, n, 1, H, W, opts, dev_t(si, cuda))
+    assert (rows[:, 15].cpu().numpy() == 2).all() and (rows[:, 0].cpu().numpy() == 1.0).all()
+
+
+# ----------------------------------------------------------------------------------------
+# array-level Umeyama / IRLS against the reference's golden outputs
+# ----------------------------------------------------------------------------------------
+def row_close(row, s, R, t, tol=REL):
+    r = row.cpu().numpy()
+    assert abs(r[0] - s) <= tol * abs(s), (r[0], s)
+    assert rel_err(r[1:10].reshape(3, 3), R) <= tol
+    assert np.abs(r[10:13] - t).max() <= tol * max(1.0, np.abs(t).max())
+
+
+def test_umeyama_points_against_reference_golden(golden, cuda):
+    g = golden("umeyama")
+    src, dst, w = dev_t(g["src"], cuda), dev_t(g["dst"], cuda), dev_t(g["w"], cuda)
+    row_close(ops.umeyama_points(src, dst, w), float(g["W_s"]), g["W_R"], g["W_t"])
+    row_close(ops.umeyama_points(src.float(), dst.float(), w), float(g["W32_s"]), g["W32_R"], g["W32_t"])
+    row_close(ops.umeyama_points(src, dev_t(g["dst_m"], cuda), w), float(g["Wm_s"]), g["Wm_R"], g["Wm_t"])    # reflection fix
+    row_close(ops.umeyama_points(src, dst, None, L.UMEYAMA_MEAN), float(g["U_s"]), g["U_R"], g["U_t"])
+    row_close(ops.umeyama_points(src, dev_t(g["dst_m"], cuda), None, L.UMEYAMA_MEAN), float(g["Um_s"]), g["Um_R"], g["Um_t"])
+    row_close(ops.umeyama_points(src[:3].contiguous(), dst[:3].contiguous(), None, L.UMEYAMA_MEAN),
+              float(g["U3_s"]), g["U3_R"], g["U3_t"], tol=1e-9)                                              # rank-2 covariance
+    pm1, pm2 = dev_t(g["pm1"], cuda), dev_t(g["pm2"], cuda)
+    # utils/align.py:224: first argument ("point_map2") is the TARGET, second the source
+    row_close(ops.umeyama_points(pm2.view(-1, 3), pm1.view(-1, 3), None, L.UMEYAMA_NORMRATIO), float(g["N_s"]), g["N_R"], g["N_t"])
+
+
+def test_irls_points_against_reference_golden(golden, cuda):
+    g = golden("irls")
+    pm1, pm2 = g["pm1"].reshape(-1, 3), g["pm2"].reshape(-1, 3)
+    for tag, (a1, a2) in {"same": (g["c1"], g["c1"]), "indep": (g["c1"], g["c2"])}.items():
+        c1, c2 = a1.reshape(-1), a2.reshape(-1)
+        thr = g[f"{tag}0_thr"]
+        nz1, nz2 = np.flatnonzero(c1 > thr), np.flatnonzero(c2 > thr)       # utils/align.py:145-151
+        for seed in (0, 1):
+            idx = g[f"{tag}{seed}_idx"]
+            row = ops.irls_points(dev_t(pm2, cuda), dev_t(pm1, cuda), dev_t(c2, cuda), dev_t(c1, cuda),
+                                  idx_src=dev_t(nz2[idx], cuda), idx_dst=dev_t(nz1[idx], cuda))
+            row_close(row, float(g[f"{tag}{seed}_s"]), g[f"{tag}{seed}_R"], g[f"{tag}{seed}_t"])
+
+
+# ----------------------------------------------------------------------------------------
+# voxel grid
+# ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 1000, 200003])
+def test_voxel_downsample_bit_exact(cuda, n):
+    rng = np.random.default_rng(n + 1)
+    pts = rng.normal(0, 1.0, (n, 3)).astype(np.float32)
+    if n >= 1000:
+        pts[:200] = pts[0] + rng.normal(0, 1e-4, (200, 3)).astype(np.float32)   # heavy collisions in one voxel
+        pts[300] = [np.nan, 0, 0]
+        pts[301] = [1e30, 0, 0]                                                  # key out of range
+        pts[302] = [-0.0, 0.02, -0.02]                                           # exact voxel boundaries
+    rgb = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    mask = rng.random(n) < 0.9
+    if n == 0:
+        return
+    for use_rgb, use_mask in ((True, True), (False, False)):
+        out = ops.voxel_downsample([(dev_t(pts, cuda), dev_t(rgb, cuda) if use_rgb else None,
+                                     dev_t(mask, cuda) if use_mask else None)], 0.02)
+        xyz, col, cnt, key = sp.voxel_downsample(pts, 0.02, rgb if use_rgb else None, mask if use_mask else None)
+        assert np.array_equal(out[3].cpu().numpy(), key)            # voxel set: bit-exact keys
+        assert np.array_equal(out[2].cpu().numpy(), cnt)            # counts: bit-exact
+        assert np.array_equal(out[0].cpu().numpy(), xyz)            # integer accumulation -> positions bit-exact too
+        if use_rgb:
+            assert np.array_equal(out[1].cpu().numpy(), col)
+
+
+def test_voxel_accumulates_across_clouds(cuda):
+    rng = np.random.default_rng(4)
+    a = rng.normal(0, 0.5, (5000, 3)).astype(np.float32)
+    b = rng.normal(0, 0.5, (7000, 3)).astype(np.float32)
+    out = ops.voxel_downsample([(dev_t(a, cuda), None, None), (dev_t(b, cuda), None, None)], 0.05)
+    xyz, _, cnt, key = sp.voxel_downsample(np.concatenate([a, b]), 0.05)
+    assert np.array_equal(out[3].cpu().numpy(), key) and np.array_equal(out[2].cpu().numpy(), cnt)
+    assert np.array_equal(out[0].cpu().numpy(), xyz)
+
+
+def test_errors_are_loud(cuda):
+    with pytest.raises(RuntimeError):
+        ops.unproject_filter(torch.zeros(1, 4, 4), None, torch.zeros(1, 200, dtype=torch.uint8))      # CPU tensor
+    d = torch.zeros(1, 4, 4, device=cuda)
+    cams = torch.zeros(1, L.CAM_BYTES, dtype=torch.uint8, device=cuda)
+    with pytest.raises(L.Da3sError):
+        ctx = ops.context(cuda)
+        rc = ctx.lib.da3s_unproject_filter(ctx.h, 0, 0, 0, 1, 4, 4, 0, 0.0, 0, 0.0, 0.0, 0, 0, 0, 0, 0)
+        L.check(rc, "null args")
+    with pytest.raises(ValueError):
+        ops.unproject_filter(d, d, cams, conf_cmp="<")
