@@ -39,7 +39,7 @@ struct PairArgs {
     const float* thr;                       // [n_pairs]
     const float* dscale;                    // [n_pairs] (nullable = 1)
     PairState* state;                       // [n_pairs]
-    double* eff;                            // [n_pairs][overlap][12]  camera-frame (A | b) of the current estimate
+    double* eff;                            // [n_pairs][overlap][EFF_LEN]  residual map of the current estimate
     const float* gate;                      // [n_pairs][12] winning hypothesis (nullable)
     float gate_thr2;
     double* partials;                       // [n_pairs][overlap*tiles][MOM_LEN]
@@ -54,7 +54,7 @@ struct FrameConst {
     float cuA, cvA, ifuA, ifvA, cuB, cvB, ifuB, ifvB;
     float MfA[12], MfB[12];                 // float32 c2w (RANSAC world points, SPEC 4)
     float gate[12];
-    double effA[9], effb[3];
+    double By[9], Bx[9], c[3];              // residual = By y + Bx x + c  (By = I in camera mode)
     float thr, ds;
     int gate_on;
 };
@@ -73,9 +73,9 @@ __device__ __forceinline__ void load_frame_const(FrameConst& fc, const da3s_pair
         for (int k = 0; k < 12; ++k) fc.gate[k] = a.gate[12 * (size_t)pair + k];
     }
     if (a.eff) {
-        const double* e = a.eff + ((size_t)pair * a.overlap + frame) * 12;
-        for (int k = 0; k < 9; ++k) fc.effA[k] = e[k];
-        for (int k = 0; k < 3; ++k) fc.effb[k] = e[9 + k];
+        const double* e = a.eff + ((size_t)pair * a.overlap + frame) * EFF_LEN;
+        for (int k = 0; k < 9; ++k) { fc.By[k] = e[k]; fc.Bx[k] = e[9 + k]; }
+        for (int k = 0; k < 3; ++k) fc.c[k] = e[18 + k];
     }
 }
 
@@ -130,13 +130,13 @@ __device__ __noinline__ void write_row(const PairArgs& a, int pair, const PairSt
 
 __device__ __noinline__ void set_effective(const PairArgs& a, int pair, const PairState& st) {
     for (int f = 0; f < a.overlap; ++f) {
-        double* e = a.eff + ((size_t)pair * a.overlap + f) * 12;
+        double* e = a.eff + ((size_t)pair * a.overlap + f) * EFF_LEN;
         if (a.world) {
             const da3s_pair pr = a.pairs[pair];
-            effective_cam_transform(st.s, st.R, st.t, pr.cam_b[f].c2w, pr.cam_a[f].c2w, e, e + 9);
+            effective_residual_transform(st.s, st.R, st.t, pr.cam_b[f].c2w, pr.cam_a[f].c2w, e);
         } else {
-            for (int k = 0; k < 9; ++k) e[k] = st.s * st.R[k];
-            for (int k = 0; k < 3; ++k) e[9 + k] = st.t[k];
+            for (int k = 0; k < 9; ++k) { e[k] = (k % 4 == 0) ? 1.0 : 0.0; e[9 + k] = -st.s * st.R[k]; }
+            for (int k = 0; k < 3; ++k) e[18 + k] = -st.t[k];
         }
     }
 }
@@ -212,9 +212,14 @@ pair_moments_kernel(PairArgs a) {
         double w = (double)__fsqrt_rn(__fmul_rn(ca, cb));    // utils/align.py:166 in float32
         const double X0 = x[0], X1 = x[1], X2 = x[2], Y0 = y[0], Y1 = y[1], Y2 = y[2];
         if (huber) {
-            double r0 = Y0 - (fc.effA[0] * X0 + fc.effA[1] * X1 + fc.effA[2] * X2 + fc.effb[0]);
-            double r1 = Y1 - (fc.effA[3] * X0 + fc.effA[4] * X1 + fc.effA[5] * X2 + fc.effb[1]);
-            double r2 = Y2 - (fc.effA[6] * X0 + fc.effA[7] * X1 + fc.effA[8] * X2 + fc.effb[2]);
+            double r0 = fc.Bx[0] * X0 + fc.Bx[1] * X1 + fc.Bx[2] * X2 + fc.c[0];
+            double r1 = fc.Bx[3] * X0 + fc.Bx[4] * X1 + fc.Bx[5] * X2 + fc.c[1];
+            double r2 = fc.Bx[6] * X0 + fc.Bx[7] * X1 + fc.Bx[8] * X2 + fc.c[2];
+            if (a.world) {                                  // block-uniform
+                r0 += fc.By[0] * Y0 + fc.By[1] * Y1 + fc.By[2] * Y2;
+                r1 += fc.By[3] * Y0 + fc.By[4] * Y1 + fc.By[5] * Y2;
+                r2 += fc.By[6] * Y0 + fc.By[7] * Y1 + fc.By[8] * Y2;
+            } else { r0 += Y0; r1 += Y1; r2 += Y2; }
             double r = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
             if (r > delta) w *= delta / r;                   // utils/align.py:94-109, :186-191
             acc[MOM_SR] += r;
@@ -227,7 +232,8 @@ pair_moments_kernel(PairArgs a) {
         acc[MOM_SYX + 0] += wy0 * X0; acc[MOM_SYX + 1] += wy0 * X1; acc[MOM_SYX + 2] += wy0 * X2;
         acc[MOM_SYX + 3] += wy1 * X0; acc[MOM_SYX + 4] += wy1 * X1; acc[MOM_SYX + 5] += wy1 * X2;
         acc[MOM_SYX + 6] += wy2 * X0; acc[MOM_SYX + 7] += wy2 * X1; acc[MOM_SYX + 8] += wy2 * X2;
-        acc[MOM_SXX] += wx0 * X0 + wx1 * X1 + wx2 * X2;
+        acc[MOM_SXX + 0] += wx0 * X0; acc[MOM_SXX + 1] += wx0 * X1; acc[MOM_SXX + 2] += wx0 * X2;
+        acc[MOM_SXX + 3] += wx1 * X1; acc[MOM_SXX + 4] += wx1 * X2; acc[MOM_SXX + 5] += wx2 * X2;
         acc[MOM_WMAX] = fmax(acc[MOM_WMAX], w);
         acc[MOM_N] += 1.0;
     };
@@ -759,7 +765,7 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     WS_ALLOC(ctx, float, thr, n_pairs);
     WS_ALLOC(ctx, float, dscale, n_pairs);
     WS_ALLOC(ctx, PairState, state, n_pairs);
-    WS_ALLOC(ctx, double, eff, (size_t)n_pairs * overlap * 12);
+    WS_ALLOC(ctx, double, eff, (size_t)n_pairs * overlap * EFF_LEN);
     WS_ALLOC(ctx, float, gate, (size_t)n_pairs * 12);
     WS_ALLOC(ctx, double, partials, (size_t)n_pairs * n_tiles * MOM_LEN);
     WS_ALLOC(ctx, unsigned int, tickets, n_pairs);
@@ -839,11 +845,11 @@ __global__ void __launch_bounds__(PT_THREADS)
 points_moments_kernel(PointsArgs a) {
     __shared__ double red[PT_THREADS / 32][MOM_LEN];
     __shared__ bool is_last;
-    __shared__ double eff[12];
+    __shared__ double eff[EFF_LEN];
     __shared__ double cen[6];
     PairArgs& pa = a.pa;
     if (STAGE == 0 && pa.state[0].done) return;
-    if (threadIdx.x < 12 && pa.eff) eff[threadIdx.x] = pa.eff[threadIdx.x];
+    if (threadIdx.x < EFF_LEN && pa.eff) eff[threadIdx.x] = pa.eff[threadIdx.x];
     if (STAGE == 1 && threadIdx.x < 6) cen[threadIdx.x] = a.norm_state[threadIdx.x];
     __syncthreads();
     double acc[MOM_LEN];
@@ -869,9 +875,9 @@ points_moments_kernel(PointsArgs a) {
         if (a.weights) w = a.weights_f64 ? ((const double*)a.weights)[i] : (double)((const float*)a.weights)[i];
         if (a.irls) {
             w = (double)__fsqrt_rn(__fmul_rn(a.conf_dst[id], a.conf_src[is]));       // utils/align.py:166
-            double r0 = Y[0] - (eff[0] * X[0] + eff[1] * X[1] + eff[2] * X[2] + eff[9]);
-            double r1 = Y[1] - (eff[3] * X[0] + eff[4] * X[1] + eff[5] * X[2] + eff[10]);
-            double r2 = Y[2] - (eff[6] * X[0] + eff[7] * X[1] + eff[8] * X[2] + eff[11]);
+            double r0 = Y[0] + (eff[9] * X[0] + eff[10] * X[1] + eff[11] * X[2] + eff[18]);
+            double r1 = Y[1] + (eff[12] * X[0] + eff[13] * X[1] + eff[14] * X[2] + eff[19]);
+            double r2 = Y[2] + (eff[15] * X[0] + eff[16] * X[1] + eff[17] * X[2] + eff[20]);
             double r = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
             if (r > pa.huber_delta) w *= pa.huber_delta / r;
             acc[MOM_SR] += r;
@@ -884,7 +890,8 @@ points_moments_kernel(PointsArgs a) {
         acc[MOM_SYX + 0] += wy0 * X[0]; acc[MOM_SYX + 1] += wy0 * X[1]; acc[MOM_SYX + 2] += wy0 * X[2];
         acc[MOM_SYX + 3] += wy1 * X[0]; acc[MOM_SYX + 4] += wy1 * X[1]; acc[MOM_SYX + 5] += wy1 * X[2];
         acc[MOM_SYX + 6] += wy2 * X[0]; acc[MOM_SYX + 7] += wy2 * X[1]; acc[MOM_SYX + 8] += wy2 * X[2];
-        acc[MOM_SXX] += wx0 * X[0] + wx1 * X[1] + wx2 * X[2];
+        acc[MOM_SXX + 0] += wx0 * X[0]; acc[MOM_SXX + 1] += wx0 * X[1]; acc[MOM_SXX + 2] += wx0 * X[2];
+        acc[MOM_SXX + 3] += wx1 * X[1]; acc[MOM_SXX + 4] += wx1 * X[2]; acc[MOM_SXX + 5] += wx2 * X[2];
         acc[MOM_WMAX] = fmax(acc[MOM_WMAX], w);
         acc[MOM_N] += 1.0;
     }
@@ -965,7 +972,7 @@ points_moments_kernel(PointsArgs a) {
 static int points_common(da3s_ctx* ctx, PointsArgs& a, long long count, int huber, int variant, double delta,
                          int max_it, double tol, int min_points, double* row) {
     WS_ALLOC(ctx, PairState, state, 1);
-    WS_ALLOC(ctx, double, eff, 12);
+    WS_ALLOC(ctx, double, eff, EFF_LEN);
     WS_ALLOC(ctx, unsigned int, tickets, 1);
     long long nb = (count + PT_PER_BLOCK - 1) / PT_PER_BLOCK;
     if (nb < 1) nb = 1;

@@ -50,12 +50,16 @@ __device__ __forceinline__ void hist_add(unsigned int* hist, unsigned int digit,
 
 template <int PASS>
 __global__ void __launch_bounds__(SEL_THREADS)
-select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* __restrict__ state,
-                   unsigned int* __restrict__ ghist /* [n_segs][2][SEL_BINS] */,
-                   unsigned int* __restrict__ tickets, da3s_select_out* __restrict__ out) {
+select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* state,
+                   unsigned int* ghist /* [n_segs][2][SEL_BINS] */,
+                   unsigned int* tickets, da3s_select_out* out) {
     __shared__ unsigned int hist[2][SEL_BINS];
     __shared__ bool is_last;
     __shared__ long long scan_tot[SEL_THREADS];
+    __shared__ unsigned int new_prefix[2];
+    __shared__ long long new_rank[2];
+    __shared__ long long sh_rank[2];
+    __shared__ int sh_empty;
     const int seg_id = blockIdx.y;
     const da3s_select_seg seg = segs[seg_id];
     SelState st;
@@ -155,11 +159,11 @@ select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* __restric
                     }
                 } else { st.rank[0] = st.rank[1] = 0; }
                 state[seg_id].n_valid = st.n_valid; state[seg_id].empty = st.empty; state[seg_id].gamma = st.gamma;
-                state[seg_id].rank[0] = st.rank[0]; state[seg_id].rank[1] = st.rank[1];
+                sh_rank[0] = st.rank[0]; sh_rank[1] = st.rank[1]; sh_empty = st.empty;
             }
         }
         __syncthreads();
-        if (PASS == 0) { st.rank[0] = state[seg_id].rank[0]; st.rank[1] = state[seg_id].rank[1]; st.empty = state[seg_id].empty; }
+        if (PASS == 0) { st.rank[0] = sh_rank[0]; st.rank[1] = sh_rank[1]; st.empty = sh_empty; }
         __syncthreads();
         const long long want = st.rank[q];
         long long run = scan_tot[threadIdx.x];
@@ -169,8 +173,8 @@ select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* __restric
                 if (want >= run && want < run + loc[k]) {      // exactly one (thread, k) matches
                     unsigned int b = threadIdx.x * per + k;
                     unsigned int old = PASS == 0 ? 0u : st.prefix[q];
-                    state[seg_id].prefix[q] = (old << bits) | b;
-                    state[seg_id].rank[q] = want - run;
+                    new_prefix[q] = (old << bits) | b;
+                    new_rank[q] = want - run;
                 }
                 run += loc[k];
             }
@@ -179,10 +183,17 @@ select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* __restric
     }
     // clear the global histogram and the ticket for the next pass / next call
     for (int i = threadIdx.x; i < 2 * SEL_BINS; i += SEL_THREADS) gh[i] = 0;
-    if (threadIdx.x == 0) tickets[seg_id] = 0;
+    if (threadIdx.x == 0) {
+        tickets[seg_id] = 0;
+        if (!st.empty) {                                       // thread 0 alone publishes the narrowed state
+            state[seg_id].prefix[0] = new_prefix[0]; state[seg_id].prefix[1] = new_prefix[1];
+            state[seg_id].rank[0] = new_rank[0];     state[seg_id].rank[1] = new_rank[1];
+        }
+    }
     if (PASS == 2 && threadIdx.x == 0) {
-        __threadfence();
-        SelState f = state[seg_id];
+        SelState f;
+        f.prefix[0] = new_prefix[0]; f.prefix[1] = new_prefix[1];
+        f.n_valid = st.n_valid; f.gamma = st.gamma; f.empty = st.empty;
         da3s_select_out o;
         o.n_valid = f.n_valid;
         o.gamma = f.gamma;

@@ -8,10 +8,12 @@
 //   [1..3]   Sx  = sum w x
 //   [4..6]   Sy  = sum w y
 //   [7..15]  Syx = sum w y x^T   (row-major, Syx[i][j] = sum w y_i x_j)
-//   [16]     Sxx = sum w |x|^2
-//   [17]     Sr  = sum residual (diagnostic, IRLS only)
-//   [18]     wmax (max weight; combined with max, not +)
-//   [19]     n   (count, exact in float64)
+//   [16..21] Sxx = sum w x x^T   (symmetric: xx, xy, xz, yy, yz, zz).  The full matrix, not
+//            just its trace, so that the move to world coordinates is exact for ANY
+//            camera-to-world matrix (float32 rotations are orthonormal only to ~6e-8)
+//   [22]     Sr  = sum residual (diagnostic, IRLS only)
+//   [23]     wmax (max weight; combined with max, not +)
+//   [24]     n   (count, exact in float64)
 #pragma once
 
 #include <math.h>
@@ -27,10 +29,11 @@
 #define MOM_SY 4
 #define MOM_SYX 7
 #define MOM_SXX 16
-#define MOM_SR 17
-#define MOM_WMAX 18
-#define MOM_N 19
-#define MOM_LEN 20
+#define MOM_SR 22
+#define MOM_WMAX 23
+#define MOM_N 24
+#define MOM_LEN 25
+#define EFF_LEN 21          // per (pair, frame): By[9] | Bx[9] | c[3];  residual = By y + Bx x + c
 
 HD double det3(const double* M) {
     return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) +
@@ -162,7 +165,7 @@ HD bool umeyama_from_moments(const double* mom, double wscale, int variant, doub
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j)
             cov[3 * i + j] = (mom[MOM_SYX + 3 * i + j] / wscale - my[i] * Sx[j] - Sy[i] * mx[j] + S0 * my[i] * mx[j]) / den;
-    double var = (mom[MOM_SXX] / wscale - 2.0 * (mx[0] * Sx[0] + mx[1] * Sx[1] + mx[2] * Sx[2]) +
+    double var = ((mom[MOM_SXX] + mom[MOM_SXX + 3] + mom[MOM_SXX + 5]) / wscale - 2.0 * (mx[0] * Sx[0] + mx[1] * Sx[1] + mx[2] * Sx[2]) +
                   S0 * (mx[0] * mx[0] + mx[1] * mx[1] + mx[2] * mx[2])) / den;
     double U[9], Sg[3], V[9];
     svd3(cov, U, Sg, V);
@@ -194,10 +197,9 @@ HD bool umeyama_from_moments(const double* mom, double wscale, int variant, doub
     return true;
 }
 
-// Raw camera-frame moments of one overlap frame -> world-frame moments, using the two
-// frames' camera-to-world transforms x_w = Mx x + mx, y_w = My y + my (rotations assumed
-// orthonormal, as the closed-form inverse of src/vggt/utils/geometry.py:119-168 does), and
-// ADD them into `acc`.  Linear in the moments, so exact up to float64 rounding.
+// Raw camera-frame moments of one overlap frame -> world-frame moments under the two frames'
+// camera-to-world maps x_w = Mx x + mx, y_w = My y + my, ADDED into `acc`.  Every moment is a
+// polynomial in the points, so this is exact (up to float64 rounding) for any affine map.
 HD void moments_to_world_add(const double* m, const double* c2w_x, const double* c2w_y, double* acc) {
     double Mx[9], My[9], tx[3], ty[3];
     for (int i = 0; i < 3; ++i) {
@@ -220,28 +222,33 @@ HD void moments_to_world_add(const double* m, const double* c2w_x, const double*
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j)
             acc[MOM_SYX + 3 * i + j] += T2[3 * i + j] + MSy[i] * tx[j] + ty[i] * MSx[j] + S0 * ty[i] * tx[j];
-    acc[MOM_SXX] += m[MOM_SXX] + 2.0 * (tx[0] * MSx[0] + tx[1] * MSx[1] + tx[2] * MSx[2]) +
-                    S0 * (tx[0] * tx[0] + tx[1] * tx[1] + tx[2] * tx[2]);
+    // sum w x_w x_w^T = Mx Sxx Mx^T + (Mx Sx) mx^T + mx (Mx Sx)^T + S0 mx mx^T
+    const double* q = &m[MOM_SXX];
+    double Sm[9] = {q[0], q[1], q[2], q[1], q[3], q[4], q[2], q[4], q[5]};
+    mat3_mul(Mx, Sm, T1);
+    mat3_mul_bt(T1, Mx, T2);
+    int idx = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j)
+            acc[MOM_SXX + idx++] += T2[3 * i + j] + MSx[i] * tx[j] + tx[i] * MSx[j] + S0 * tx[i] * tx[j];
     acc[MOM_SR] += m[MOM_SR];
     acc[MOM_WMAX] = fmax(acc[MOM_WMAX], m[MOM_WMAX]);
     acc[MOM_N] += m[MOM_N];
 }
 
-// Effective camera-frame transform of one overlap frame under the world Sim(3) (s,R,t):
-// |y_w - (s R x_w + t)| = |y - (A x + b)|  with A = My^T (sR) Mx, b = My^T (sR mx + t - my).
-HD void effective_cam_transform(double s, const double* R, const double* t,
-                                const double* c2w_x, const double* c2w_y, double* A, double* b) {
-    double Mx[9], My[9], tx[3], ty[3], sR[9];
+// Residual of one overlap frame under the world Sim(3) (s,R,t), evaluated from CAMERA-frame
+// points:  r_w = y_w - (s R x_w + t) = By y + Bx x + c  with  By = My, Bx = -s R Mx,
+// c = my - s R mx - t.  Exact for any camera-to-world matrices.
+HD void effective_residual_transform(double s, const double* R, const double* t,
+                                     const double* c2w_x, const double* c2w_y, double* eff) {
+    double Mx[9], tx[3], sR[9];
     for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) { Mx[3 * i + j] = c2w_x[4 * i + j]; My[3 * i + j] = c2w_y[4 * i + j]; sR[3 * i + j] = s * R[3 * i + j]; }
+        for (int j = 0; j < 3; ++j) { Mx[3 * i + j] = c2w_x[4 * i + j]; eff[3 * i + j] = c2w_y[4 * i + j]; sR[3 * i + j] = s * R[3 * i + j]; }
         tx[i] = c2w_x[4 * i + 3];
-        ty[i] = c2w_y[4 * i + 3];
     }
-    double T1[9];
+    double T1[9], v[3];
     mat3_mul(sR, Mx, T1);
-    mat3_tmul(My, T1, A);
-    double v[3];
+    for (int k = 0; k < 9; ++k) eff[9 + k] = -T1[k];
     mat3_vec(sR, tx, v);
-    for (int i = 0; i < 3; ++i) v[i] += t[i] - ty[i];
-    mat3_tvec(My, v, b);
+    for (int i = 0; i < 3; ++i) eff[18 + i] = c2w_y[4 * i + 3] - v[i] - t[i];
 }

@@ -126,7 +126,7 @@ template <int MODE, typename OutT, bool VEC>
 __global__ void __launch_bounds__(K1_THREADS)
 unproject_filter_kernel(K1Args a) {
     __shared__ UnprojFrame fr;
-    __shared__ float stage[VEC ? (K1_THREADS / 32) * 32 * 12 : 1];     // per-warp staging for f32 xyz
+    __shared__ __align__(16) float stage[VEC ? (K1_THREADS / 32) * 32 * 12 : 4];     // per-warp staging for f32 xyz
     __shared__ unsigned int blk_kept;
     const int frame = blockIdx.y;
     const bool world = a.flags & DA3S_UNPROJ_WORLD;

@@ -276,8 +276,9 @@ def ransac_score(pairs, n_pairs, overlap, H, W, thr, ds, A, t, ok, ransac_thr, *
     ctx = context(dev)
     n_hyp = A.shape[1]
     counts = torch.empty((n_pairs, n_hyp), dtype=torch.int32, device=dev)
+    A, t, ok = A.contiguous(), t.contiguous(), ok.contiguous()      # named: must outlive the launch
     rc = ctx.lib.da3s_ransac_score(ctx.h, _ptr(pairs), n_pairs, overlap, H, W, int(world), int(valid_depth), depth_eps,
-                                   _ptr(thr), _ptr(ds), _ptr(A.contiguous()), _ptr(t.contiguous()), _ptr(ok.contiguous()),
+                                   _ptr(thr), _ptr(ds), _ptr(A), _ptr(t), _ptr(ok),
                                    n_hyp, float(ransac_thr), _ptr(counts), _stream(pairs))
     L.check(rc, "da3s_ransac_score")
     return counts
@@ -288,9 +289,10 @@ def ransac_inlier_mask(pairs, n_pairs, overlap, H, W, thr, ds, best_A, best_t, b
     dev = pairs.device
     ctx = context(dev)
     mask = torch.empty((n_pairs, overlap * H * W), dtype=torch.uint8, device=dev)
+    best_A, best_t, best_ok = best_A.contiguous(), best_t.contiguous(), best_ok.contiguous()   # must outlive the launch
     rc = ctx.lib.da3s_ransac_inlier_mask(ctx.h, _ptr(pairs), n_pairs, overlap, H, W, int(world), int(valid_depth), depth_eps,
-                                         _ptr(thr), _ptr(ds), _ptr(best_A.contiguous()), _ptr(best_t.contiguous()),
-                                         _ptr(best_ok.contiguous()), float(ransac_thr), _ptr(mask), _stream(pairs))
+                                         _ptr(thr), _ptr(ds), _ptr(best_A), _ptr(best_t),
+                                         _ptr(best_ok), float(ransac_thr), _ptr(mask), _stream(pairs))
     L.check(rc, "da3s_ransac_inlier_mask")
     return mask.view(torch.bool)
 
@@ -333,9 +335,10 @@ def irls_points(src, dst, conf_src, conf_dst, idx_src=None, idx_dst=None, delta=
         idx_src = idx_src.to(torch.int64).contiguous()
         idx_dst = idx_dst.to(torch.int64).contiguous()
         n_idx = idx_src.numel()
+    conf_src, conf_dst = conf_src.contiguous(), conf_dst.contiguous()
     rc = ctx.lib.da3s_irls_points(ctx.h, _ptr(src), _ptr(dst), int(src.dtype == torch.float64),
-                                  _ptr(conf_src.contiguous(), "conf_src", torch.float32),
-                                  _ptr(conf_dst.contiguous(), "conf_dst", torch.float32), n, _ptr(idx_src), _ptr(idx_dst),
+                                  _ptr(conf_src, "conf_src", torch.float32),
+                                  _ptr(conf_dst, "conf_dst", torch.float32), n, _ptr(idx_src), _ptr(idx_dst),
                                   n_idx, float(delta), int(max_iterations), float(tol), _ptr(row), _stream(src))
     L.check(rc, "da3s_irls_points")
     return row
@@ -363,7 +366,9 @@ def voxel_downsample(clouds, voxel: float, table_slots: int | None = None, max_v
         xyz = xyz.contiguous().view(-1, 3)
         if mask is not None:
             mask = mask.contiguous().view(-1).view(torch.uint8)
-        rc = ctx.lib.da3s_voxel_insert(ctx.h, _ptr(xyz, "xyz", torch.float32), _ptr(rgb.contiguous() if rgb is not None else None),
+        if rgb is not None:
+            rgb = rgb.contiguous()
+        rc = ctx.lib.da3s_voxel_insert(ctx.h, _ptr(xyz, "xyz", torch.float32), _ptr(rgb),
                                        _ptr(mask), xyz.shape[0], float(voxel), st)
         L.check(rc, "da3s_voxel_insert")
     out_xyz = torch.empty((max_voxels, 3), dtype=torch.float32, device=dev)
