@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py — submap-alignment hot path on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c3vd300|seq2000|loop512|hires]
+    python bench.py --impl reference ...      # the CPU arm (oracle port on the host cores)
+
+One STEP = one pass of the whole hot path over one synthetic submap sequence already
+resident in HBM (da3slam_b200.pipeline.SequencePlan.run): exact-median thresholds -> [RANSAC]
+-> IRLS Umeyama per consecutive submap pair -> Sim(3) chain -> per-submap confidence
+percentile -> unproject + Sim(3) + filter -> voxel-grid downsample.  Metric: submap pairs
+aligned per second (whole job, all ranks); points/s is reported next to it.
+
+N > 1 (torchrun): every rank owns its own sequence (weak scaling, no data-path collective);
+only the Sim(3) rows are exchanged (one all_gather over NCCL) inside the timed step.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: 300 frames, 16-frame submaps (solver.py deque semantics -> 19 submaps / 18 pairs)
+    "c3vd300": dict(n_submaps=19, frames=16, H=518, W=518, overlap=1, n_hyp=0, outlier=0.0, export=True,
+                    table_slots=1 << 25, voxel=0.02, desc="300 frames, 19 submaps x 16 x 518x518, 18 pairs"),
+    # configs[2]: 2000 frames, 32-frame submaps, RANSAC 1024 hypotheses (make_image_chunks -> 65 submaps / 64 pairs)
+    "seq2000": dict(n_submaps=65, frames=32, H=518, W=518, overlap=1, n_hyp=1024, outlier=0.3, export=True,
+                    table_slots=1 << 27, voxel=0.02, desc="2000 frames, 65 submaps x 32 x 518x518, 64 pairs, RANSAC 1024"),
+    # configs[3]: 512 independent loop-candidate pairs (2-frame submaps, so every pair reads distinct frames)
+    "loop512": dict(n_submaps=513, frames=2, H=518, W=518, overlap=1, n_hyp=0, outlier=0.0, export=False,
+                    table_slots=0, voxel=0.02, desc="512 submap pairs, 518x518, 1 overlap frame, alignment only"),
+    # configs[4]: 1036x1036, 64-frame submaps + global voxel map
+    "hires": dict(n_submaps=8, frames=64, H=1036, W=1036, overlap=1, n_hyp=0, outlier=0.0, export=True,
+                  table_slots=1 << 27, voxel=0.02, desc="8 submaps x 64 x 1036x1036, 7 pairs, voxel map"),
+    # tiny case for CI / smoke runs of this script
+    "tiny": dict(n_submaps=4, frames=4, H=64, W=80, overlap=1, n_hyp=0, outlier=0.0, export=True,
+                 table_slots=1 << 16, voxel=0.05, desc="4 submaps x 4 x 64x80"),
+}
+RANSAC_THR = 0.02
+CONF_PERCENTILE = 65.0          # viewer.py:86-88 default slider value
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy, reference algorithm) on the host cores
+# --------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_pair(k):
+    from oracle import spec_port as sp
+    subs, w = _CPU["subs"], _CPU["w"]
+    ransac = None
+    if w["n_hyp"] > 0:
+        rng = np.random.default_rng(1000 + k)
+        ransac = dict(sample_idx=rng.integers(0, w["H"] * w["W"] * w["overlap"], size=(w["n_hyp"], 3)), thr=RANSAC_THR)
+    t0 = time.perf_counter()
+    if ransac is None:
+        out = sp.align_pair(subs[k], subs[k + 1], overlap=w["overlap"], world=True)
+    else:
+        # same stages as spec_port.align_pair, with the C restatement doing the float32-FMA scoring
+        corr = sp.pair_correspondences(subs[k], subs[k + 1], w["overlap"], True)
+        xs, ys = sp.ransac_points(corr, True)
+        A, T, ok, _ = sp.ransac_hypotheses(xs, ys, corr["mask"], ransac["sample_idx"])
+        counts = sp.ransac_score_c(A, T, ok, xs, ys, corr["mask"], RANSAC_THR)
+        best, _ = sp.ransac_best(counts, ok)
+        mask = sp.ransac_inlier_mask_c(A, T, best, xs, ys, corr["mask"], RANSAC_THR)
+        s, R, t, info = sp.irls_dense(corr["x"], corr["y"], corr["c"], mask)
+        out = dict(s=s, R=R, t=t)
+    return time.perf_counter() - t0, float(out["s"])
+
+
+def _cpu_submap(k):
+    """Reference-style export of one submap: float64 unprojection (utils/geometry.py:4-40), Sim(3)
+    (utils/geometry.py:43-70), percentile-of-positive-confidence filter (viewer.py:333-336), voxel grid."""
+    from oracle import ref_port as rp
+    from oracle import spec_port as sp
+    sub, w = _CPU["subs"][k], _CPU["w"]
+    t0 = time.perf_counter()
+    world = rp.unproject_world_f64(sub["depth"], sub["intrinsics"], sub["extrinsics"])
+    world = rp.apply_sim3(world, 1.1, np.eye(3), np.array([0.1, 0.2, 0.3]))
+    conf = sub["conf"].reshape(-1)
+    mask, _ = rp.viewer_conf_mask(conf, CONF_PERCENTILE)
+    mask &= (sub["depth"].reshape(-1) > 1e-6)
+    sp.voxel_downsample(world.reshape(-1, 3).astype(np.float32), w["voxel"], None, mask)
+    return time.perf_counter() - t0, int(mask.sum())
+
+
+def cpu_arm(w, budget_s=20.0, max_workers=None):
+    """Times a bounded sample of the workload on the host cores (one process per unit, fork)."""
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    from da3slam_b200 import synth
+    cores = os.cpu_count() or 1
+    workers = max(1, min(max_workers or cores, cores))
+    n_pairs_total = w["n_submaps"] - 1
+    n_sample = max(2, min(w["n_submaps"], 5 if w["H"] <= 600 else 3))
+    subs, _ = synth.make_sequence(n_sample, w["frames"], w["H"], w["W"], w["overlap"], seed=4321, outlier_ratio=w["outlier"])
+    _CPU["subs"], _CPU["w"] = subs, w
+    pair_ids = list(range(n_sample - 1))
+    sub_ids = list(range(n_sample)) if w["export"] else []
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=min(workers, len(pair_ids)), mp_context=ctx) as ex:
+        pair_res = list(ex.map(_cpu_pair, pair_ids))
+    wall_pairs = time.perf_counter() - t0
+    wall_subs, sub_res = 0.0, []
+    if sub_ids:
+        t0 = time.perf_counter()
+        with ProcessPoolExecutor(max_workers=min(workers, len(sub_ids)), mp_context=ctx) as ex:
+            sub_res = list(ex.map(_cpu_submap, sub_ids))
+        wall_subs = time.perf_counter() - t0
+    used = max(min(workers, len(pair_ids)), min(workers, len(sub_ids)) if sub_ids else 1)
+    # throughput with `workers` processes: units of the sample / wall; scale to the whole step
+    per_pair_wall = wall_pairs / len(pair_ids)
+    per_sub_wall = wall_subs / len(sub_ids) if sub_ids else 0.0
+    # with W workers the whole job takes ceil(units / W) rounds of the measured per-unit latency
+    lat_pair = float(np.mean([r[0] for r in pair_res]))
+    lat_sub = float(np.mean([r[0] for r in sub_res])) if sub_res else 0.0
+    rounds_p = -(-n_pairs_total // workers)
+    rounds_s = -(-w["n_submaps"] // workers) if sub_ids else 0
+    step_s = rounds_p * lat_pair + rounds_s * lat_sub
+    return dict(step_s=step_s, pairs_per_s=n_pairs_total / step_s, cores=workers, host_cores=cores, used=used,
+                lat_pair_s=lat_pair, lat_submap_s=lat_sub, wall_pairs_s=wall_pairs, wall_submaps_s=wall_subs,
+                per_pair_wall_s=per_pair_wall, per_submap_wall_s=per_sub_wall,
+                sample=f"{len(pair_ids)} pairs + {len(sub_ids)} submap exports of the workload's shape, one process per unit "
+                       f"({workers} workers available); step time extrapolated as ceil(units/workers) x per-unit latency")
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, torch copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def gpu_arm(args, w, rank, world):
+    import torch
+    import torch.distributed as dist
+    from da3slam_b200 import ops, synth
+    from da3slam_b200.pipeline import DeviceSubmap, SequencePlan
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs CUDA: the alignment path has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic sequence of this rank, resident in HBM ----
+    subs, gt = synth.make_sequence_device(w["n_submaps"], w["frames"], w["H"], w["W"], w["overlap"], seed=1234 + 1000 * rank,
+                                          outlier_ratio=w["outlier"], with_images=w["export"], device=dev)
+    dsubs = [DeviceSubmap.from_prediction(s, dev) for s in subs]
+    n_pairs = w["n_submaps"] - 1
+    M = w["overlap"] * w["H"] * w["W"]
+    sample_idx = None
+    opt = dict(world=1)
+    if w["n_hyp"] > 0:
+        rng = np.random.default_rng(99 + rank)
+        sample_idx = torch.from_numpy(rng.integers(0, M, size=(n_pairs, w["n_hyp"], 3)).astype(np.int32))
+        opt.update(n_hyp=w["n_hyp"], ransac_thr=RANSAC_THR)
+    plan = SequencePlan(dsubs, overlap=w["overlap"], voxel=w["voxel"], conf_percentile=CONF_PERCENTILE,
+                        table_slots=w["table_slots"] or None, sample_idx=sample_idx, export=w["export"], **opt)
+    ctx = ops.context(dev)
+    gathered = [torch.empty((n_pairs, 16), dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+
+    stage_names = []
+
+    def run_step(events):
+        def mark(name):
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append((name, e))
+        mark("start")
+        plan.run(mark)
+        if world > 1:                                   # the only exchange: Sim(3) rows over NCCL/NVLink
+            dist.all_gather(gathered, plan.rows)
+            mark("allgather")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        run_step(None)
+    barrier()
+    check = plan.read()                                 # raises if the voxel table overflowed
+    rows0 = check["rows"]
+    err_s = float(np.max([abs(rows0[k, 0] - gt[k][0]) / gt[k][0] for k in range(n_pairs)]))
+    iters = rows0[:, 14]
+    n_vox = int(check["voxel_key"].shape[0]) if w["export"] else 0
+
+    # ---- timed region: device-resident inputs ----
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launches
+    all_events = []
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        ev = []
+        run_step(ev)
+        all_events.append(ev)
+    t_end.record()
+    barrier()
+    launches = ctx.launches - launches0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    clock_info = clocks.stop() if clocks else None
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+    ms_per_step = elapsed_ms / args.steps
+    stages = {}
+    for ev in all_events:
+        for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
+            stages[n1] = stages.get(n1, 0.0) + e0.elapsed_time(e1) / args.steps
+
+    # ---- end-to-end: host buffers in, results out, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        h2d = 0
+        for s in subs:
+            hp = {}
+            for k in ("depth", "conf", "processed_images"):
+                if k in s:
+                    hp[k] = torch.empty(s[k].shape, dtype=s[k].dtype, pin_memory=True)
+                    hp[k].copy_(s[k])
+                    h2d += hp[k].numel() * hp[k].element_size()
+            host.append(hp)
+        torch.cuda.synchronize()
+        rows_host = torch.empty((n_pairs, 16), dtype=torch.float64, pin_memory=True)
+        d2h = rows_host.numel() * 8
+        vox_host = None
+        if w["export"]:
+            vox_host = (torch.empty((plan.grid.max_voxels, 3), dtype=torch.float32, pin_memory=True),
+                        torch.empty((plan.grid.max_voxels, 3), dtype=torch.uint8, pin_memory=True),
+                        torch.empty((plan.grid.max_voxels,), dtype=torch.int32, pin_memory=True))
+
+        def e2e_step():
+            nonlocal d2h
+            for hp, sm in zip(host, dsubs):
+                sm.depth.copy_(hp["depth"], non_blocking=True)
+                sm.conf.copy_(hp["conf"], non_blocking=True)
+                if sm.images is not None:
+                    sm.images.copy_(hp["processed_images"], non_blocking=True)
+            plan.run(None)
+            rows_host.copy_(plan.rows, non_blocking=True)
+            moved = rows_host.numel() * 8
+            if w["export"]:
+                nv = int(plan.grid.nv[0].item())               # sync: the size of the result
+                vox_host[0][:nv].copy_(plan.grid.xyz[:nv], non_blocking=True)
+                if plan.grid.rgb is not None:
+                    vox_host[1][:nv].copy_(plan.grid.rgb[:nv], non_blocking=True)
+                vox_host[2][:nv].copy_(plan.grid.count[:nv], non_blocking=True)
+                moved += nv * (12 + 3 + 4) + 16
+            torch.cuda.synchronize()
+            d2h = moved
+
+        for _ in range(max(1, min(2, args.warmup))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        k_e2e = max(1, min(args.steps, 5))
+        for _ in range(k_e2e):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / k_e2e
+        if world > 1:
+            tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.item())
+        e2e = {"value": world * n_pairs / e2e_s, "unit": "submap-pairs/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": k_e2e,
+               "api": "SequencePlan.run on pinned host predictions (torch H2D/D2H on the same stream)"}
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peaks()
+    P = w["H"] * w["W"]
+    px_export = plan.points_per_step
+    single = {}
+    if w["export"]:
+        single["unproject"] = ("unproject_filter_kernel<FAST,float,vec>", 21.0 * px_export, w["n_submaps"],
+                               "21 B/pixel (4 depth + 4 conf read, 12 xyz + 1 mask written)")
+        single["voxel_insert"] = ("voxel_insert_kernel", (12.0 + 1.0 + 3.0) * px_export, w["n_submaps"],
+                                  "16 B/point read (12 xyz + 3 rgb + 1 mask); hash-table traffic not counted")
+        single["voxel_clear"] = ("voxel_clear_kernel", 64.0 * plan.grid.table_slots, 1, "64 B/slot written")
+        single["voxel_compact"] = ("voxel_compact_kernel", 64.0 * plan.grid.table_slots, 1, "64 B/slot read")
+    passes = float(np.sum(iters))
+    align_bytes = (passes * 16.0 + 3 * 8.0) * M + (w["n_hyp"] > 0) * n_pairs * 16.0 * M
+    single["align"] = ("pair_moments_kernel (+select, +RANSAC)", align_bytes, 1,
+                       "16 B/correspondence per IRLS pass x executed passes + 3 x 8 B select passes; whole align stage timed")
+    dom = max(single, key=lambda k: stages.get(k, 0.0))
+    kname, bytes_per_step, n_launch, note = single[dom]
+    dur_ms = stages.get(dom, 0.0)
+    achieved = bytes_per_step / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": kname, "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_step / n_launch, "launches_per_step": n_launch,
+                "avg_launch_ms": dur_ms / n_launch, "stage_share_of_step": dur_ms / ms_per_step, "note": note}
+    per_stage = {}
+    for k, (kn, b, nl, _) in single.items():
+        if stages.get(k, 0) > 0:
+            per_stage[k] = {"ms": stages[k], "GB/s": b / (stages[k] * 1e-3) / 1e9, "frac_of_peak": b / (stages[k] * 1e-3) / 1e9 / peak}
+
+    out = {
+        "metric": "submap_pairs_aligned_per_sec", "value": world * n_pairs / (ms_per_step * 1e-3), "unit": "submap-pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "frames_per_submap": w["frames"], "H": w["H"], "W": w["W"],
+                   "overlap": w["overlap"], "pairs_per_gpu": n_pairs, "n_hyp": w["n_hyp"], "voxel": w["voxel"],
+                   "conf_percentile": CONF_PERCENTILE, "irls": "huber delta=1.0, <=20 it, tol 1e-6 (utils/align.py defaults)",
+                   "l2": f"inputs {sum(s['depth'].numel() * 8 for s in subs) / 1e6:.0f} MB per GPU vs 126 MB L2; no explicit flush",
+                   "parallelism": f"pairs sharded, {world} rank(s), Sim(3) rows all_gather only"},
+        "points_per_sec": world * px_export / (ms_per_step * 1e-3) if w["export"] else None,
+        "pixels_per_step_per_gpu": px_export, "voxels_out": n_vox,
+        "stages_ms": stages, "stage_bandwidth": per_stage,
+        "accuracy": {"max_rel_scale_error_vs_ground_truth": err_s, "irls_iterations_mean": float(np.mean(iters))},
+        "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3vd300", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-workers", type=int, default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        vals, info = [], None
+        for _ in range(max(0, args.warmup)):
+            cpu_arm(w, max_workers=args.cpu_workers)
+        for _ in range(max(1, args.steps)):
+            info = cpu_arm(w, max_workers=args.cpu_workers)
+            vals.append(info["pairs_per_s"])
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": "submap_pairs_aligned_per_sec", "value": v, "unit": "submap-pairs/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["step_s"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "desc": w["desc"]},
+                "cpu_baseline": {"value": v, "unit": "submap-pairs/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                                 "per_pair_latency_s": info["lat_pair_s"], "per_submap_export_latency_s": info["lat_submap_s"]},
+                "e2e": {"value": v, "unit": "submap-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_arm(w, max_workers=args.cpu_workers)           # before CUDA is initialised (fork-safe)
+    out = gpu_arm(args, w, rank, world)
+    if out is None:
+        return 0
+    if cpu is not None:
+        out["cpu_baseline"] = {"value": cpu["pairs_per_s"], "unit": "submap-pairs/s", "cores": cpu["cores"], "kind": "port",
+                               "sample": cpu["sample"], "per_pair_latency_s": cpu["lat_pair_s"],
+                               "per_submap_export_latency_s": cpu["lat_submap_s"], "host_cores": cpu["host_cores"],
+                               "step_s_extrapolated": cpu["step_s"]}
+    else:
+        out["cpu_baseline"] = None
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

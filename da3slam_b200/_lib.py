@@ -71,6 +71,7 @@ SIGNATURES = {
     "da3s_select": (_I, [_P, _P, _I, _L, _P, _P]),
     "da3s_align_opts_default": (None, [C.POINTER(AlignOpts)]),
     "da3s_align_pairs": (_I, [_P, _P, _I, _I, _I, _I, C.POINTER(AlignOpts), _P, _P, _P, _P, _P]),
+    "da3s_accumulate_sim3": (_I, [_P, _P, _I, _P, _P]),
     "da3s_pair_thresholds": (_I, [_P, _P, _I, _I, _I, _I, C.POINTER(AlignOpts), _P, _P, _P, _P]),
     "da3s_ransac_score": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "da3s_ransac_hypotheses": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _P, _P, _P, _P, _P]),

@@ -1048,3 +1048,37 @@ extern "C" int da3s_irls_points(da3s_ctx* ctx, const void* src, const void* dst,
     }
     return DA3S_OK;
 }
+
+// ---------------------------------------------------------------------------------
+// Sim(3) chain (utils/geometry.py:73-119): n tiny compositions, one thread.
+// ---------------------------------------------------------------------------------
+__global__ void accumulate_sim3_kernel(const double* __restrict__ rows, int n, double* __restrict__ cum) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double s = 1.0, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
+    cum[0] = s;
+    for (int k = 0; k < 9; ++k) cum[1 + k] = R[k];
+    for (int k = 0; k < 3; ++k) cum[10 + k] = t[k];
+    for (int i = 0; i < n; ++i) {
+        const double* r = rows + (size_t)i * DA3S_ROW_LEN;
+        const double sn = r[DA3S_ROW_S];
+        const double* Rn = r + DA3S_ROW_R;
+        const double* tn = r + DA3S_ROW_T;
+        double Rt[3], R2[9];
+        mat3_vec(R, tn, Rt);                              // t' = s_prev (R_prev t_next) + t_prev
+        for (int k = 0; k < 3; ++k) t[k] = s * Rt[k] + t[k];
+        mat3_mul(R, Rn, R2);                              // R' = R_prev R_next
+        for (int k = 0; k < 9; ++k) R[k] = R2[k];
+        s = s * sn;                                       // s' = s_prev s_next
+        double* o = cum + (size_t)(i + 1) * 13;
+        o[0] = s;
+        for (int k = 0; k < 9; ++k) o[1 + k] = R[k];
+        for (int k = 0; k < 3; ++k) o[10 + k] = t[k];
+    }
+}
+
+extern "C" int da3s_accumulate_sim3(da3s_ctx* ctx, const double* rows, int n_rows, double* cum, void* stream) {
+    if (!ctx || !cum || n_rows < 0 || (n_rows > 0 && !rows)) return DA3S_EINVAL;
+    accumulate_sim3_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rows, n_rows, cum);
+    DA3S_LAUNCH_CHECK(ctx);
+    return DA3S_OK;
+}

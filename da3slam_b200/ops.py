@@ -96,8 +96,9 @@ def build_cams(intrinsics: torch.Tensor, extrinsics: torch.Tensor, general_inver
 # ------------------------------------------------------------------------------------------
 def unproject_filter(depth, conf, cams, *, mode="closed", world=False, out_f64=False, conf_cmp=None,
                      conf_thr=0.0, conf_thr_dev=None, conf_floor=None, depth_eps=None, world_z=False,
-                     sim3=None, want_mask=True, want_count=True):
-    """depth [N,H,W] f32 (+ conf) -> (xyz [N,H,W,3], mask [N,H,W] bool or None, n_kept tensor or None)."""
+                     sim3=None, want_mask=True, want_count=True, xyz_out=None, mask_out=None):
+    """depth [N,H,W] f32 (+ conf) -> (xyz [N,H,W,3], mask [N,H,W] bool or None, n_kept tensor or None).
+    xyz_out / mask_out (uint8) may be preallocated buffers of the right shape."""
     depth = depth.contiguous()
     N, H, W = depth.shape
     ctx = context(depth.device)
@@ -126,8 +127,10 @@ def unproject_filter(depth, conf, cams, *, mode="closed", world=False, out_f64=F
             flags |= L.SIM3_PER_FRAME
         else:
             assert s3.shape == (13,)
-    xyz = torch.empty((N, H, W, 3), dtype=torch.float64 if out_f64 else torch.float32, device=depth.device)
-    mask = torch.empty((N, H, W), dtype=torch.uint8, device=depth.device) if want_mask else None
+    xyz = xyz_out if xyz_out is not None else torch.empty((N, H, W, 3), dtype=torch.float64 if out_f64 else torch.float32,
+                                                          device=depth.device)
+    assert xyz.numel() == N * H * W * 3 and xyz.dtype == (torch.float64 if out_f64 else torch.float32)
+    mask = mask_out if mask_out is not None else (torch.empty((N, H, W), dtype=torch.uint8, device=depth.device) if want_mask else None)
     cnt = torch.zeros((1,), dtype=torch.int64, device=depth.device) if want_count else None
     rc = ctx.lib.da3s_unproject_filter(
         ctx.h, _ptr(depth, "depth", torch.float32), _ptr(conf, "conf", torch.float32), _ptr(cams, "cams"), N, H, W, flags,
@@ -164,11 +167,57 @@ def apply_sim3(points: torch.Tensor, sim3: torch.Tensor, out_f64: bool | None = 
 # ------------------------------------------------------------------------------------------
 # exact selection
 # ------------------------------------------------------------------------------------------
+SELECT_OUT_BYTES = C.sizeof(L.SelectOut)
+SELECT_VALUE_OFFSET = L.SelectOut.value.offset
+
+
 def select(segments, device):
     """segments: list of dicts(a=tensor, [b, ca, cb], kind, stat, percent, conf_th, eps).
     Returns a structured numpy array (n_valid, lo, hi, value, gamma) — this helper
-    synchronises; the pair pipeline uses the device-side entry instead."""
+    synchronises; select_async and the pair pipeline do not."""
+    host = select_async(segments, device).cpu().numpy()
+    dt = np.dtype([("n_valid", np.int64), ("lo", np.float32), ("hi", np.float32), ("value", np.float32), ("gamma", np.float32)])
+    return host.view(dt).reshape(len(segments))
+
+
+def select_value_view(d_out: torch.Tensor) -> torch.Tensor:
+    """[n] float32 strided view of the `value` field of a select_async result (stays on device)."""
+    return d_out.view(torch.float32).view(d_out.shape[0], SELECT_OUT_BYTES // 4)[:, SELECT_VALUE_OFFSET // 4]
+
+
+class SelectPlan:
+    """A prebuilt device segment table: run() only enqueues the three selection passes."""
+
+    def __init__(self, segments, device):
+        self.device = device
+        self.n = len(segments)
+        self.d_segs, self.max_n, self._keep = _build_segs(segments, device)
+        self.out = torch.empty((self.n, SELECT_OUT_BYTES), dtype=torch.uint8, device=device)
+
+    def run(self) -> torch.Tensor:
+        ctx = context(self.device)
+        rc = ctx.lib.da3s_select(ctx.h, _ptr(self.d_segs), self.n, self.max_n, _ptr(self.out), _stream(self.d_segs))
+        L.check(rc, "da3s_select")
+        return self.out
+
+    def value_ptr_tensor(self, i) -> torch.Tensor:
+        """1-element float32 view of record i's `value` — pass as conf_thr_dev."""
+        return select_value_view(self.out)[i:i + 1]
+
+
+def select_async(segments, device) -> torch.Tensor:
+    """Same as select() but returns the raw device records [n, 24] uint8 without synchronising
+    the stream (building the segment table does copy a few bytes to the device)."""
     ctx = context(device)
+    d_segs, max_n, keep = _build_segs(segments, device)
+    n = len(segments)
+    d_out = torch.empty((n, C.sizeof(L.SelectOut)), dtype=torch.uint8, device=device)
+    rc = ctx.lib.da3s_select(ctx.h, _ptr(d_segs), n, max_n, _ptr(d_out), _stream(d_segs))
+    L.check(rc, "da3s_select")
+    return d_out
+
+
+def _build_segs(segments, device):
     n = len(segments)
     segs = (L.SelectSeg * n)()
     keep = []
@@ -192,12 +241,7 @@ def select(segments, device):
         max_n = max(max_n, a.numel())
     raw = np.frombuffer(bytes(segs), dtype=np.uint8).copy()
     d_segs = torch.from_numpy(raw).to(device)
-    d_out = torch.empty((n, C.sizeof(L.SelectOut)), dtype=torch.uint8, device=device)
-    rc = ctx.lib.da3s_select(ctx.h, _ptr(d_segs), n, max_n, _ptr(d_out), _stream(d_segs))
-    L.check(rc, "da3s_select")
-    host = d_out.cpu().numpy()
-    dt = np.dtype([("n_valid", np.int64), ("lo", np.float32), ("hi", np.float32), ("value", np.float32), ("gamma", np.float32)])
-    return host.view(dt).reshape(n)
+    return d_segs, max_n, keep
 
 
 # ------------------------------------------------------------------------------------------
@@ -241,6 +285,17 @@ def align_pairs(pairs: torch.Tensor, n_pairs: int, overlap: int, H: int, W: int,
                                   _ptr(aux), _ptr(counts), _stream(pairs))
     L.check(rc, "da3s_align_pairs")
     return rows, aux, counts
+
+
+def accumulate_sim3(rows: torch.Tensor) -> torch.Tensor:
+    """[n,16] pair rows -> [n+1,13] cumulative Sim(3) (identity first), on the device."""
+    rows = rows.contiguous()
+    n = rows.shape[0]
+    ctx = context(rows.device)
+    cum = torch.empty((n + 1, 13), dtype=torch.float64, device=rows.device)
+    L.check(ctx.lib.da3s_accumulate_sim3(ctx.h, _ptr(rows, "rows", torch.float64), n, _ptr(cum), _stream(rows)),
+            "da3s_accumulate_sim3")
+    return cum
 
 
 def pair_thresholds(pairs, n_pairs, overlap, H, W, opts):
@@ -347,6 +402,55 @@ def irls_points(src, dst, conf_src, conf_dst, idx_src=None, idx_dst=None, delta=
 # ------------------------------------------------------------------------------------------
 # voxel grid
 # ------------------------------------------------------------------------------------------
+class VoxelGrid:
+    """Stage-level handle on the context's hash grid: begin() / insert() / finish() only enqueue
+    kernels; read() synchronises and trims the outputs."""
+
+    def __init__(self, device, table_slots: int, max_voxels: int, with_rgb: bool):
+        assert table_slots & (table_slots - 1) == 0
+        self.device = device
+        self.table_slots = table_slots
+        self.max_voxels = max_voxels
+        self.ctx = context(device, table_slots * 64 + (256 << 20))
+        self.xyz = torch.empty((max_voxels, 3), dtype=torch.float32, device=device)
+        self.rgb = torch.empty((max_voxels, 3), dtype=torch.uint8, device=device) if with_rgb else None
+        self.count = torch.empty((max_voxels,), dtype=torch.int32, device=device)
+        self.key = torch.empty((max_voxels,), dtype=torch.int64, device=device)
+        self.nv = torch.zeros((2,), dtype=torch.int64, device=device)      # [n_voxels, n_dropped]
+
+    def _st(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def begin(self):
+        L.check(self.ctx.lib.da3s_voxel_begin(self.ctx.h, self.table_slots, self._st()), "da3s_voxel_begin")
+
+    def insert(self, xyz, rgb, mask, voxel):
+        n = xyz.numel() // 3
+        rc = self.ctx.lib.da3s_voxel_insert(self.ctx.h, _ptr(xyz, "xyz", torch.float32), _ptr(rgb, "rgb", torch.uint8),
+                                            _ptr(mask, "mask"), n, float(voxel), self._st())
+        L.check(rc, "da3s_voxel_insert")
+
+    def finish(self, voxel):
+        rc = self.ctx.lib.da3s_voxel_finish(self.ctx.h, float(voxel), self.max_voxels, _ptr(self.xyz), _ptr(self.rgb),
+                                            _ptr(self.count), _ptr(self.key), C.c_void_p(self.nv.data_ptr()),
+                                            C.c_void_p(self.nv.data_ptr() + 8), self._st())
+        L.check(rc, "da3s_voxel_finish")
+
+    def read(self, sort=False):
+        n, dropped = (int(v) for v in self.nv.cpu())
+        if dropped:
+            raise L.Da3sError(L.ENOMEM, "VoxelGrid", f"hash table full: {dropped} points dropped")
+        if n > self.max_voxels:
+            raise L.Da3sError(L.ENOMEM, "VoxelGrid", f"{n} voxels > max_voxels {self.max_voxels}")
+        xyz, cnt, key = self.xyz[:n], self.count[:n], self.key[:n]
+        rgb = self.rgb[:n] if self.rgb is not None else None
+        if sort:
+            order = torch.argsort(key)
+            xyz, cnt, key = xyz[order], cnt[order], key[order]
+            rgb = rgb[order] if rgb is not None else None
+        return xyz, rgb, cnt, key
+
+
 def voxel_downsample(clouds, voxel: float, table_slots: int | None = None, max_voxels: int | None = None, sort=True):
     """clouds: list of (xyz [n,3] f32, rgb [n,3] u8 or None, mask [n] bool/u8 or None) CUDA tensors, all
     accumulated into one grid.  Returns (xyz [m,3] f32, rgb [m,3] u8 or None, count [m] i32, key [m] i64)."""

@@ -126,3 +126,90 @@ def export_map(submaps, cumulative, voxel, conf_percentile=None, conf_thr=None, 
         rgb = sm.images[first:].reshape(-1, 3) if sm.images is not None else None
         clouds.append((xyz.view(-1, 3), rgb, mask.reshape(-1)))
     return ops.voxel_downsample(clouds, voxel, table_slots, max_voxels, sort=sort)
+
+
+class SequencePlan:
+    """Everything that is static for one submap sequence resident in HBM — pair table,
+    selection segments, output buffers, the voxel grid — so that run() ONLY enqueues kernels
+    on the current stream (no allocation, no host<->device copy, no synchronisation):
+
+        pair thresholds (exact medians) -> [RANSAC] -> IRLS Umeyama -> rows
+        -> Sim(3) chain (device) -> per-submap confidence percentile (exact)
+        -> unproject + Sim(3) + filter per submap -> voxel grid insert -> compaction.
+
+    read() synchronises and returns host/trimmed results.  This is one "step" of bench.py."""
+
+    def __init__(self, submaps, overlap=1, voxel=0.02, conf_percentile=65.0, unproject_mode="fast", table_slots=None,
+                 max_voxels=None, sample_idx=None, export=True, skip_overlap=True, **opt_kw):
+        self.submaps = submaps
+        self.n = len(submaps)
+        self.dev = submaps[0].depth.device
+        self.F, self.H, self.W = submaps[0].depth.shape
+        self.overlap = overlap
+        self.voxel = float(voxel)
+        self.mode = unproject_mode
+        self.export = export
+        self.opts = L.default_opts(**opt_kw)
+        self.n_pairs = self.n - 1
+        self.entries = [pair_entry(submaps[k], submaps[k + 1], overlap) for k in range(self.n_pairs)]
+        self.pair_table = ops.make_pairs(self.entries, self.dev)
+        self.sample_idx = None
+        if self.opts.n_hyp > 0:
+            self.sample_idx = sample_idx.to(self.dev, torch.int32).contiguous()
+        self.rows = None
+        self.cum = None
+        if export:
+            # frames re-observed by the next submap are exported once (solver.py:100-114 adds them twice)
+            self.first = [0] + [overlap if skip_overlap else 0] * (self.n - 1)
+            segs = [dict(a=sm.conf[f0:], kind=L.SEL_POSITIVE, stat=L.SEL_PERCENTILE, percent=float(min(conf_percentile, 99.9)))
+                    for sm, f0 in zip(submaps, self.first)]
+            self.percentiles = ops.SelectPlan(segs, self.dev)
+            self.xyz = [torch.empty((self.F - f0, self.H, self.W, 3), dtype=torch.float32, device=self.dev) for f0 in self.first]
+            self.mask = [torch.empty((self.F - f0, self.H, self.W), dtype=torch.uint8, device=self.dev) for f0 in self.first]
+            self.n_kept = torch.zeros((1,), dtype=torch.int64, device=self.dev)
+            total = sum(x.numel() // 3 for x in self.xyz)
+            if table_slots is None:
+                table_slots = 1 << max(12, int(np.ceil(np.log2(max(total // 4, 4096)))))
+                table_slots = min(table_slots, 1 << 27)
+            if max_voxels is None:
+                max_voxels = table_slots // 2
+            self.grid = ops.VoxelGrid(self.dev, table_slots, max_voxels, submaps[0].images is not None)
+            self.points_per_step = total
+        else:
+            self.points_per_step = 0
+        ops.context(self.dev)            # make sure the context (and its workspace) exists before the first timed run
+
+    def run(self, mark=None):
+        """Enqueue one step.  `mark(name)` is called between stages (bench.py records CUDA events)."""
+        mark = mark or (lambda name: None)
+        self.rows, _, _ = ops.align_pairs(self.pair_table, self.n_pairs, self.overlap, self.H, self.W, self.opts,
+                                          self.sample_idx)
+        mark("align")
+        self.cum = ops.accumulate_sim3(self.rows)
+        if not self.export:
+            mark("chain")
+            return
+        self.percentiles.run()
+        mark("percentile")
+        self.n_kept.zero_()
+        for k, sm in enumerate(self.submaps):
+            f0 = self.first[k]
+            ops.unproject_filter(sm.depth[f0:], sm.conf[f0:], sm.cams[f0:], mode=self.mode, world=True, sim3=self.cum[k],
+                                 conf_cmp=">=", conf_thr_dev=self.percentiles.value_ptr_tensor(k), conf_floor=0.0,
+                                 depth_eps=1e-6, xyz_out=self.xyz[k], mask_out=self.mask[k], want_count=False)
+        mark("unproject")
+        self.grid.begin()
+        mark("voxel_clear")
+        for k, sm in enumerate(self.submaps):
+            rgb = sm.images[self.first[k]:] if sm.images is not None else None
+            self.grid.insert(self.xyz[k], rgb, self.mask[k], self.voxel)
+        mark("voxel_insert")
+        self.grid.finish(self.voxel)
+        mark("voxel_compact")
+
+    def read(self, sort=False):
+        out = {"rows": self.rows.cpu().numpy(), "cum": self.cum.cpu().numpy()}
+        if self.export:
+            xyz, rgb, cnt, key = self.grid.read(sort=sort)
+            out.update(voxel_xyz=xyz, voxel_rgb=rgb, voxel_count=cnt, voxel_key=key)
+        return out

@@ -147,3 +147,61 @@ def make_pair(H, W, frames=2, overlap=1, seed=1234, **kw):
 def to_device(sub, device="cuda"):
     import torch
     return {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in sub.items()}
+
+
+# ------------------------------------------------------------------------------------------
+# device-side generator (same distributions, torch RNG on the GPU): used by bench.py where
+# 10^8 pixels would take minutes with numpy.  Extrinsics / ground truth are drawn on the host.
+# ------------------------------------------------------------------------------------------
+def make_sequence_device(n_submaps, frames, H, W, overlap=1, seed=1234, outlier_ratio=0.0, depth_noise=0.002,
+                         with_images=True, device="cuda", conf_offset=0.0):
+    """Returns (submaps, gt): submaps are dicts of CUDA tensors with the Prediction fields."""
+    import torch
+    rng = np.random.default_rng(seed)
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    dev = torch.device(device)
+    u = (torch.arange(W, device=dev, dtype=torch.float32) / W).view(1, 1, W)
+    v = (torch.arange(H, device=dev, dtype=torch.float32) / H).view(1, H, 1)
+    K = torch.from_numpy(make_intrinsics(frames, H, W)).to(dev)
+    b = min(6, H // 4, W // 4)
+    band = torch.zeros((H, W), dtype=torch.bool, device=dev)
+    if b > 0:
+        band[:b] = True
+        band[-b:] = True
+        band[:, :b] = True
+        band[:, -b:] = True
+    subs, gt, prev = [], [], None
+    for k in range(n_submaps):
+        E = trajectory_w2c(rng, frames)
+        p = {name: torch.from_numpy(rng.uniform(lo, hi, size=(frames, 1, 1)).astype(np.float32)).to(dev)
+             for name, (lo, hi) in dict(d0=(1.2, 2.2), a=(0.2, 0.7), f1=(0.5, 2.5), f2=(0.5, 2.5), ph=(0, 2 * np.pi)).items()}
+        depth = p["d0"] + p["a"] * torch.sin(2 * np.pi * u * p["f1"] + p["ph"]) * torch.cos(2 * np.pi * v * p["f2"])
+        depth = depth.clamp_(0.5, 3.0) + 0.002 * torch.randn((frames, H, W), device=dev, generator=g)
+        conf = conf_offset + torch.exp(0.75 * torch.randn((frames, H, W), device=dev, generator=g))
+        conf[torch.rand((frames, H, W), device=dev, generator=g) < 0.05] = conf_offset
+        conf[:, band] = conf_offset + 0.01 * torch.rand((frames, int(band.sum())), device=dev, generator=g)
+        if prev is not None:
+            s, R, t = random_sim3(rng)
+            gt.append((s, R, t))
+            Ep = prev["extrinsics"][-overlap:].double().cpu().numpy()
+            Rp, tp = c2w_of(Ep)
+            Rc = np.einsum("ij,njk->nik", R.T, Rp)
+            tc = np.einsum("ij,nj->ni", R.T, tp - t) / s
+            E[:overlap] = w2c_from_c2w(Rc, tc)
+            d = prev["depth"][-overlap:] / float(s) + depth_noise * torch.randn((overlap, H, W), device=dev, generator=g)
+            if outlier_ratio > 0:
+                bad = torch.rand((overlap, H, W), device=dev, generator=g) < outlier_ratio
+                d = torch.where(bad, 0.3 + 3.7 * torch.rand((overlap, H, W), device=dev, generator=g), d)
+            depth[:overlap] = d
+        sub = {"depth": depth.contiguous(), "conf": conf.contiguous(),
+               "extrinsics": torch.from_numpy(E.astype(F32)).to(dev), "intrinsics": K.clone()}
+        if with_images:
+            sub["processed_images"] = torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, device=dev, generator=g)
+        subs.append(sub)
+        prev = sub
+    return subs, gt
+
+
+def submap_to_host(sub):
+    return {k: v.cpu().numpy() for k, v in sub.items()}

@@ -206,6 +206,13 @@ int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs /* device */, int n_p
                      da3s_pair_aux* aux /* nullable */, int32_t* hyp_counts_out /* nullable */,
                      void* stream);
 
+/* Sim(3) chain accumulation on the device (utils/geometry.py:73-119): rows[k] maps submap k+1
+ * into submap k; cum[0] = identity, cum[k+1] = cum[k] o rows[k].  cum: [n_rows+1, 13] float64
+ * (s, R row-major, t) — directly usable as the per-frame/per-submap `sim3` of
+ * da3s_unproject_filter, so the map export needs no host round trip. */
+int da3s_accumulate_sim3(da3s_ctx* ctx, const double* rows /* [n_rows,16] */, int n_rows,
+                         double* cum /* [n_rows+1,13] */, void* stream);
+
 /* Stage-level entry points (the same kernels; used by the parity tests and by callers
  * that already hold thresholds / hypotheses). */
 int da3s_pair_thresholds(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
