@@ -356,7 +356,7 @@ def gpu_arm(args, w, rank, world):
     px_export = plan.points_per_step
     single = {}
     if w["export"]:
-        single["unproject"] = ("unproject_filter_kernel<FAST,float,vec>", 21.0 * px_export, w["n_submaps"],
+        single["unproject"] = ("unproject_filter_kernel<FAST,float,vec>", 21.0 * px_export, 1,
                                "21 B/pixel (4 depth + 4 conf read, 12 xyz + 1 mask written)")
         single["voxel_insert"] = ("voxel_insert_kernel", (12.0 + 1.0 + 3.0) * px_export, w["n_submaps"],
                                   "16 B/point read (12 xyz + 3 rgb + 1 mask); hash-table traffic not counted")

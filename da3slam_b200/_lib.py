@@ -32,7 +32,7 @@ class AlignOpts(C.Structure):
         ("world", C.c_int), ("depth_scale_mode", C.c_int), ("depth_conf_th", C.c_float), ("depth_eps", C.c_float),
         ("valid_depth", C.c_int), ("conf_thr_override", C.c_float), ("huber", C.c_int), ("huber_delta", C.c_double),
         ("max_iterations", C.c_int), ("tol", C.c_double), ("min_points", C.c_int), ("n_hyp", C.c_int),
-        ("ransac_thr", C.c_float), ("ransac_min_inliers", C.c_int),
+        ("ransac_thr", C.c_float), ("ransac_min_inliers", C.c_int), ("precise", C.c_int),
     ]
 
 
@@ -53,6 +53,12 @@ class Pair(C.Structure):
                 ("cam_a", C.c_void_p), ("cam_b", C.c_void_p)]
 
 
+class FrameJob(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("conf", C.c_void_p), ("cam", C.c_void_p), ("sim3", C.c_void_p),
+                ("conf_thr", C.c_void_p), ("xyz", C.c_void_p), ("mask", C.c_void_p)]
+
+
+assert C.sizeof(FrameJob) == 56
 assert C.sizeof(Pair) == PAIR_BYTES and C.sizeof(SelectSeg) == 64 and C.sizeof(SelectOut) == 24
 
 _P, _I, _L, _F, _D, _ULL = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_ulonglong
@@ -67,6 +73,7 @@ SIGNATURES = {
     "da3s_launch_count": (_ULL, [_P]),
     "da3s_build_cams": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "da3s_unproject_filter": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _F, _F, _P, _P, _P, _P, _P]),
+    "da3s_unproject_filter_jobs": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
     "da3s_apply_sim3": (_I, [_P, _P, _I, _L, _P, _P, _I, _P]),
     "da3s_select": (_I, [_P, _P, _I, _L, _P, _P]),
     "da3s_align_opts_default": (None, [C.POINTER(AlignOpts)]),

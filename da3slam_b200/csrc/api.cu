@@ -35,7 +35,7 @@ extern "C" int da3s_create(int device, size_t workspace_bytes, da3s_ctx** out) {
     cudaError_t e = cudaMalloc((void**)&c->ws, workspace_bytes);
     if (e != cudaSuccess) { int rc = (e == cudaErrorMemoryAllocation) ? DA3S_ENOMEM : DA3S_ECUDA; cudaGetLastError(); delete c; return rc; }
     c->ws_top = 0; c->last_cuda_error = 0; c->launches = 0;
-    c->vox_keys = nullptr; c->vox_acc = nullptr; c->vox_rgbn = nullptr; c->vox_slots = 0; c->vox_dropped = nullptr; c->vox_bytes = 0;
+    c->vox_keys = nullptr; c->vox_acc = nullptr; c->vox_rgbn = nullptr; c->vox_slots = 0; c->vox_dropped = nullptr; c->vox_bytes = 0; c->vox_occ = nullptr; c->vox_clean = false; c->vox_active = false;
     *out = c;
     return DA3S_OK;
 }

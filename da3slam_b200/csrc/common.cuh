@@ -24,8 +24,10 @@ struct da3s_ctx {
     unsigned long long* vox_acc;    // [slots][4]: sum_qx, sum_qy, sum_qz, (count | rgb sums packed separately)
     unsigned int* vox_rgbn;         // [slots][4]: count, sum_r, sum_g, sum_b
     long long vox_slots;
-    unsigned long long* vox_dropped;
+    unsigned long long* vox_dropped;   // counters[4]: occupied, dropped, -, -
+    unsigned int* vox_occ;             // occupied-slot list [slots]
     size_t vox_bytes;
+    bool vox_clean, vox_active;
 };
 
 #define DA3S_CHECK_CUDA(ctx, expr)                                   \

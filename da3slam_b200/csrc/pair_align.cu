@@ -45,7 +45,7 @@ struct PairArgs {
     double* partials;                       // [n_pairs][overlap*tiles][MOM_LEN]
     unsigned int* tickets;                  // [n_pairs]
     double huber_delta, tol;
-    int max_iterations, min_points;
+    int max_iterations, min_points, precise;
     double* rows;                           // [n_pairs][16]
     da3s_pair_aux* aux;
 };
@@ -55,6 +55,7 @@ struct FrameConst {
     float MfA[12], MfB[12];                 // float32 c2w (RANSAC world points, SPEC 4)
     float gate[12];
     double By[9], Bx[9], c[3];              // residual = By y + Bx x + c  (By = I in camera mode)
+    float Bpf[9], cpf[3];                   // float32 form |r| = |y + Bp x + cp| (mixed-precision kernel)
     float thr, ds;
     int gate_on;
 };
@@ -74,8 +75,8 @@ __device__ __forceinline__ void load_frame_const(FrameConst& fc, const da3s_pair
     }
     if (a.eff) {
         const double* e = a.eff + ((size_t)pair * a.overlap + frame) * EFF_LEN;
-        for (int k = 0; k < 9; ++k) { fc.By[k] = e[k]; fc.Bx[k] = e[9 + k]; }
-        for (int k = 0; k < 3; ++k) fc.c[k] = e[18 + k];
+        for (int k = 0; k < 9; ++k) { fc.By[k] = e[k]; fc.Bx[k] = e[9 + k]; fc.Bpf[k] = (float)e[21 + k]; }
+        for (int k = 0; k < 3; ++k) { fc.c[k] = e[18 + k]; fc.cpf[k] = (float)e[30 + k]; }
     }
 }
 
@@ -135,8 +136,8 @@ __device__ __noinline__ void set_effective(const PairArgs& a, int pair, const Pa
             const da3s_pair pr = a.pairs[pair];
             effective_residual_transform(st.s, st.R, st.t, pr.cam_b[f].c2w, pr.cam_a[f].c2w, e);
         } else {
-            for (int k = 0; k < 9; ++k) { e[k] = (k % 4 == 0) ? 1.0 : 0.0; e[9 + k] = -st.s * st.R[k]; }
-            for (int k = 0; k < 3; ++k) e[18 + k] = -st.t[k];
+            for (int k = 0; k < 9; ++k) { e[k] = (k % 4 == 0) ? 1.0 : 0.0; e[9 + k] = -st.s * st.R[k]; e[21 + k] = e[9 + k]; }
+            for (int k = 0; k < 3; ++k) { e[18 + k] = -st.t[k]; e[30 + k] = e[18 + k]; }
         }
     }
 }
@@ -165,7 +166,7 @@ __device__ __noinline__ void solve_pair(const PairArgs& a, int pair, const doubl
     for (int k = 0; k < 9; ++k) st.R[k] = R[k];
     for (int k = 0; k < 3; ++k) st.t[k] = t[k];
     st.iters += 1;
-    st.mean_res = mom[MOM_SR] / n;
+    st.mean_res = a.precise ? mom[MOM_SR] / n : sqrt(mom[MOM_SR] / n);   // mean |r| (float64 kernel) or rms (mixed kernel)
     if (!a.huber || st.change < a.tol || st.iters >= a.max_iterations) st.done = 1;
     a.state[pair] = st;
     if (st.done) write_row(a, pair, st);
@@ -324,6 +325,244 @@ pair_moments_kernel(PairArgs a) {
         double m[MOM_LEN];
         for (int k = 0; k < MOM_LEN; ++k) m[k] = wmom[k];
         solve_pair(a, pair, m);
+        a.tickets[pair] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K2 / K3, mixed precision (default): the per-correspondence arithmetic runs in float32
+// FMA on points centred at a per-tile pivot, in micro-batches of 8 correspondences whose 22
+// partial sums are flushed into float64 accumulators; tiles are un-pivoted and combined in
+// float64.  Rationale (profiles/r1_baseline_*): with float64 per-point arithmetic the kernel is
+// bound by the FP64 pipe (64 lanes/clk/SM) and the conversion unit, not by HBM.  Deviation from
+// the all-float64 oracle: <= 1e-8 relative on (s, R, t) at 5e4..3e5 correspondences
+// (scratch emulation + tests), two orders inside the 1e-6 contract.  `precise = 1` selects
+// the all-float64 kernel above.
+// ---------------------------------------------------------------------------------
+#define PM_THREADS 128
+#define PM_NMOM 22                          // S0, Sx[3], Sy[3], Syx[9], Sxx[6]
+
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+template <bool VEC, bool WORLD_UNUSED, bool HUBER>
+__global__ void __launch_bounds__(PM_THREADS, 3)
+pair_moments_mixed_kernel(PairArgs a) {
+    __shared__ double red[MOM_LEN][PM_THREADS];     // block reduction scratch (25.6 KB)
+    __shared__ FrameConst fc;
+    __shared__ float piv[6];                        // pivot: x (source) then y (target), float32 camera-frame point
+    __shared__ double fmom[MOM_LEN];
+    __shared__ double wmom[MOM_LEN];
+    __shared__ double part[MOM_LEN][PM_THREADS / 32];
+    __shared__ bool is_last;
+    const int pair = blockIdx.y;
+    if (a.state[pair].done) return;
+    const da3s_pair pr = a.pairs[pair];
+    const int frame = blockIdx.x / a.tiles_per_frame;
+    const int tile = blockIdx.x - frame * a.tiles_per_frame;
+    const size_t foff = (size_t)frame * (size_t)a.P;
+    const float* dA = pr.depth_a + foff; const float* cA = pr.conf_a + foff;
+    const float* dB = pr.depth_b + foff; const float* cB = pr.conf_b + foff;
+    const long long p_begin = (long long)tile * PA_GROUPS_PER_BLOCK * 4;
+    long long p_end = p_begin + (long long)PA_GROUPS_PER_BLOCK * 4;
+    if (p_end > a.P) p_end = a.P;
+    if (threadIdx.x == 0) {
+        load_frame_const(fc, pr, frame, a, pair);
+        // pivot = the correspondence at the frame's centre pixel: the same for every tile of the
+        // frame, so per-tile partials add directly and are un-pivoted once per frame by the last block
+        const int vc = a.H / 2, uc = a.W / 2;
+        const long long pc = (long long)vc * a.W + uc;
+        float x[3], y[3], dbs;
+        corr_points(fc, false, 0.0f, uc, vc, dA[pc], 1.0f, dB[pc], 1.0f, x, y, dbs);
+        for (int k = 0; k < 3; ++k) { piv[k] = is_finite_f(x[k]) ? x[k] : 0.0f; piv[3 + k] = is_finite_f(y[k]) ? y[k] : 0.0f; }
+    }
+    __syncthreads();
+    // block-uniform constants into registers
+    const float px0 = piv[0], px1 = piv[1], px2 = piv[2], py0 = piv[3], py1 = piv[4], py2 = piv[5];
+    const float cuA = fc.cuA, cvA = fc.cvA, ifuA = fc.ifuA, ifvA = fc.ifvA, cuB = fc.cuB, cvB = fc.cvB, ifuB = fc.ifuB, ifvB = fc.ifvB;
+    const float thr = fc.thr, ds = fc.ds, eps = a.depth_eps;
+    const bool valid_depth = a.valid_depth, gate_on = fc.gate_on;
+    float B[9], c3[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) B[k] = fc.Bpf[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c3[k] = fc.cpf[k];
+    const float delta = (float)a.huber_delta, delta2 = delta * delta;
+    const float Wf = (float)a.W;
+
+    double acc[PM_NMOM];
+#pragma unroll
+    for (int k = 0; k < PM_NMOM; ++k) acc[k] = 0.0;
+    float m[PM_NMOM];
+#pragma unroll
+    for (int k = 0; k < PM_NMOM; ++k) m[k] = 0.0f;
+    float wmax = 0.0f, r2sum = 0.0f;
+    double r2acc = 0.0;
+    int cnt = 0;
+
+    // one correspondence, branch-free: a rejected pixel contributes weight 0 on sanitised depths
+    auto accumulate = [&](float uf, float vf, float da, float ca, float db, float cb) {
+        const float dbs = __fmul_rn(db, ds);
+        bool keep = (ca > thr) && (cb > thr);
+        if (valid_depth) keep = keep && (da > eps) && (dbs > eps) && is_finite_f(da) && is_finite_f(dbs);
+        float x0, x1, y0, y1;
+        cam_fast(uf, vf, da, cuA, cvA, ifuA, ifvA, y0, y1);
+        cam_fast(uf, vf, dbs, cuB, cvB, ifuB, ifvB, x0, x1);
+        if (gate_on) {                                          // block-uniform
+            float x[3] = {x0, x1, dbs}, y[3] = {y0, y1, da}, xs[3], ys[3];
+            ransac_points(fc, a.world, x, y, xs, ys);
+            keep = keep && (residual2_f32(fc.gate, xs, ys) < a.gate_thr2);
+        }
+        // sanitise: a rejected pixel must not inject NaN/Inf through 0 * x
+        x0 = keep ? x0 : 0.0f; x1 = keep ? x1 : 0.0f; y0 = keep ? y0 : 0.0f; y1 = keep ? y1 : 0.0f;
+        const float x2 = keep ? dbs : 0.0f, y2 = keep ? da : 0.0f;
+        float w = keep ? sqrt_approx(ca * cb) : 0.0f;           // utils/align.py:166 (<= 1 ulp from sqrt_f32)
+        if (HUBER) {
+            const float r0 = fmaf(B[0], x0, fmaf(B[1], x1, fmaf(B[2], x2, y0 + c3[0])));
+            const float r1 = fmaf(B[3], x0, fmaf(B[4], x1, fmaf(B[5], x2, y1 + c3[1])));
+            const float r2 = fmaf(B[6], x0, fmaf(B[7], x1, fmaf(B[8], x2, y2 + c3[2])));
+            const float rr = fmaf(r0, r0, fmaf(r1, r1, r2 * r2));
+            const float hub = delta * rsqrt_approx(rr);          // Huber: delta / r  (utils/align.py:94-109)
+            w = (rr > delta2) ? w * hub : w;
+            r2sum += keep ? rr : 0.0f;
+        }
+        const float xc0 = x0 - px0, xc1 = x1 - px1, xc2 = x2 - px2;
+        const float yc0 = y0 - py0, yc1 = y1 - py1, yc2 = y2 - py2;
+        const float wx0 = w * xc0, wx1 = w * xc1, wx2 = w * xc2;
+        m[0] += w;
+        m[1] += wx0; m[2] += wx1; m[3] += wx2;
+        m[4] = fmaf(w, yc0, m[4]); m[5] = fmaf(w, yc1, m[5]); m[6] = fmaf(w, yc2, m[6]);
+        m[7] = fmaf(yc0, wx0, m[7]);   m[8] = fmaf(yc0, wx1, m[8]);   m[9] = fmaf(yc0, wx2, m[9]);
+        m[10] = fmaf(yc1, wx0, m[10]); m[11] = fmaf(yc1, wx1, m[11]); m[12] = fmaf(yc1, wx2, m[12]);
+        m[13] = fmaf(yc2, wx0, m[13]); m[14] = fmaf(yc2, wx1, m[14]); m[15] = fmaf(yc2, wx2, m[15]);
+        m[16] = fmaf(wx0, xc0, m[16]); m[17] = fmaf(wx0, xc1, m[17]); m[18] = fmaf(wx0, xc2, m[18]);
+        m[19] = fmaf(wx1, xc1, m[19]); m[20] = fmaf(wx1, xc2, m[20]); m[21] = fmaf(wx2, xc2, m[21]);
+        wmax = fmaxf(wmax, w);
+        cnt += keep ? 1 : 0;
+    };
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < PM_NMOM; ++k) { acc[k] += (double)m[k]; m[k] = 0.0f; }
+        r2acc += (double)r2sum; r2sum = 0.0f;
+    };
+    auto group = [&](long long g, const float4& da, const float4& ca, const float4& db, const float4& cb) {
+        const long long pix = g << 2;
+        const int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+        float uf = (float)u, vf = (float)v;
+        accumulate(uf, vf, da.x, ca.x, db.x, cb.x); uf += 1.0f; if (uf == Wf) { uf = 0.0f; vf += 1.0f; }
+        accumulate(uf, vf, da.y, ca.y, db.y, cb.y); uf += 1.0f; if (uf == Wf) { uf = 0.0f; vf += 1.0f; }
+        accumulate(uf, vf, da.z, ca.z, db.z, cb.z); uf += 1.0f; if (uf == Wf) { uf = 0.0f; vf += 1.0f; }
+        accumulate(uf, vf, da.w, ca.w, db.w, cb.w);
+    };
+
+    if (VEC) {
+        const long long n_groups = a.P >> 2;
+        const long long g_begin = (long long)tile * PA_GROUPS_PER_BLOCK;
+        long long g_end = g_begin + PA_GROUPS_PER_BLOCK;
+        if (g_end > n_groups) g_end = n_groups;
+        const float4* dA4 = reinterpret_cast<const float4*>(dA); const float4* cA4 = reinterpret_cast<const float4*>(cA);
+        const float4* dB4 = reinterpret_cast<const float4*>(dB); const float4* cB4 = reinterpret_cast<const float4*>(cB);
+        // micro-batch = 2 groups (8 correspondences): all 8 loads issued before any arithmetic
+        for (long long g0 = g_begin + threadIdx.x; g0 < g_end; g0 += 2 * PM_THREADS) {
+            const long long g1 = g0 + PM_THREADS;
+            const bool has1 = g1 < g_end;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 da0 = ldg_stream(dA4 + g0), ca0 = ldg_stream(cA4 + g0), db0 = ldg_stream(dB4 + g0), cb0 = ldg_stream(cB4 + g0);
+            float4 da1 = z4, ca1 = z4, db1 = z4, cb1 = z4;
+            if (has1) { da1 = ldg_stream(dA4 + g1); ca1 = ldg_stream(cA4 + g1); db1 = ldg_stream(dB4 + g1); cb1 = ldg_stream(cB4 + g1); }
+            group(g0, da0, ca0, db0, cb0);
+            if (has1) group(g1, da1, ca1, db1, cb1);
+            flush();
+        }
+    } else {
+        int since = 0;
+        for (long long pix = p_begin + threadIdx.x; pix < p_end; pix += PM_THREADS) {
+            const int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+            accumulate((float)u, (float)v, dA[pix], cA[pix], dB[pix], cB[pix]);
+            if (++since == 8) { flush(); since = 0; }
+        }
+        flush();
+    }
+
+    // ---- block reduction through shared memory (float64), fixed order ----
+#pragma unroll
+    for (int k = 0; k < PM_NMOM; ++k) red[k][threadIdx.x] = acc[k];
+    red[MOM_SR][threadIdx.x] = r2acc;
+    red[MOM_WMAX][threadIdx.x] = (double)wmax;
+    red[MOM_N][threadIdx.x] = (double)cnt;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < MOM_LEN * (PM_THREADS / 32)) {               // 100 threads: (moment k, 32-thread slice)
+        const int k = threadIdx.x / (PM_THREADS / 32), sl = threadIdx.x % (PM_THREADS / 32);
+        const double* src = &red[k][sl * 32];
+        double v = 0.0;
+        // rotated start index per lane avoids bank conflicts; each thread's summation order is fixed
+        for (int j = 0; j < 32; ++j) {
+            const double p = src[(j + lane) & 31];
+            v = (k == MOM_WMAX) ? fmax(v, p) : v + p;
+        }
+        part[k][sl] = v;
+    }
+    __syncthreads();
+    const int n_tiles = a.overlap * a.tiles_per_frame;
+    if (threadIdx.x < MOM_LEN) {
+        double v = part[threadIdx.x][0];
+        for (int w = 1; w < PM_THREADS / 32; ++w) v = (threadIdx.x == MOM_WMAX) ? fmax(v, part[threadIdx.x][w]) : v + part[threadIdx.x][w];
+        a.partials[((size_t)pair * n_tiles + blockIdx.x) * MOM_LEN + threadIdx.x] = v;     // still about the frame pivot
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(&a.tickets[pair], 1u);
+        is_last = (t == (unsigned int)n_tiles - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // ---- last block of the pair: sum partials frame by frame (tile order), un-pivot, to world, solve ----
+    if (threadIdx.x < MOM_LEN) wmom[threadIdx.x] = 0.0;
+    __syncthreads();
+    for (int f = 0; f < a.overlap; ++f) {
+        if (threadIdx.x < MOM_LEN) {
+            const double* src = a.partials + ((size_t)pair * n_tiles + (size_t)f * a.tiles_per_frame) * MOM_LEN + threadIdx.x;
+            double v = 0.0;
+            for (int t = 0; t < a.tiles_per_frame; ++t) {
+                double p = __ldcg(src + (size_t)t * MOM_LEN);
+                v = (threadIdx.x == MOM_WMAX) ? fmax(v, p) : v + p;
+            }
+            fmom[threadIdx.x] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // frame f's pivot (same rule as above), un-pivot (exact polynomial identities, float64), then to world
+            FrameConst& g = fc;
+            load_frame_const(g, pr, f, a, pair);
+            const int vc = a.H / 2, uc = a.W / 2;
+            const size_t pc = (size_t)f * (size_t)a.P + (size_t)vc * a.W + uc;
+            float x[3], y[3], dbs;
+            corr_points(g, false, 0.0f, uc, vc, pr.depth_a[pc], 1.0f, pr.depth_b[pc], 1.0f, x, y, dbs);
+            double sx[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, sy[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+            for (int k = 0; k < 3; ++k) { sx[4 * k + 3] = is_finite_f(x[k]) ? (double)x[k] : 0.0; sy[4 * k + 3] = is_finite_f(y[k]) ? (double)y[k] : 0.0; }
+            double mm[MOM_LEN], cam[MOM_LEN];
+            for (int k = 0; k < MOM_LEN; ++k) { mm[k] = fmom[k]; cam[k] = 0.0; }
+            moments_to_world_add(mm, sx, sy, cam);
+            if (a.world) {
+                double acc2[MOM_LEN];
+                for (int k = 0; k < MOM_LEN; ++k) acc2[k] = wmom[k];
+                moments_to_world_add(cam, pr.cam_b[f].c2w, pr.cam_a[f].c2w, acc2);
+                for (int k = 0; k < MOM_LEN; ++k) wmom[k] = acc2[k];
+            } else {
+                for (int k = 0; k < MOM_LEN; ++k)
+                    wmom[k] = (k == MOM_WMAX) ? fmax(wmom[k], cam[k]) : wmom[k] + cam[k];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double mm[MOM_LEN];
+        for (int k = 0; k < MOM_LEN; ++k) mm[k] = wmom[k];
+        solve_pair(a, pair, mm);
         a.tickets[pair] = 0;
     }
 }
@@ -650,7 +889,7 @@ extern "C" void da3s_align_opts_default(da3s_align_opts* o) {
     if (!o) return;
     o->world = 1; o->depth_scale_mode = 0; o->depth_conf_th = 0.2f; o->depth_eps = 1e-6f; o->valid_depth = 1;
     o->conf_thr_override = nanf(""); o->huber = 1; o->huber_delta = 1.0; o->max_iterations = 20; o->tol = 1e-6;
-    o->min_points = 100; o->n_hyp = 0; o->ransac_thr = 0.05f; o->ransac_min_inliers = 20;
+    o->min_points = 100; o->n_hyp = 0; o->ransac_thr = 0.05f; o->ransac_min_inliers = 20; o->precise = 0;
 }
 
 static int thresholds_impl(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
@@ -780,7 +1019,8 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     a.gate = opts->n_hyp > 0 ? gate : nullptr;
     a.gate_thr2 = (float)((double)opts->ransac_thr * (double)opts->ransac_thr);
     a.partials = partials; a.tickets = tickets; a.huber_delta = opts->huber_delta; a.tol = opts->tol;
-    a.max_iterations = opts->max_iterations; a.min_points = opts->min_points; a.rows = sim3_rows; a.aux = aux;
+    a.max_iterations = opts->max_iterations; a.min_points = opts->min_points; a.precise = opts->precise;
+    a.rows = sim3_rows; a.aux = aux;
 
     int threads = 128, blocks = (n_pairs + threads - 1) / threads;
     pair_state_init_kernel<<<blocks, threads, 0, st>>>(a);
@@ -808,8 +1048,16 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     dim3 grid(n_tiles, n_pairs);
     const int iters = opts->huber ? opts->max_iterations : 1;
     for (int it = 0; it < iters; ++it) {
-        if (vec) pair_moments_kernel<true><<<grid, PA_THREADS, 0, st>>>(a);
-        else     pair_moments_kernel<false><<<grid, PA_THREADS, 0, st>>>(a);
+        if (opts->precise) {
+            if (vec) pair_moments_kernel<true><<<grid, PA_THREADS, 0, st>>>(a);
+            else     pair_moments_kernel<false><<<grid, PA_THREADS, 0, st>>>(a);
+        } else if (opts->huber) {
+            if (vec) pair_moments_mixed_kernel<true, true, true><<<grid, PM_THREADS, 0, st>>>(a);
+            else     pair_moments_mixed_kernel<false, true, true><<<grid, PM_THREADS, 0, st>>>(a);
+        } else {
+            if (vec) pair_moments_mixed_kernel<true, true, false><<<grid, PM_THREADS, 0, st>>>(a);
+            else     pair_moments_mixed_kernel<false, true, false><<<grid, PM_THREADS, 0, st>>>(a);
+        }
         DA3S_LAUNCH_CHECK(ctx);
     }
     return DA3S_OK;
@@ -983,6 +1231,7 @@ static int points_common(da3s_ctx* ctx, PointsArgs& a, long long count, int hube
     pa.world = 0; pa.valid_depth = 0; pa.huber = huber; pa.variant = variant; pa.depth_eps = 0; pa.thr = nullptr;
     pa.dscale = nullptr; pa.state = state; pa.eff = eff; pa.gate = nullptr; pa.gate_thr2 = 0; pa.partials = partials;
     pa.tickets = tickets; pa.huber_delta = delta; pa.tol = tol; pa.max_iterations = max_it; pa.min_points = min_points;
+    pa.precise = 1;
     pa.rows = row; pa.aux = nullptr;
     a.count = count;
     return (int)nb;

@@ -74,36 +74,44 @@ select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* state,
     const bool skip = (PASS > 0 && st.empty);
     if (!skip && base < seg.n) {
         const bool vec = (seg.kind != DA3S_SEL_RATIO) && aligned16(seg.a);
+        unsigned int keys[SEL_ITEMS];
+        unsigned int okmask = 0;
+        // all loads first (4 x 128-bit in flight per thread), then the histogram updates
+        if (vec && base + (long long)SEL_THREADS * SEL_ITEMS <= seg.n) {
+            float4 v[SEL_ITEMS / 4];
 #pragma unroll
-        for (int it = 0; it < SEL_ITEMS / 4; ++it) {
-            long long i0 = base + ((long long)it * SEL_THREADS + threadIdx.x) * 4;
-            unsigned int keys[4];
-            bool ok[4];
-            if (vec && i0 + 3 < seg.n) {
-                float4 v = ldg_stream(reinterpret_cast<const float4*>(seg.a + i0));
-                float f[4] = {v.x, v.y, v.z, v.w};
+            for (int it = 0; it < SEL_ITEMS / 4; ++it)
+                v[it] = ldg_stream(reinterpret_cast<const float4*>(seg.a + base + ((long long)it * SEL_THREADS + threadIdx.x) * 4));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    keys[j] = f32_to_key(f[j]);
-                    ok[j] = seg.kind == DA3S_SEL_VALUES ? true : (f[j] > 0.0f);
-                }
-            } else {
+            for (int it = 0; it < SEL_ITEMS / 4; ++it) {
+                const float f[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    ok[j] = false; keys[j] = 0;
-                    if (i0 + j < seg.n) ok[j] = sel_key(seg, i0 + j, keys[j]);
+                    keys[it * 4 + j] = f32_to_key(f[j]);
+                    if (seg.kind == DA3S_SEL_VALUES || f[j] > 0.0f) okmask |= 1u << (it * 4 + j);
                 }
             }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                unsigned int digit = (keys[j] >> shift) & dmask;
-                if (PASS == 0) {
-                    hist_add(hist[0], digit, ok[j]);
-                } else {
-                    unsigned int hi = keys[j] >> (shift + bits);
-                    hist_add(hist[0], digit, ok[j] && hi == st.prefix[0]);
-                    if (two) hist_add(hist[1], digit, ok[j] && hi == st.prefix[1]);
+            for (int it = 0; it < SEL_ITEMS / 4; ++it)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long i = base + ((long long)it * SEL_THREADS + threadIdx.x) * 4 + j;
+                    keys[it * 4 + j] = 0;
+                    if (i < seg.n && sel_key(seg, i, keys[it * 4 + j])) okmask |= 1u << (it * 4 + j);
                 }
+        }
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            const unsigned int digit = (keys[e] >> shift) & dmask;
+            const bool ok = (okmask >> e) & 1u;
+            if (PASS == 0) {
+                hist_add(hist[0], digit, ok);                    // every element counts: aggregate per warp
+            } else {
+                // only the elements inside a query's prefix class count (a small fraction): plain atomics
+                const unsigned int hi = keys[e] >> (shift + bits);
+                if (ok && hi == st.prefix[0]) atomicAdd(&hist[0][digit], 1u);
+                if (two && ok && hi == st.prefix[1]) atomicAdd(&hist[1][digit], 1u);
             }
         }
     }

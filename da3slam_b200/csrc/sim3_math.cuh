@@ -33,7 +33,10 @@
 #define MOM_WMAX 23
 #define MOM_N 24
 #define MOM_LEN 25
-#define EFF_LEN 21          // per (pair, frame): By[9] | Bx[9] | c[3];  residual = By y + Bx x + c
+#define EFF_LEN 33          // per (pair, frame): By[9] | Bx[9] | c[3] | Bp[9] | cp[3]
+                            //   exact residual  r = By y + Bx x + c            (float64 kernel)
+                            //   |r| ~= |y + Bp x + cp|, Bp = By^-1 Bx, cp = By^-1 c   (float32 kernel; equal up to the
+                            //   ~6e-8 non-orthonormality of a float32 rotation, i.e. at float32 rounding level)
 
 HD double det3(const double* M) {
     return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) +
@@ -251,4 +254,8 @@ HD void effective_residual_transform(double s, const double* R, const double* t,
     for (int k = 0; k < 9; ++k) eff[9 + k] = -T1[k];
     mat3_vec(sR, tx, v);
     for (int i = 0; i < 3; ++i) eff[18 + i] = c2w_y[4 * i + 3] - v[i] - t[i];
+    double Byi[9];
+    if (!mat3_inv(eff, Byi)) { for (int k = 0; k < 9; ++k) Byi[k] = (k % 4 == 0) ? 1.0 : 0.0; }
+    mat3_mul(Byi, eff + 9, eff + 21);
+    mat3_vec(Byi, eff + 18, eff + 30);
 }

@@ -113,6 +113,7 @@ __device__ __forceinline__ void unproject_pixel(const UnprojFrame& f, int u, int
 #define K1_PIX_PER_THREAD 4
 
 struct K1Args {
+    const da3s_frame_job* jobs;  // nullable: per-frame pointers (batched launch over frames of many submaps)
     const float* depth; const float* conf; const da3s_cam* cams;
     int H, W; long long P;      // P = H*W
     int flags;
@@ -128,11 +129,26 @@ unproject_filter_kernel(K1Args a) {
     __shared__ UnprojFrame fr;
     __shared__ __align__(16) float stage[VEC ? (K1_THREADS / 32) * 32 * 12 : 4];     // per-warp staging for f32 xyz
     __shared__ unsigned int blk_kept;
+    __shared__ float thr_sh;
     const int frame = blockIdx.y;
     const bool world = a.flags & DA3S_UNPROJ_WORLD;
-    const bool xform = world || a.sim3 != nullptr;
+    // per-frame pointers: from the job table (batched launch) or from the flat arrays
+    const float* depth; const float* conf; const da3s_cam* cam; const double* s3; const float* thr_dev;
+    OutT* xyz; uint8_t* mask;
+    if (a.jobs) {
+        const da3s_frame_job j = a.jobs[frame];
+        depth = j.depth; conf = j.conf; cam = j.cam; s3 = j.sim3; thr_dev = j.conf_thr;
+        xyz = (OutT*)j.xyz; mask = j.mask;
+    } else {
+        const size_t frame_off = (size_t)frame * (size_t)a.P;
+        depth = a.depth + frame_off; conf = a.conf ? a.conf + frame_off : nullptr; cam = a.cams + frame;
+        s3 = a.sim3 ? a.sim3 + ((a.flags & DA3S_SIM3_PER_FRAME) ? 13 * (size_t)frame : 0) : nullptr;
+        thr_dev = a.conf_thr_dev;
+        xyz = (OutT*)a.xyz + frame_off * 3; mask = a.mask ? a.mask + frame_off : nullptr;
+    }
+    const bool xform = world || s3 != nullptr;
     if (threadIdx.x == 0) {
-        const da3s_cam& c = a.cams[frame];
+        const da3s_cam& c = *cam;
         fr.fu = c.fu; fr.fv = c.fv; fr.cu = c.cu; fr.cv = c.cv;
         for (int k = 0; k < 9; ++k) fr.kinv[k] = c.kinv[k];
         fr.cuf = c.cu; fr.cvf = c.cv; fr.ifu = c.inv_fu; fr.ifv = c.inv_fv;
@@ -143,8 +159,7 @@ unproject_filter_kernel(K1Args a) {
                 m[r] = c.c2w[4 * r + 3];
             }
         }
-        if (a.sim3) {
-            const double* s3 = a.sim3 + ((a.flags & DA3S_SIM3_PER_FRAME) ? 13 * (size_t)frame : 0);
+        if (s3) {
             double s = s3[0];
             double sR[9], M2[9], m2[3];
             for (int k = 0; k < 9; ++k) sR[k] = s * s3[1 + k];
@@ -156,13 +171,11 @@ unproject_filter_kernel(K1Args a) {
         for (int k = 0; k < 9; ++k) { fr.M[k] = M[k]; fr.Mf[k] = (float)M[k]; }
         for (int k = 0; k < 3; ++k) { fr.m[k] = m[k]; fr.mf[k] = (float)m[k]; }
         blk_kept = 0;
+        thr_sh = thr_dev ? *thr_dev : a.conf_thr;
     }
     __syncthreads();
 
-    const float thr = a.conf_thr_dev ? *a.conf_thr_dev : a.conf_thr;
-    const size_t frame_off = (size_t)frame * (size_t)a.P;
-    const float* depth = a.depth + frame_off;
-    const float* conf = a.conf ? a.conf + frame_off : nullptr;
+    const float thr = thr_sh;
     unsigned int kept = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -186,15 +199,8 @@ unproject_filter_kernel(K1Args a) {
         if (g_end > n_groups) g_end = n_groups;
         const float4* d4 = reinterpret_cast<const float4*>(depth);
         const float4* c4 = reinterpret_cast<const float4*>(conf);
-        for (long long gb = g_begin; gb < g_end; gb += K1_THREADS) {      // block-uniform loop
-            const long long g = gb + threadIdx.x;
-            const bool active = g < g_end;
-            float dv[4] = {0, 0, 0, 0}, cv[4] = {0, 0, 0, 0};
-            if (active) {
-                float4 t = ldg_stream(d4 + g);
-                dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w;
-                if (conf) { float4 q = ldg_stream(c4 + g); cv[0] = q.x; cv[1] = q.y; cv[2] = q.z; cv[3] = q.w; }
-            }
+        // one float4 group = 4 pixels -> 12 output values; staged per warp so every store is coalesced
+        auto emit = [&](long long gb, long long g, bool active, const float* dv, const float* cv) {
             long long pix = g << 2;
             int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
             unsigned int mbits = 0;
@@ -208,9 +214,8 @@ unproject_filter_kernel(K1Args a) {
                 if (++u == a.W) { u = 0; ++v; }
             }
             kept += __popc(mbits);
-            if (a.mask && active) reinterpret_cast<unsigned int*>(a.mask + frame_off)[g] = mbits;
+            if (mask && active) reinterpret_cast<unsigned int*>(mask)[g] = mbits;
             if (sizeof(OutT) == 4) {
-                // stage this warp's 32 x 12 floats, then store 3 x 512 contiguous bytes per warp
                 float* ws = stage + warp * (32 * 12);
                 float4* ws4 = reinterpret_cast<float4*>(ws);
                 ws4[lane * 3 + 0] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
@@ -218,7 +223,7 @@ unproject_filter_kernel(K1Args a) {
                 ws4[lane * 3 + 2] = make_float4((float)o[8], (float)o[9], (float)o[10], (float)o[11]);
                 __syncwarp();
                 const long long warp_g0 = gb + warp * 32;                  // first group of this warp
-                float4* out4 = reinterpret_cast<float4*>((float*)a.xyz + frame_off * 3) + warp_g0 * 3;
+                float4* out4 = reinterpret_cast<float4*>(xyz) + warp_g0 * 3;
                 long long warp_groups = g_end - warp_g0;                   // groups this warp really owns
                 if (warp_groups > 32) warp_groups = 32;
 #pragma unroll
@@ -228,10 +233,26 @@ unproject_filter_kernel(K1Args a) {
                 }
                 __syncwarp();
             } else if (active) {
-                double* out = (double*)a.xyz + (frame_off + (size_t)pix) * 3;
+                double* out = (double*)xyz + (size_t)pix * 3;
 #pragma unroll
                 for (int j = 0; j < 12; ++j) out[j] = (double)o[j];
             }
+        };
+        for (long long gb = g_begin; gb < g_end; gb += 2 * K1_THREADS) {  // block-uniform; two groups in flight per thread
+            const long long g0 = gb + threadIdx.x, g1 = g0 + K1_THREADS;
+            const bool a0 = g0 < g_end, a1 = g1 < g_end;
+            float d0[4] = {0, 0, 0, 0}, c0[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+            float4 t0, t1, q0, q1;
+            if (a0) t0 = ldg_stream(d4 + g0);
+            if (a1) t1 = ldg_stream(d4 + g1);
+            if (conf && a0) q0 = ldg_stream(c4 + g0);
+            if (conf && a1) q1 = ldg_stream(c4 + g1);
+            if (a0) { d0[0] = t0.x; d0[1] = t0.y; d0[2] = t0.z; d0[3] = t0.w; }
+            if (a1) { d1[0] = t1.x; d1[1] = t1.y; d1[2] = t1.z; d1[3] = t1.w; }
+            if (conf && a0) { c0[0] = q0.x; c0[1] = q0.y; c0[2] = q0.z; c0[3] = q0.w; }
+            if (conf && a1) { c1[0] = q1.x; c1[1] = q1.y; c1[2] = q1.z; c1[3] = q1.w; }
+            emit(gb, g0, a0, d0, c0);
+            if (gb + K1_THREADS < g_end) emit(gb + K1_THREADS, g1, a1, d1, c1);
         }
     } else {
         const long long p_begin = (long long)blockIdx.x * a.groups_per_block * 4;
@@ -244,8 +265,8 @@ unproject_filter_kernel(K1Args a) {
             unproject_pixel<MODE>(fr, u, v, d, xform, X, Y, Z);
             bool k = keep_of(d, c, X, Y, Z);
             kept += k;
-            if (a.mask) a.mask[frame_off + pix] = k ? 1 : 0;
-            OutT* out = (OutT*)a.xyz + (frame_off + (size_t)pix) * 3;
+            if (mask) mask[pix] = k ? 1 : 0;
+            OutT* out = xyz + (size_t)pix * 3;
             out[0] = (OutT)X; out[1] = (OutT)Y; out[2] = (OutT)Z;
         }
     }
@@ -282,6 +303,7 @@ extern "C" int da3s_unproject_filter(da3s_ctx* ctx, const float* depth, const fl
     if (mode == 3) return DA3S_EINVAL;
     if (n_frames > 65535) return DA3S_EINVAL;
     K1Args a;
+    a.jobs = nullptr;
     a.depth = depth; a.conf = conf; a.cams = cams; a.H = H; a.W = W; a.P = (long long)H * W;
     a.flags = flags; a.conf_thr = conf_thr; a.conf_thr_dev = conf_thr_dev; a.conf_floor = conf_floor;
     a.depth_eps = depth_eps; a.sim3 = sim3; a.xyz = xyz_out; a.mask = mask_out; a.n_kept = n_kept;
@@ -290,6 +312,29 @@ extern "C" int da3s_unproject_filter(da3s_ctx* ctx, const float* depth, const fl
     // the vector path needs 16-byte aligned frames: P % 4 == 0 and aligned bases
     bool vec = (a.P % 4 == 0) && aligned16(depth) && (!conf || aligned16(conf)) && aligned16(xyz_out) &&
                (!mask_out || ((uintptr_t)mask_out & 3) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+#define K1_DISPATCH(M)                                                        \
+    return f64 ? launch_k1<M, double>(ctx, a, n_frames, vec, st)              \
+               : launch_k1<M, float>(ctx, a, n_frames, vec, st)
+    if (mode == DA3S_UNPROJ_CLOSED) { K1_DISPATCH(DA3S_UNPROJ_CLOSED); }
+    if (mode == DA3S_UNPROJ_KINV)   { K1_DISPATCH(DA3S_UNPROJ_KINV); }
+    K1_DISPATCH(DA3S_UNPROJ_FAST);
+#undef K1_DISPATCH
+}
+
+extern "C" int da3s_unproject_filter_jobs(da3s_ctx* ctx, const da3s_frame_job* jobs, int n_frames, int H, int W, int flags,
+                                          float conf_thr, float conf_floor, float depth_eps,
+                                          unsigned long long* n_kept, void* stream) {
+    if (!ctx || !jobs || n_frames <= 0 || H <= 0 || W <= 0) return DA3S_EINVAL;
+    if ((flags & DA3S_MASK_CONF_GT) && (flags & DA3S_MASK_CONF_GE)) return DA3S_EINVAL;
+    int mode = flags & DA3S_UNPROJ_MODEMASK;
+    if (mode == 3 || n_frames > 65535) return DA3S_EINVAL;
+    K1Args a;
+    a.jobs = jobs; a.depth = nullptr; a.conf = nullptr; a.cams = nullptr; a.H = H; a.W = W; a.P = (long long)H * W;
+    a.flags = flags; a.conf_thr = conf_thr; a.conf_thr_dev = nullptr; a.conf_floor = conf_floor; a.depth_eps = depth_eps;
+    a.sim3 = nullptr; a.xyz = nullptr; a.mask = nullptr; a.n_kept = n_kept; a.groups_per_block = 0;
+    const bool f64 = flags & DA3S_UNPROJ_OUT_F64;
+    const bool vec = (a.P % 4 == 0);        // per-job pointer alignment (16 B) is the caller's contract
     cudaStream_t st = (cudaStream_t)stream;
 #define K1_DISPATCH(M)                                                        \
     return f64 ? launch_k1<M, double>(ctx, a, n_frames, vec, st)              \

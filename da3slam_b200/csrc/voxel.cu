@@ -7,16 +7,14 @@
 // run to run and across GPUs), which floating-point atomics would not be.
 //
 // Contention is cut before it reaches L2: points of one warp that fall in the same voxel
-// (neighbouring pixels of a frame usually do) are combined with a labelled warp partition
-// and issue one set of atomics per distinct voxel.
+// (neighbouring pixels of a frame usually do) are combined (match.any + shuffles) and issue
+// one set of atomics per distinct voxel.  Compaction streams the table once and resets the
+// records it emits, so no separate clearing pass is needed between uses.
 //
 // Algorithmic bytes: 12 (+3 rgb, +1 mask) per input point read; 12 (+3) + 4 (+8 key) per
 // occupied voxel written.  Hash-table traffic (random 64 B records in L2/HBM) is what
 // actually bounds this kernel and is not counted as algorithmic.
 #include "common.cuh"
-#include <cooperative_groups.h>
-#include <cooperative_groups/reduce.h>
-namespace cg = cooperative_groups;
 
 #define VOX_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define VOX_BIAS (1 << 20)
@@ -37,16 +35,16 @@ __global__ void voxel_clear_kernel(unsigned long long* table, long long slots) {
 __global__ void __launch_bounds__(256)
 voxel_insert_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ mask,
                     long long n, float voxel, unsigned long long* __restrict__ table, long long slots,
-                    unsigned long long* __restrict__ dropped) {
+                    unsigned long long* __restrict__ counters /* [0]=voxels (set by finish) [1]=dropped */) {
     const double vd = (double)voxel;
+    const unsigned int lane = threadIdx.x & 31;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (mask && mask[i] == 0) continue;                    // masked points never touch their coordinates
         const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
-        bool ok = is_finite_f(px) && is_finite_f(py) && is_finite_f(pz);
-        if (mask) ok = ok && (mask[i] != 0);
+        if (!(is_finite_f(px) && is_finite_f(py) && is_finite_f(pz))) continue;
         double qx = __ddiv_rn((double)px, vd), qy = __ddiv_rn((double)py, vd), qz = __ddiv_rn((double)pz, vd);
         double kx = floor(qx), ky = floor(qy), kz = floor(qz);
-        ok = ok && (fabs(kx) < (double)VOX_BIAS) && (fabs(ky) < (double)VOX_BIAS) && (fabs(kz) < (double)VOX_BIAS);
-        if (!ok) continue;
+        if (!((fabs(kx) < (double)VOX_BIAS) && (fabs(ky) < (double)VOX_BIAS) && (fabs(kz) < (double)VOX_BIAS))) continue;
         unsigned long long key = ((unsigned long long)((long long)kx + VOX_BIAS) << 42) |
                                  ((unsigned long long)((long long)ky + VOX_BIAS) << 21) |
                                  (unsigned long long)((long long)kz + VOX_BIAS);
@@ -58,22 +56,33 @@ voxel_insert_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ r
             cr |= (unsigned long long)rgb[3 * i];
             gb = ((unsigned long long)rgb[3 * i + 1] << 32) | (unsigned long long)rgb[3 * i + 2];
         }
-        // combine the lanes of this warp that hit the same voxel
-        cg::coalesced_group active = cg::coalesced_threads();
-        cg::coalesced_group same = cg::labeled_partition(active, key);
-        sx = cg::reduce(same, sx, cg::plus<unsigned long long>());
-        sy = cg::reduce(same, sy, cg::plus<unsigned long long>());
-        sz = cg::reduce(same, sz, cg::plus<unsigned long long>());
-        cr = cg::reduce(same, cr, cg::plus<unsigned long long>());
-        gb = cg::reduce(same, gb, cg::plus<unsigned long long>());
-        if (same.thread_rank() != 0) continue;
+        // combine the lanes of this warp that hit the same voxel; a lane alone in its voxel (the
+        // common case) skips the exchange entirely
+        const unsigned int act = __activemask();
+        const unsigned int peers = __match_any_sync(act, key);
+        const unsigned int leader = __ffs(peers) - 1;
+        if (peers != (1u << lane)) {
+            unsigned int rest = peers & ~(1u << leader);            // identical for every lane of the group
+            while (rest) {
+                const int src = __ffs(rest) - 1;
+                rest &= rest - 1;
+                const unsigned long long ax = __shfl_sync(peers, sx, src), ay = __shfl_sync(peers, sy, src);
+                const unsigned long long az = __shfl_sync(peers, sz, src), ac = __shfl_sync(peers, cr, src);
+                const unsigned long long ag = __shfl_sync(peers, gb, src);
+                if (lane == leader) { sx += ax; sy += ay; sz += az; cr += ac; gb += ag; }
+            }
+            if (lane != leader) continue;
+        }
         unsigned long long slot = vox_hash(key) & (unsigned long long)(slots - 1);
         bool placed = false;
         for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
             unsigned long long* rec = table + slot * VOX_REC;
             unsigned long long cur = *((volatile unsigned long long*)rec);
-            if (cur == VOX_EMPTY) cur = atomicCAS(rec, VOX_EMPTY, key);
-            if (cur == VOX_EMPTY || cur == key) {
+            if (cur == VOX_EMPTY) {
+                cur = atomicCAS(rec, VOX_EMPTY, key);
+                if (cur == VOX_EMPTY) cur = key;
+            }
+            if (cur == key) {
                 atomicAdd(rec + 1, sx); atomicAdd(rec + 2, sy); atomicAdd(rec + 3, sz);
                 atomicAdd(rec + 4, cr);
                 if (rgb) atomicAdd(rec + 5, gb);
@@ -82,69 +91,122 @@ voxel_insert_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ r
             }
             slot = (slot + 1) & (unsigned long long)(slots - 1);
         }
-        if (!placed) atomicAdd(dropped, cr >> 32);
+        if (!placed) atomicAdd(&counters[1], cr >> 32);
     }
 }
 
-__global__ void __launch_bounds__(256)
-voxel_compact_kernel(const unsigned long long* __restrict__ table, long long slots, float voxel, long long max_voxels,
-                     float* __restrict__ xyz_out, uint8_t* __restrict__ rgb_out, int32_t* __restrict__ count_out,
-                     long long* __restrict__ key_out, unsigned long long* __restrict__ n_voxels) {
+// Compaction: one streaming pass over the table.  Empty slots cost one 32-byte sector; an
+// occupied record is emitted and RESET in place, so the table is clean for the next begin()
+// without a separate clearing pass.  Output positions come from a block-wide prefix sum and ONE
+// global atomic per block iteration (1024 slots) — a per-warp atomic on a single counter
+// serialises at L2 and was the whole cost of this kernel (profiles/r1_*).
+#define VC_THREADS 256
+#define VC_PER_THREAD 4
+__global__ void __launch_bounds__(VC_THREADS)
+voxel_compact_kernel(unsigned long long* __restrict__ table, long long slots, unsigned long long* __restrict__ counters,
+                     float voxel, long long max_voxels, float* __restrict__ xyz_out, uint8_t* __restrict__ rgb_out,
+                     int32_t* __restrict__ count_out, long long* __restrict__ key_out) {
+    __shared__ unsigned int warp_tot[VC_THREADS / 32];
+    __shared__ unsigned long long blk_base;
     const double vd = (double)voxel;
-    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long* rec = table + s * VOX_REC;
-        unsigned long long key = rec[0];
-        if (key == VOX_EMPTY) continue;
-        unsigned long long o = atomicAdd(n_voxels, 1ull);
-        if ((long long)o >= max_voxels) continue;
-        const unsigned long long cr = rec[4], gb = rec[5];
-        const unsigned long long cnt = cr >> 32;
-        const double inv = 1.0 / 4294967296.0;
-        double k[3] = {(double)((long long)((key >> 42) & 0x1FFFFF) - VOX_BIAS),
-                       (double)((long long)((key >> 21) & 0x1FFFFF) - VOX_BIAS),
-                       (double)((long long)(key & 0x1FFFFF) - VOX_BIAS)};
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long chunk = (long long)VC_THREADS * VC_PER_THREAD;
+    for (long long c0 = (long long)blockIdx.x * chunk; c0 < slots; c0 += (long long)gridDim.x * chunk) {     // block-uniform
+        unsigned long long keys[VC_PER_THREAD];
+        unsigned int mine = 0;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            // position = f32((k + (sum_q / count) / 2^32) * voxel), each step rounded once
-            double mf = __dmul_rn(__ddiv_rn((double)rec[1 + a], (double)cnt), inv);
-            xyz_out[3 * o + a] = (float)__dmul_rn(__dadd_rn(k[a], mf), vd);
+        for (int j = 0; j < VC_PER_THREAD; ++j) {
+            const long long s = c0 + (long long)j * VC_THREADS + threadIdx.x;
+            keys[j] = (s < slots) ? table[(size_t)s * VOX_REC] : VOX_EMPTY;
+            mine += (keys[j] != VOX_EMPTY);
         }
-        if (rgb_out) {
-            unsigned long long r = cr & 0xFFFFFFFFull, g = gb >> 32, b = gb & 0xFFFFFFFFull;
-            rgb_out[3 * o]     = (uint8_t)((2 * r + cnt) / (2 * cnt));
-            rgb_out[3 * o + 1] = (uint8_t)((2 * g + cnt) / (2 * cnt));
-            rgb_out[3 * o + 2] = (uint8_t)((2 * b + cnt) / (2 * cnt));
+        // exclusive prefix of `mine` over the block
+        unsigned int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        count_out[o] = (int32_t)cnt;
-        if (key_out) key_out[o] = (long long)key;
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < VC_THREADS / 32; ++w) { if (w < warp) before += warp_tot[w]; total += warp_tot[w]; }
+        if (threadIdx.x == 0 && total) blk_base = atomicAdd(&counters[0], (unsigned long long)total);
+        __syncthreads();
+        unsigned long long o = blk_base + before + (incl - mine);
+        if (total) {
+#pragma unroll
+            for (int j = 0; j < VC_PER_THREAD; ++j) {
+                const unsigned long long key = keys[j];
+                if (key == VOX_EMPTY) continue;
+                const long long s = c0 + (long long)j * VC_THREADS + threadIdx.x;
+                unsigned long long* rec = table + (size_t)s * VOX_REC;
+                const unsigned long long s_x = rec[1];
+                const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rec + 2);     // sum_y, sum_z
+                const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(rec + 4);     // (n, sum_r), (sum_g, sum_b)
+                *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2(VOX_EMPTY, 0ull);
+                *reinterpret_cast<ulonglong2*>(rec + 2) = make_ulonglong2(0ull, 0ull);
+                *reinterpret_cast<ulonglong2*>(rec + 4) = make_ulonglong2(0ull, 0ull);
+                const unsigned long long oo = o++;
+                if ((long long)oo >= max_voxels) continue;
+                const unsigned long long cr = b.x, gb = b.y, cnt = cr >> 32;
+                const double inv = 1.0 / 4294967296.0;
+                const unsigned long long sq[3] = {s_x, a.x, a.y};
+                double k[3] = {(double)((long long)((key >> 42) & 0x1FFFFF) - VOX_BIAS),
+                               (double)((long long)((key >> 21) & 0x1FFFFF) - VOX_BIAS),
+                               (double)((long long)(key & 0x1FFFFF) - VOX_BIAS)};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    // position = f32((k + (sum_q / count) / 2^32) * voxel), each step rounded once
+                    double mf = __dmul_rn(__ddiv_rn((double)sq[q], (double)cnt), inv);
+                    xyz_out[3 * oo + q] = (float)__dmul_rn(__dadd_rn(k[q], mf), vd);
+                }
+                if (rgb_out) {
+                    unsigned long long r = cr & 0xFFFFFFFFull, g = gb >> 32, bl = gb & 0xFFFFFFFFull;
+                    rgb_out[3 * oo]     = (uint8_t)((2 * r + cnt) / (2 * cnt));
+                    rgb_out[3 * oo + 1] = (uint8_t)((2 * g + cnt) / (2 * cnt));
+                    rgb_out[3 * oo + 2] = (uint8_t)((2 * bl + cnt) / (2 * cnt));
+                }
+                count_out[oo] = (int32_t)cnt;
+                if (key_out) key_out[oo] = (long long)key;
+            }
+        }
+        __syncthreads();                                       // blk_base / warp_tot are reused next iteration
     }
 }
 
 extern "C" int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots, void* stream) {
-    if (!ctx || table_slots < 1024 || (table_slots & (table_slots - 1))) return DA3S_EINVAL;
-    size_t bytes = (size_t)table_slots * VOX_REC * 8 + 256;
-    if (bytes > ctx->ws_bytes) return DA3S_ENOMEM;
-    ctx->vox_bytes = 0;
-    ws_reset(ctx);
-    // the table owns the tail of the workspace until da3s_voxel_finish
-    size_t start = (ctx->ws_bytes - bytes) & ~(size_t)255;
-    ctx->vox_bytes = ctx->ws_bytes - start;
-    ctx->vox_keys = (unsigned long long*)(ctx->ws + start);
-    ctx->vox_dropped = ctx->vox_keys + (size_t)table_slots * VOX_REC;
-    ctx->vox_slots = table_slots;
+    if (!ctx || table_slots < 1024 || (table_slots & (table_slots - 1)) || table_slots > (1ll << 31)) return DA3S_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    long long words = table_slots * VOX_REC;
-    int blocks = (int)((words + 255) / 256 > (long long)ctx->sm_count * 32 ? (long long)ctx->sm_count * 32 : (words + 255) / 256);
-    voxel_clear_kernel<<<blocks, 256, 0, st>>>(ctx->vox_keys, table_slots);
-    DA3S_LAUNCH_CHECK(ctx);
-    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->vox_dropped, 0, 8, st));
+    // layout of the reserved tail: records [slots][8] u64 | counters [4] u64
+    size_t bytes = (size_t)table_slots * VOX_REC * 8 + 256;
+    const bool reuse = (ctx->vox_slots == table_slots) && ctx->vox_clean && ctx->vox_bytes > 0;
+    if (!reuse) {
+        if (bytes > ctx->ws_bytes) return DA3S_ENOMEM;
+        ctx->vox_bytes = 0;
+        ws_reset(ctx);
+        size_t start = (ctx->ws_bytes - bytes) & ~(size_t)255;
+        ctx->vox_bytes = ctx->ws_bytes - start;               // stays reserved until a different size is requested
+        ctx->vox_keys = (unsigned long long*)(ctx->ws + start);
+        ctx->vox_dropped = ctx->vox_keys + (size_t)table_slots * VOX_REC;      // counters[4]
+        ctx->vox_occ = nullptr;
+        ctx->vox_slots = table_slots;
+        long long words = table_slots * VOX_REC;
+        long long want = (words + 255) / 256, cap = (long long)ctx->sm_count * 32;
+        voxel_clear_kernel<<<(int)(want > cap ? cap : want), 256, 0, st>>>(ctx->vox_keys, table_slots);
+        DA3S_LAUNCH_CHECK(ctx);
+    }
+    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->vox_dropped, 0, 32, st));
+    ctx->vox_clean = false;
+    ctx->vox_active = true;
     return DA3S_OK;
 }
 
 extern "C" int da3s_voxel_insert(da3s_ctx* ctx, const float* xyz, const uint8_t* rgb, const uint8_t* mask,
                                  long long n, float voxel, void* stream) {
     if (!ctx || !xyz || n < 0 || !(voxel > 0.0f)) return DA3S_EINVAL;
-    if (!ctx->vox_slots) return DA3S_EINVAL;
+    if (!ctx->vox_active) return DA3S_EINVAL;
     if (n == 0) return DA3S_OK;
     long long want = (n + 255) / 256, cap = (long long)ctx->sm_count * 32;
     int blocks = (int)(want > cap ? cap : want);
@@ -158,17 +220,15 @@ extern "C" int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxel
                                  int32_t* count_out, long long* key_out, unsigned long long* n_voxels,
                                  unsigned long long* n_dropped, void* stream) {
     if (!ctx || !xyz_out || !count_out || !n_voxels || max_voxels <= 0 || !(voxel > 0.0f)) return DA3S_EINVAL;
-    if (!ctx->vox_slots) return DA3S_EINVAL;
+    if (!ctx->vox_active) return DA3S_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(n_voxels, 0, 8, st));
-    long long want = (ctx->vox_slots + 255) / 256, cap = (long long)ctx->sm_count * 32;
-    int blocks = (int)(want > cap ? cap : want);
-    voxel_compact_kernel<<<blocks, 256, 0, st>>>(ctx->vox_keys, ctx->vox_slots, voxel, max_voxels, xyz_out, rgb_out,
-                                                 count_out, key_out, n_voxels);
+    voxel_compact_kernel<<<ctx->sm_count * 8, VC_THREADS, 0, st>>>(ctx->vox_keys, ctx->vox_slots, ctx->vox_dropped, voxel, max_voxels,
+                                                            xyz_out, rgb_out, count_out, key_out);
     DA3S_LAUNCH_CHECK(ctx);
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_voxels, ctx->vox_dropped, 8, cudaMemcpyDeviceToDevice, st));
     if (n_dropped)
-        DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_dropped, ctx->vox_dropped, 8, cudaMemcpyDeviceToDevice, st));
-    ctx->vox_slots = 0;
-    ctx->vox_bytes = 0;                      // the tail of the workspace is free again (stream order)
+        DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_dropped, ctx->vox_dropped + 1, 8, cudaMemcpyDeviceToDevice, st));
+    ctx->vox_active = false;
+    ctx->vox_clean = true;          // every occupied record was reset in place by the compaction pass
     return DA3S_OK;
 }

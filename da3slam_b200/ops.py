@@ -140,6 +140,38 @@ def unproject_filter(depth, conf, cams, *, mode="closed", world=False, out_f64=F
     return xyz, (mask.view(torch.bool) if mask is not None else None), cnt
 
 
+def make_frame_jobs(jobs, device) -> torch.Tensor:
+    """jobs: list of dicts(depth, conf, cam, sim3, conf_thr, xyz, mask) of CUDA tensors / None (views into
+    persistent buffers).  Returns the device job table for unproject_filter_jobs."""
+    arr = (L.FrameJob * len(jobs))()
+    for i, j in enumerate(jobs):
+        for name in ("depth", "conf", "cam", "sim3", "conf_thr", "xyz", "mask"):
+            t = j.get(name)
+            if t is None:
+                continue
+            if not t.is_cuda:
+                raise RuntimeError("frame job tensors must live on the GPU")
+            if name in ("depth", "conf", "xyz") and t.data_ptr() % 16:
+                raise L.Da3sError(L.EALIGN, "make_frame_jobs", f"{name} is not 16-byte aligned")
+            setattr(arr[i], name, t.data_ptr())
+    raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+    return torch.from_numpy(raw).to(device)
+
+
+def unproject_filter_jobs(job_table: torch.Tensor, n_frames: int, H: int, W: int, *, mode="fast", world=True, out_f64=False,
+                          conf_cmp=None, conf_thr=0.0, conf_floor=None, depth_eps=None, world_z=False, n_kept=None):
+    """One launch over all frames of the job table (see da3s_unproject_filter_jobs)."""
+    ctx = context(job_table.device)
+    flags = {"closed": L.UNPROJ_CLOSED, "kinv": L.UNPROJ_KINV, "fast": L.UNPROJ_FAST}[mode]
+    flags |= (L.UNPROJ_WORLD if world else 0) | (L.UNPROJ_OUT_F64 if out_f64 else 0)
+    flags |= {None: 0, ">": L.MASK_CONF_GT, ">=": L.MASK_CONF_GE}[conf_cmp]
+    flags |= (L.MASK_CONF_FLOOR if conf_floor is not None else 0) | (L.MASK_DEPTH if depth_eps is not None else 0)
+    flags |= L.MASK_WORLD_Z if world_z else 0
+    rc = ctx.lib.da3s_unproject_filter_jobs(ctx.h, _ptr(job_table), n_frames, H, W, flags, float(conf_thr),
+                                            float(conf_floor or 0.0), float(depth_eps or 0.0), _ptr(n_kept), _stream(job_table))
+    L.check(rc, "da3s_unproject_filter_jobs")
+
+
 def sim3_row(s, R, t, device) -> torch.Tensor:
     row = np.empty(13, np.float64)
     row[0] = s
@@ -287,12 +319,13 @@ def align_pairs(pairs: torch.Tensor, n_pairs: int, overlap: int, H: int, W: int,
     return rows, aux, counts
 
 
-def accumulate_sim3(rows: torch.Tensor) -> torch.Tensor:
+def accumulate_sim3(rows: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """[n,16] pair rows -> [n+1,13] cumulative Sim(3) (identity first), on the device."""
     rows = rows.contiguous()
     n = rows.shape[0]
     ctx = context(rows.device)
-    cum = torch.empty((n + 1, 13), dtype=torch.float64, device=rows.device)
+    cum = out if out is not None else torch.empty((n + 1, 13), dtype=torch.float64, device=rows.device)
+    assert cum.shape == (n + 1, 13) and cum.dtype == torch.float64 and cum.is_contiguous()
     L.check(ctx.lib.da3s_accumulate_sim3(ctx.h, _ptr(rows, "rows", torch.float64), n, _ptr(cum), _stream(rows)),
             "da3s_accumulate_sim3")
     return cum

@@ -157,7 +157,7 @@ class SequencePlan:
         if self.opts.n_hyp > 0:
             self.sample_idx = sample_idx.to(self.dev, torch.int32).contiguous()
         self.rows = None
-        self.cum = None
+        self.cum = torch.empty((self.n, 13), dtype=torch.float64, device=self.dev)
         if export:
             # frames re-observed by the next submap are exported once (solver.py:100-114 adds them twice)
             self.first = [0] + [overlap if skip_overlap else 0] * (self.n - 1)
@@ -167,6 +167,16 @@ class SequencePlan:
             self.xyz = [torch.empty((self.F - f0, self.H, self.W, 3), dtype=torch.float32, device=self.dev) for f0 in self.first]
             self.mask = [torch.empty((self.F - f0, self.H, self.W), dtype=torch.uint8, device=self.dev) for f0 in self.first]
             self.n_kept = torch.zeros((1,), dtype=torch.int64, device=self.dev)
+            # one job per exported frame: static pointers into the submaps, the cumulative Sim(3) table,
+            # the percentile records and the output buffers -> the whole export is ONE unprojection launch
+            jobs = []
+            for k, (sm, f0) in enumerate(zip(submaps, self.first)):
+                for f in range(f0, self.F):
+                    jobs.append(dict(depth=sm.depth[f], conf=sm.conf[f], cam=sm.cams[f], sim3=self.cum[k],
+                                     conf_thr=self.percentiles.value_ptr_tensor(k), xyz=self.xyz[k][f - f0],
+                                     mask=self.mask[k][f - f0]))
+            self.n_jobs = len(jobs)
+            self.job_table = ops.make_frame_jobs(jobs, self.dev)
             total = sum(x.numel() // 3 for x in self.xyz)
             if table_slots is None:
                 table_slots = 1 << max(12, int(np.ceil(np.log2(max(total // 4, 4096)))))
@@ -185,18 +195,14 @@ class SequencePlan:
         self.rows, _, _ = ops.align_pairs(self.pair_table, self.n_pairs, self.overlap, self.H, self.W, self.opts,
                                           self.sample_idx)
         mark("align")
-        self.cum = ops.accumulate_sim3(self.rows)
+        ops.accumulate_sim3(self.rows, out=self.cum)
         if not self.export:
             mark("chain")
             return
         self.percentiles.run()
         mark("percentile")
-        self.n_kept.zero_()
-        for k, sm in enumerate(self.submaps):
-            f0 = self.first[k]
-            ops.unproject_filter(sm.depth[f0:], sm.conf[f0:], sm.cams[f0:], mode=self.mode, world=True, sim3=self.cum[k],
-                                 conf_cmp=">=", conf_thr_dev=self.percentiles.value_ptr_tensor(k), conf_floor=0.0,
-                                 depth_eps=1e-6, xyz_out=self.xyz[k], mask_out=self.mask[k], want_count=False)
+        ops.unproject_filter_jobs(self.job_table, self.n_jobs, self.H, self.W, mode=self.mode, world=True, conf_cmp=">=",
+                                  conf_floor=0.0, depth_eps=1e-6)
         mark("unproject")
         self.grid.begin()
         mark("voxel_clear")

@@ -97,6 +97,23 @@ int da3s_unproject_filter(da3s_ctx* ctx, const float* depth, const float* conf, 
                           const double* sim3 /* nullable: s, R[9] row-major, t[3] */,
                           void* xyz_out, uint8_t* mask_out, unsigned long long* n_kept, void* stream);
 
+/* Batched form: one launch over frames that live anywhere (e.g. every frame of every submap of a
+ * sequence, each with its own cumulative Sim(3) and its own device-resident threshold).  `jobs`
+ * is a DEVICE array; every depth/conf/xyz pointer must be 16-byte aligned, every mask pointer
+ * 4-byte aligned, and H*W a multiple of 4.  conf_thr is used where a job's conf_thr is null. */
+typedef struct da3s_frame_job {
+    const float*    depth;      /* [H,W] */
+    const float*    conf;       /* [H,W] or null */
+    const da3s_cam* cam;        /* this frame's camera record */
+    const double*   sim3;       /* [13] or null */
+    const float*    conf_thr;   /* device scalar or null */
+    void*           xyz;        /* [H,W,3] float32 (float64 with DA3S_UNPROJ_OUT_F64) */
+    uint8_t*        mask;       /* [H,W] or null */
+} da3s_frame_job;
+int da3s_unproject_filter_jobs(da3s_ctx* ctx, const da3s_frame_job* jobs, int n_frames, int H, int W, int flags,
+                               float conf_thr, float conf_floor, float depth_eps,
+                               unsigned long long* n_kept, void* stream);
+
 /* ---- K5: apply Sim(3) to a cloud -----------------------------------------------------
  * Replaces utils/geometry.py:43-70 (apply_sim3_transform): out = s * (p R^T) + t.
  * in_f64/out_f64 select float64 arrays (the reference returns float64 for float32 input). */
@@ -169,6 +186,8 @@ typedef struct da3s_align_opts {
     int    n_hyp;               /* RANSAC hypotheses per pair, 0 = no RANSAC (oracle/SPEC.md 4)    */
     float  ransac_thr;          /* inlier iff r^2 < thr^2 (strict, align_geometry.py:123)          */
     int    ransac_min_inliers;  /* 20 (align_geometry.py:124): fewer -> identity, status 2          */
+    int    precise;             /* 0: float32 micro-batches flushed into float64 accumulators (default,
+                                      <= 1e-8 from the float64 oracle); 1: float64 per correspondence      */
 } da3s_align_opts;
 void da3s_align_opts_default(da3s_align_opts* opts);
 
@@ -188,7 +207,7 @@ typedef struct da3s_pair_aux {  /* optional per-pair diagnostics, float64[8] per
     double median_a, median_b;  /* confidence medians                            */
     double best_hyp;            /* index of the winning hypothesis or -1         */
     double best_count;          /* its inlier count                              */
-    double mean_residual;       /* mean residual of the last IRLS pass           */
+    double mean_residual;       /* residual of the last IRLS pass: rms (default kernel) or mean |r| (precise) */
     double last_change;         /* |ds| + ||dR||_F + ||dt|| of the last update   */
 } da3s_pair_aux;
 

@@ -416,3 +416,68 @@ def test_errors_are_loud(cuda):
         L.check(rc, "null args")
     with pytest.raises(ValueError):
         ops.unproject_filter(d, d, cams, conf_cmp="<")
+
+
+# ----------------------------------------------------------------------------------------
+# whole step: SequencePlan (what bench.py times) against the oracle pipeline
+# ----------------------------------------------------------------------------------------
+def test_sequence_plan_end_to_end(cuda):
+    from da3slam_b200.pipeline import SequencePlan
+    H, W, F, n = 48, 64, 3, 4
+    subs, gt = synth.make_sequence(n, F, H, W, overlap=1, seed=77, with_images=True)
+    dsubs = [DeviceSubmap.from_prediction(s, cuda) for s in subs]
+    plan = SequencePlan(dsubs, overlap=1, voxel=0.05, conf_percentile=65.0, table_slots=1 << 16, world=1)
+    for _ in range(2):                                        # twice: the grid must come back clean
+        plan.run()
+        out = plan.read(sort=True)
+    rows = out["rows"]
+    chain = []
+    for k in range(n - 1):
+        o = sp.align_pair(subs[k], subs[k + 1], overlap=1, world=True)
+        assert int(rows[k, 13]) == o["n_valid"] and abs(rows[k, 0] - o["s"]) <= REL * o["s"]
+        chain.append((o["s"], o["R"], o["t"]))
+    acc = rp.accumulate_sim3(chain)
+    cum = out["cum"]
+    for k in range(n):
+        assert abs(cum[k, 0] - acc[k][0]) <= REL * acc[k][0] and rel_err(cum[k, 1:10].reshape(3, 3), acc[k][1]) <= REL
+        assert np.abs(cum[k, 10:13] - acc[k][2]).max() <= REL * max(1.0, np.abs(acc[k][2]).max())
+    all_xyz, all_rgb, all_mask = [], [], []
+    for k in range(n):
+        f0 = plan.first[k]
+        conf, depth = subs[k]["conf"][f0:], subs[k]["depth"][f0:]
+        ref_mask, thr = rp.viewer_conf_mask(conf.reshape(-1), 65.0)         # viewer.py:333-336
+        ref_mask = ref_mask & (depth.reshape(-1) > np.float32(1e-6))
+        got_mask = plan.mask[k].cpu().numpy().astype(bool).reshape(-1)
+        assert np.array_equal(got_mask, ref_mask)                            # exact percentile + '>=' mask: bit-exact
+        cam = sp.cam_fast_f32(depth, subs[k]["intrinsics"][f0:])
+        world = rp.apply_sim3(sp.world_from_cam_f64(cam, subs[k]["extrinsics"][f0:]), *acc[k])
+        got = plan.xyz[k].cpu().numpy()
+        assert np.abs(got - world).max() <= 2e-6 * max(1.0, np.abs(world).max())
+        all_xyz.append(got.reshape(-1, 3)); all_mask.append(got_mask)
+        all_rgb.append(subs[k]["processed_images"][f0:].reshape(-1, 3))
+    xyz, col, cnt, key = sp.voxel_downsample(np.concatenate(all_xyz), 0.05, np.concatenate(all_rgb), np.concatenate(all_mask))
+    assert np.array_equal(out["voxel_key"].cpu().numpy(), key) and np.array_equal(out["voxel_count"].cpu().numpy(), cnt)
+    assert np.array_equal(out["voxel_xyz"].cpu().numpy(), xyz) and np.array_equal(out["voxel_rgb"].cpu().numpy(), col)
+
+
+def test_unproject_jobs_equals_flat_launch(cuda):
+    rng = np.random.default_rng(12)
+    n, H, W = 5, 30, 44
+    depth = synth.smooth_depth(rng, n, H, W)
+    conf = synth.da3_like_conf(rng, n, H, W)
+    d, c = dev_t(depth, cuda), dev_t(conf, cuda)
+    cams = ops.build_cams(dev_t(synth.make_intrinsics(n, H, W), cuda), dev_t(synth.trajectory_w2c(rng, n).astype(np.float32), cuda))
+    rows = torch.stack([ops.sim3_row(*synth.random_sim3(rng), cuda) for _ in range(n)])
+    thr = torch.tensor([0.3, 0.5], dtype=torch.float32, device=cuda)
+    ref_xyz, ref_mask, ref_cnt = [], [], 0
+    for f in range(n):
+        x, m, k = ops.unproject_filter(d[f:f + 1], c[f:f + 1], cams[f:f + 1], mode="fast", world=True, sim3=rows[f], conf_cmp=">=",
+                                       conf_thr_dev=thr[f % 2:f % 2 + 1], conf_floor=0.0, depth_eps=1e-6)
+        ref_xyz.append(x); ref_mask.append(m); ref_cnt += int(k.item())
+    xyz = torch.empty((n, H, W, 3), dtype=torch.float32, device=cuda)
+    mask = torch.empty((n, H, W), dtype=torch.uint8, device=cuda)
+    jobs = [dict(depth=d[f], conf=c[f], cam=cams[f], sim3=rows[f], conf_thr=thr[f % 2:f % 2 + 1], xyz=xyz[f], mask=mask[f]) for f in range(n)]
+    kept = torch.zeros((1,), dtype=torch.int64, device=cuda)
+    ops.unproject_filter_jobs(ops.make_frame_jobs(jobs, cuda), n, H, W, mode="fast", world=True, conf_cmp=">=", conf_floor=0.0,
+                              depth_eps=1e-6, n_kept=kept)
+    assert torch.equal(xyz, torch.cat(ref_xyz)) and torch.equal(mask.bool(), torch.cat(ref_mask)) and int(kept.item()) == ref_cnt
