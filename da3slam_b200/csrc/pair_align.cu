@@ -16,6 +16,7 @@
 // moments — so world mode costs nothing per pixel.
 #include "common.cuh"
 #include "sim3_math.cuh"
+#include <cooperative_groups.h>
 
 int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, long long max_n,
                      da3s_select_out* out, cudaStream_t st);
@@ -44,6 +45,9 @@ struct PairArgs {
     float gate_thr2;
     double* partials;                       // [n_pairs][overlap*tiles][MOM_LEN]
     unsigned int* tickets;                  // [n_pairs]
+    int* n_active;                          // pairs active when the IRLS kernel starts (constant while it runs)
+    int* done_count;                        // [max_iterations] pairs finished during pass p (persistent kernel's exit test)
+    unsigned long long* work_counter;       // [max_iterations] next (pair, tile) item of pass p
     double huber_delta, tol;
     int max_iterations, min_points, precise;
     double* rows;                           // [n_pairs][16]
@@ -75,8 +79,9 @@ __device__ __forceinline__ void load_frame_const(FrameConst& fc, const da3s_pair
     }
     if (a.eff) {
         const double* e = a.eff + ((size_t)pair * a.overlap + frame) * EFF_LEN;
-        for (int k = 0; k < 9; ++k) { fc.By[k] = e[k]; fc.Bx[k] = e[9 + k]; fc.Bpf[k] = (float)e[21 + k]; }
-        for (int k = 0; k < 3; ++k) { fc.c[k] = e[18 + k]; fc.cpf[k] = (float)e[30 + k]; }
+        // written by another block in the previous pass of the persistent kernel: read through L2
+        for (int k = 0; k < 9; ++k) { fc.By[k] = __ldcg(e + k); fc.Bx[k] = __ldcg(e + 9 + k); fc.Bpf[k] = (float)__ldcg(e + 21 + k); }
+        for (int k = 0; k < 3; ++k) { fc.c[k] = __ldcg(e + 18 + k); fc.cpf[k] = (float)__ldcg(e + 30 + k); }
     }
 }
 
@@ -142,7 +147,7 @@ __device__ __noinline__ void set_effective(const PairArgs& a, int pair, const Pa
     }
 }
 
-__device__ __noinline__ void solve_pair(const PairArgs& a, int pair, const double* mom /* world or camera moments */) {
+__device__ __noinline__ void solve_pair(const PairArgs& a, int pair, const double* mom /* world or camera moments */, int pass = 0) {
     PairState st = a.state[pair];
     const double n = mom[MOM_N];
     st.n_valid = n;
@@ -153,6 +158,7 @@ __device__ __noinline__ void solve_pair(const PairArgs& a, int pair, const doubl
         st.status = 1; st.done = 1; st.change = 0.0;
         a.state[pair] = st;
         write_row(a, pair, st);
+        if (a.done_count) atomicAdd(&a.done_count[pass], 1);
         return;
     }
     double s, R[9], t[3];
@@ -168,9 +174,11 @@ __device__ __noinline__ void solve_pair(const PairArgs& a, int pair, const doubl
     st.iters += 1;
     st.mean_res = a.precise ? mom[MOM_SR] / n : sqrt(mom[MOM_SR] / n);   // mean |r| (float64 kernel) or rms (mixed kernel)
     if (!a.huber || st.change < a.tol || st.iters >= a.max_iterations) st.done = 1;
-    a.state[pair] = st;
     if (st.done) write_row(a, pair, st);
     else set_effective(a, pair, st);
+    __threadfence();                        // rows / residual map before the flag that releases them
+    a.state[pair] = st;
+    if (st.done && a.done_count) atomicAdd(&a.done_count[pass], 1);
 }
 
 // ---------------------------------------------------------------------------------
@@ -345,9 +353,13 @@ pair_moments_kernel(PairArgs a) {
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// PERSISTENT: one cooperative launch runs every IRLS iteration.  Blocks stride over the
+// (pair, tile) work items of the pairs that have not converged, the last block of a pair
+// (ticket) solves it, a grid-wide barrier separates iterations, and the kernel ends as soon as
+// no pair is active — no empty launches, no host involvement between iterations.
 template <bool VEC, bool WORLD_UNUSED, bool HUBER>
 __global__ void __launch_bounds__(PM_THREADS, 3)
-pair_moments_mixed_kernel(PairArgs a) {
+pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     __shared__ double red[MOM_LEN][PM_THREADS];     // block reduction scratch (25.6 KB)
     __shared__ FrameConst fc;
     __shared__ float piv[6];                        // pivot: x (source) then y (target), float32 camera-frame point
@@ -355,11 +367,30 @@ pair_moments_mixed_kernel(PairArgs a) {
     __shared__ double wmom[MOM_LEN];
     __shared__ double part[MOM_LEN][PM_THREADS / 32];
     __shared__ bool is_last;
-    const int pair = blockIdx.y;
-    if (a.state[pair].done) return;
+    __shared__ int pair_done;
+    __shared__ long long cur_item;
+    cooperative_groups::grid_group grid_g = cooperative_groups::this_grid();
+    const int n_tiles_all = a.overlap * a.tiles_per_frame;
+    const long long n_items = (long long)a.n_pairs * n_tiles_all;
+  for (int pass = 0; pass < max_passes; ++pass) {
+   for (;;) {
+    // dynamic work distribution: the block that happens to solve a pair (serial epilogue) simply
+    // takes fewer tiles, instead of delaying a fixed share of them
+    __syncthreads();                                // shared scratch of the previous item is free
+    if (threadIdx.x == 0) {
+        long long it = (long long)atomicAdd(&a.work_counter[pass], 1ull);
+        cur_item = it;
+        pair_done = (it < n_items) ? *((volatile int*)&a.state[(int)(it / n_tiles_all)].done) : 1;
+    }
+    __syncthreads();
+    const long long item = cur_item;
+    if (item >= n_items) break;
+    const int pair = (int)(item / n_tiles_all);
+    const int item_tile = (int)(item - (long long)pair * n_tiles_all);
+    if (pair_done) continue;                        // block-uniform: converged pairs cost nothing
     const da3s_pair pr = a.pairs[pair];
-    const int frame = blockIdx.x / a.tiles_per_frame;
-    const int tile = blockIdx.x - frame * a.tiles_per_frame;
+    const int frame = item_tile / a.tiles_per_frame;
+    const int tile = item_tile - frame * a.tiles_per_frame;
     const size_t foff = (size_t)frame * (size_t)a.P;
     const float* dA = pr.depth_a + foff; const float* cA = pr.conf_a + foff;
     const float* dB = pr.depth_b + foff; const float* cB = pr.conf_b + foff;
@@ -508,7 +539,7 @@ pair_moments_mixed_kernel(PairArgs a) {
     if (threadIdx.x < MOM_LEN) {
         double v = part[threadIdx.x][0];
         for (int w = 1; w < PM_THREADS / 32; ++w) v = (threadIdx.x == MOM_WMAX) ? fmax(v, part[threadIdx.x][w]) : v + part[threadIdx.x][w];
-        a.partials[((size_t)pair * n_tiles + blockIdx.x) * MOM_LEN + threadIdx.x] = v;     // still about the frame pivot
+        a.partials[((size_t)pair * n_tiles + item_tile) * MOM_LEN + threadIdx.x] = v;      // still about the frame pivot
     }
     __threadfence();
     __syncthreads();
@@ -517,7 +548,7 @@ pair_moments_mixed_kernel(PairArgs a) {
         is_last = (t == (unsigned int)n_tiles - 1);
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) continue;
     __threadfence();
 
     // ---- last block of the pair: sum partials frame by frame (tile order), un-pivot, to world, solve ----
@@ -562,9 +593,18 @@ pair_moments_mixed_kernel(PairArgs a) {
     if (threadIdx.x == 0) {
         double mm[MOM_LEN];
         for (int k = 0; k < MOM_LEN; ++k) mm[k] = wmom[k];
-        solve_pair(a, pair, mm);
+        solve_pair(a, pair, mm, pass);
         a.tickets[pair] = 0;
     }
+   }   // items
+   grid_g.sync();                                   // every solve of this pass is visible everywhere
+   // pairs still active = active at start - finished in passes <= this one.  Only counters of
+   // completed passes are read, so every block takes the same decision (a fast block already
+   // working on the next pass writes done_count[pass + 1]).
+   int active = *((volatile int*)a.n_active);
+   for (int q = 0; q <= pass; ++q) active -= *((volatile int*)&a.done_count[q]);
+   if (active <= 0) break;
+  }    // passes
 }
 
 // ---------------------------------------------------------------------------------
@@ -582,6 +622,10 @@ __global__ void pair_state_init_kernel(PairArgs a) {
     a.state[pair] = st;
     a.tickets[pair] = 0;
     set_effective(a, pair, st);
+    if (pair == 0 && a.n_active) {
+        *a.n_active = a.n_pairs;
+        for (int q = 0; q < a.max_iterations; ++q) { a.done_count[q] = 0; a.work_counter[q] = 0ull; }
+    }
 }
 
 __global__ void make_pair_segs_kernel(const da3s_pair* pairs, int n_pairs, long long M, int depth_mode,
@@ -801,7 +845,7 @@ ransac_score_kernel(RansacArgs a) {
 // winner per pair: max count, ties to the lowest index; fewer than min_inliers -> no model
 __global__ void __launch_bounds__(256)
 ransac_best_kernel(const int32_t* counts, const uint8_t* hyp_ok, const float* hyp_A, const float* hyp_t, int n_hyp,
-                   int min_inliers, PairState* state, float* gate, double* rows, da3s_pair_aux* aux) {
+                   int min_inliers, PairState* state, float* gate, double* rows, da3s_pair_aux* aux, int* n_active) {
     __shared__ unsigned long long best[256];
     const int pair = blockIdx.x;
     unsigned long long b = 0;
@@ -825,6 +869,7 @@ ransac_best_kernel(const int32_t* counts, const uint8_t* hyp_ok, const float* hy
         if (h < 0 || cnt < min_inliers) {                    // align_geometry.py:124
             st.done = 1; st.status = 2; st.gate_on = 0; st.n_valid = 0.0;
             state[pair] = st;
+            if (n_active) atomicSub(n_active, 1);
             double* r = rows + (size_t)pair * DA3S_ROW_LEN;
             r[DA3S_ROW_S] = 1.0;
             for (int q = 0; q < 9; ++q) r[DA3S_ROW_R + q] = (q % 4 == 0) ? 1.0 : 0.0;
@@ -1008,6 +1053,9 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     WS_ALLOC(ctx, float, gate, (size_t)n_pairs * 12);
     WS_ALLOC(ctx, double, partials, (size_t)n_pairs * n_tiles * MOM_LEN);
     WS_ALLOC(ctx, unsigned int, tickets, n_pairs);
+    WS_ALLOC(ctx, int, n_active, 1);
+    WS_ALLOC(ctx, int, done_count, opts->max_iterations);
+    WS_ALLOC(ctx, unsigned long long, work_counter, opts->max_iterations);
 
     int rc = thresholds_impl(ctx, pairs, n_pairs, overlap, H, W, opts, thr, dscale, aux, st);
     if (rc != DA3S_OK) return rc;
@@ -1018,7 +1066,7 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     a.depth_eps = opts->depth_eps; a.thr = thr; a.dscale = dscale; a.state = state; a.eff = eff;
     a.gate = opts->n_hyp > 0 ? gate : nullptr;
     a.gate_thr2 = (float)((double)opts->ransac_thr * (double)opts->ransac_thr);
-    a.partials = partials; a.tickets = tickets; a.huber_delta = opts->huber_delta; a.tol = opts->tol;
+    a.partials = partials; a.tickets = tickets; a.n_active = n_active; a.done_count = done_count; a.work_counter = work_counter; a.huber_delta = opts->huber_delta; a.tol = opts->tol;
     a.max_iterations = opts->max_iterations; a.min_points = opts->min_points; a.precise = opts->precise;
     a.rows = sim3_rows; a.aux = aux;
 
@@ -1040,26 +1088,34 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
                                thr, dscale, hyp_A, hyp_t, hyp_ok, nh, opts->ransac_thr, counts, stream);
         if (rc != DA3S_OK) return rc;
         ransac_best_kernel<<<n_pairs, 256, 0, st>>>(counts, hyp_ok, hyp_A, hyp_t, nh, opts->ransac_min_inliers, state, gate,
-                                                    sim3_rows, aux);
+                                                    sim3_rows, aux, n_active);
         DA3S_LAUNCH_CHECK(ctx);
     }
 
     const bool vec = (P % 4 == 0);          // per-pair pointer alignment is the caller's contract (EALIGN documented)
     dim3 grid(n_tiles, n_pairs);
     const int iters = opts->huber ? opts->max_iterations : 1;
-    for (int it = 0; it < iters; ++it) {
-        if (opts->precise) {
+    if (opts->precise) {
+        for (int it = 0; it < iters; ++it) {
             if (vec) pair_moments_kernel<true><<<grid, PA_THREADS, 0, st>>>(a);
             else     pair_moments_kernel<false><<<grid, PA_THREADS, 0, st>>>(a);
-        } else if (opts->huber) {
-            if (vec) pair_moments_mixed_kernel<true, true, true><<<grid, PM_THREADS, 0, st>>>(a);
-            else     pair_moments_mixed_kernel<false, true, true><<<grid, PM_THREADS, 0, st>>>(a);
-        } else {
-            if (vec) pair_moments_mixed_kernel<true, true, false><<<grid, PM_THREADS, 0, st>>>(a);
-            else     pair_moments_mixed_kernel<false, true, false><<<grid, PM_THREADS, 0, st>>>(a);
+            DA3S_LAUNCH_CHECK(ctx);
         }
-        DA3S_LAUNCH_CHECK(ctx);
+        return DA3S_OK;
     }
+    // persistent cooperative launch: as many blocks as can be co-resident, never more than there are items
+    const void* fn = opts->huber ? (vec ? (const void*)pair_moments_mixed_kernel<true, true, true> : (const void*)pair_moments_mixed_kernel<false, true, true>)
+                                 : (vec ? (const void*)pair_moments_mixed_kernel<true, true, false> : (const void*)pair_moments_mixed_kernel<false, true, false>);
+    int per_sm = 0;
+    DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PM_THREADS, 0));
+    if (per_sm < 1) return DA3S_ECUDA;
+    long long coop_blocks = (long long)per_sm * ctx->sm_count;
+    const long long items = (long long)n_pairs * n_tiles;
+    if (coop_blocks > items) coop_blocks = items;
+    int max_passes = iters;
+    void* kargs[] = {(void*)&a, (void*)&max_passes};
+    DA3S_CHECK_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3((unsigned int)coop_blocks), dim3(PM_THREADS), kargs, 0, st));
+    ctx->launches++;
     return DA3S_OK;
 }
 
@@ -1230,7 +1286,7 @@ static int points_common(da3s_ctx* ctx, PointsArgs& a, long long count, int hube
     pa.pairs = nullptr; pa.n_pairs = 1; pa.overlap = 1; pa.H = 1; pa.W = 1; pa.P = 1; pa.tiles_per_frame = (int)nb;
     pa.world = 0; pa.valid_depth = 0; pa.huber = huber; pa.variant = variant; pa.depth_eps = 0; pa.thr = nullptr;
     pa.dscale = nullptr; pa.state = state; pa.eff = eff; pa.gate = nullptr; pa.gate_thr2 = 0; pa.partials = partials;
-    pa.tickets = tickets; pa.huber_delta = delta; pa.tol = tol; pa.max_iterations = max_it; pa.min_points = min_points;
+    pa.tickets = tickets; pa.n_active = nullptr; pa.done_count = nullptr; pa.work_counter = nullptr; pa.huber_delta = delta; pa.tol = tol; pa.max_iterations = max_it; pa.min_points = min_points;
     pa.precise = 1;
     pa.rows = row; pa.aux = nullptr;
     a.count = count;
@@ -1301,33 +1357,57 @@ extern "C" int da3s_irls_points(da3s_ctx* ctx, const void* src, const void* dst,
 // ---------------------------------------------------------------------------------
 // Sim(3) chain (utils/geometry.py:73-119): n tiny compositions, one thread.
 // ---------------------------------------------------------------------------------
-__global__ void accumulate_sim3_kernel(const double* __restrict__ rows, int n, double* __restrict__ cum) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    double s = 1.0, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
-    cum[0] = s;
-    for (int k = 0; k < 9; ++k) cum[1 + k] = R[k];
-    for (int k = 0; k < 3; ++k) cum[10 + k] = t[k];
-    for (int i = 0; i < n; ++i) {
-        const double* r = rows + (size_t)i * DA3S_ROW_LEN;
-        const double sn = r[DA3S_ROW_S];
-        const double* Rn = r + DA3S_ROW_R;
-        const double* tn = r + DA3S_ROW_T;
-        double Rt[3], R2[9];
-        mat3_vec(R, tn, Rt);                              // t' = s_prev (R_prev t_next) + t_prev
-        for (int k = 0; k < 3; ++k) t[k] = s * Rt[k] + t[k];
-        mat3_mul(R, Rn, R2);                              // R' = R_prev R_next
-        for (int k = 0; k < 9; ++k) R[k] = R2[k];
-        s = s * sn;                                       // s' = s_prev s_next
-        double* o = cum + (size_t)(i + 1) * 13;
-        o[0] = s;
-        for (int k = 0; k < 9; ++k) o[1 + k] = R[k];
-        for (int k = 0; k < 3; ++k) o[10 + k] = t[k];
+// rows are staged through shared memory in chunks (coalesced loads/stores by the whole block);
+// the n sequential 3x3 compositions themselves run on one thread out of shared memory.
+#define ACC_CHUNK 128
+__global__ void __launch_bounds__(256)
+accumulate_sim3_kernel(const double* __restrict__ rows, int n, double* __restrict__ cum) {
+    __shared__ double in[ACC_CHUNK * DA3S_ROW_LEN];
+    __shared__ double out[ACC_CHUNK * 13];
+    __shared__ double cur[13];
+    if (threadIdx.x < 13) {
+        double v = (threadIdx.x == 0 || threadIdx.x == 1 || threadIdx.x == 5 || threadIdx.x == 9) ? 1.0 : 0.0;
+        cur[threadIdx.x] = v;
+        cum[threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int base = 0; base < n; base += ACC_CHUNK) {
+        const int m = (n - base) < ACC_CHUNK ? (n - base) : ACC_CHUNK;
+        for (int i = threadIdx.x; i < m * DA3S_ROW_LEN; i += blockDim.x) in[i] = rows[(size_t)base * DA3S_ROW_LEN + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = cur[0], R[9], t[3];
+            for (int k = 0; k < 9; ++k) R[k] = cur[1 + k];
+            for (int k = 0; k < 3; ++k) t[k] = cur[10 + k];
+            for (int i = 0; i < m; ++i) {
+                const double* r = in + i * DA3S_ROW_LEN;
+                const double sn = r[DA3S_ROW_S];
+                const double* Rn = r + DA3S_ROW_R;
+                const double* tn = r + DA3S_ROW_T;
+                double Rt[3], R2[9];
+                mat3_vec(R, tn, Rt);                              // t' = s_prev (R_prev t_next) + t_prev
+                for (int k = 0; k < 3; ++k) t[k] = s * Rt[k] + t[k];
+                mat3_mul(R, Rn, R2);                              // R' = R_prev R_next
+                for (int k = 0; k < 9; ++k) R[k] = R2[k];
+                s = s * sn;                                       // s' = s_prev s_next
+                double* o = out + i * 13;
+                o[0] = s;
+                for (int k = 0; k < 9; ++k) o[1 + k] = R[k];
+                for (int k = 0; k < 3; ++k) o[10 + k] = t[k];
+            }
+            cur[0] = s;
+            for (int k = 0; k < 9; ++k) cur[1 + k] = R[k];
+            for (int k = 0; k < 3; ++k) cur[10 + k] = t[k];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < m * 13; i += blockDim.x) cum[(size_t)(base + 1) * 13 + i] = out[i];
+        __syncthreads();
     }
 }
 
 extern "C" int da3s_accumulate_sim3(da3s_ctx* ctx, const double* rows, int n_rows, double* cum, void* stream) {
     if (!ctx || !cum || n_rows < 0 || (n_rows > 0 && !rows)) return DA3S_EINVAL;
-    accumulate_sim3_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rows, n_rows, cum);
+    accumulate_sim3_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(rows, n_rows, cum);
     DA3S_LAUNCH_CHECK(ctx);
     return DA3S_OK;
 }

@@ -1,28 +1,48 @@
 // select.cu — exact, batched order statistics (median / percentile) of float32 data.
 //
-// Segmented MSD radix select, 3 passes over the keys (11 + 11 + 10 bits).  Each pass is
-// ONE kernel: every block histograms its slice of its segment in shared memory
-// (warp-aggregated atomics), merges into the segment's global histogram, and the last
-// block to finish (ticket) scans the histogram, narrows the (prefix, rank) state of the
-// segment's two queries and clears the histogram for the next pass.  No host round trip.
+// One full pass over the data instead of three:
+//   A  sample    one block per segment sorts a 4096-element strided sample in shared memory
+//                (bitonic) and brackets the wanted rank between two sample keys [lo, hi]
+//                (+-5 sigma of the sampling error).  Segments of <= 4096 elements are answered here.
+//   B  count     ONE streaming pass: per element 2 compares; counts elements below / equal to
+//                the pivots and appends the few (~8 %) strictly inside the bracket to a
+//                candidate buffer (block-aggregated append).  The last block of a segment
+//                (ticket) computes the exact ranks from the exact count and maps them into the
+//                candidates — or, if the bracket missed or the buffer overflowed (heavy ties,
+//                adversarial data), redirects the next stage to the full segment.  Exactness
+//                never depends on the sample; only the amount of work does.
+//   C  radix     3-pass MSD radix select (11+11+10 bits) over the candidates (or, on fallback,
+//                over the whole segment with the same grid looping).  The final pass
+//                reproduces numpy >= 2's float32 finishing arithmetic bit for bit
+//                (SURVEY.md appendix A): median of an even count = (a + b) / 2; percentile =
+//                float32 virtual index (n-1) * (p / 100f), lerp with the gamma >= 0.5 branch.
+// Everything is device-side: no host round trip, fixed launch sequence (5 kernels).
 //
-// The finishing arithmetic reproduces numpy >= 2 on float32 input bit for bit
-// (SURVEY.md appendix A): median of an even count = (a + b) / 2 in float32; percentile =
-// float32 virtual index (n-1) * (p / 100f), float32 lerp with the gamma >= 0.5 branch.
-//
-// Algorithmic bytes: 4 B x 3 passes per element (16 B x 3 for the depth-ratio kind).
+// Algorithmic bytes: 4 B per element (16 B for the depth-ratio kind) read once.
 #include "common.cuh"
 
 #define SEL_THREADS 256
-#define SEL_ITEMS 16                       // elements per thread per block (4 float4)
+#define SEL_ITEMS 16                       // elements per thread per block iteration (4 float4)
 #define SEL_BINS 2048
+#define SEL_SAMPLE 4096
+#define SEL_KIND_KEYS 100                  // internal: the segment already holds ordered uint32 keys
 
-struct SelState {
-    unsigned int prefix[2];
-    long long rank[2];                     // rank of the wanted element inside the current prefix class
+struct SelWork {                           // per segment, device resident
+    const void* data;                      // stage C input: candidate keys (or the original `a` on fallback)
+    long long n;                           // elements in `data`
+    int kind;                              // SEL_KIND_KEYS or the original kind (fallback)
+    int done;                              // 1: answered by the sample stage; 2: no valid element
+    unsigned int lo_key, hi_key;           // bracket from the sample
+    long long rank[2];                     // ranks to find inside `data`
+    int resolved[2];                       // the order statistic is already known (a pivot)
+    unsigned int resolved_key[2];
     long long n_valid;
     float gamma;
-    int empty;
+    int overflow;
+    // stage B counters
+    unsigned long long c_valid, c_less, c_eqlo, c_eqhi, c_cand;
+    // stage C state
+    unsigned int prefix[2];
 };
 
 __device__ __forceinline__ int sel_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
@@ -40,43 +60,130 @@ __device__ __forceinline__ bool sel_key(const da3s_select_seg& s, long long i, u
     return ok;
 }
 
-__device__ __forceinline__ void hist_add(unsigned int* hist, unsigned int digit, bool pred) {
-    // warp-aggregated shared-memory atomic: one atomic per distinct digit in the warp
-    unsigned int act = __ballot_sync(0xffffffffu, pred);
-    if (!pred) return;
-    unsigned int peers = __match_any_sync(act, digit);
-    if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+// ranks of the two order statistics numpy uses, and the interpolation weight
+__device__ __forceinline__ void sel_ranks(long long n, int stat, float percent, long long& k0, long long& k1, float& gamma) {
+    gamma = 0.0f;
+    if (n <= 0) { k0 = k1 = 0; return; }
+    if (stat == DA3S_SEL_MEDIAN) { k0 = (n - 1) / 2; k1 = n / 2; return; }
+    // numpy: q = p / float32(100); virt = (n-1) * q in float32; floor; clamp
+    float qf = __fdiv_rn(percent, 100.0f);
+    float virt = __fmul_rn((float)(n - 1), qf);
+    float prev = floorf(virt);
+    if (virt >= (float)(n - 1)) { k0 = k1 = n - 1; }
+    else if (virt < 0.0f) { k0 = k1 = 0; }
+    else { k0 = (long long)prev; k1 = (long long)prev + 1; }
+    gamma = __fsub_rn(virt, prev);
 }
 
-template <int PASS>
+__device__ __forceinline__ void sel_finish(const da3s_select_seg& seg, long long n_valid, float gamma, bool empty,
+                                           unsigned int key0, unsigned int key1, da3s_select_out* out) {
+    da3s_select_out o;
+    o.n_valid = n_valid;
+    o.gamma = gamma;
+    if (empty) {
+        o.lo = o.hi = o.value = __int_as_float(0x7fc00000);
+    } else {
+        float a = key_to_f32(key0), b = key_to_f32(key1);
+        o.lo = a; o.hi = b;
+        if (seg.stat == DA3S_SEL_MEDIAN) {
+            // np.median: odd -> the element; even -> np.mean of the two = (a+b)/2 in float32
+            o.value = (n_valid & 1) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);
+        } else {
+            // numpy _lerp in float32
+            float diff = __fsub_rn(b, a);
+            float v = __fadd_rn(a, __fmul_rn(diff, gamma));
+            if (gamma >= 0.5f) v = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+            o.value = v;
+        }
+    }
+    *out = o;
+}
+
+// ---------------------------------------------------------------------------------
+// A: sample, sort, bracket
+// ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SEL_THREADS)
-select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* state,
-                   unsigned int* ghist /* [n_segs][2][SEL_BINS] */,
-                   unsigned int* tickets, da3s_select_out* out) {
-    __shared__ unsigned int hist[2][SEL_BINS];
+select_sample_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, da3s_select_out* out) {
+    __shared__ unsigned int keys[SEL_SAMPLE];
+    __shared__ unsigned int n_ok;
+    const int seg_id = blockIdx.x;
+    const da3s_select_seg seg = segs[seg_id];
+    if (threadIdx.x == 0) n_ok = 0;
+    __syncthreads();
+    const long long n = seg.n;
+    const long long m = n < SEL_SAMPLE ? n : SEL_SAMPLE;
+    unsigned int mine = 0;
+    for (int j = threadIdx.x; j < SEL_SAMPLE; j += SEL_THREADS) {
+        unsigned int k = 0xFFFFFFFFu;
+        if (j < m) {
+            const long long i = (n <= SEL_SAMPLE) ? j : (long long)(((unsigned long long)j * (unsigned long long)n) / SEL_SAMPLE);
+            unsigned int kk;
+            if (sel_key(seg, i, kk)) { k = kk; ++mine; }
+        }
+        keys[j] = k;
+    }
+    atomicAdd(&n_ok, mine);
+    __syncthreads();
+    // bitonic sort, ascending; rejected samples (0xFFFFFFFF) sink to the end
+    for (unsigned int k = 2; k <= SEL_SAMPLE; k <<= 1)
+        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned int t = threadIdx.x; t < SEL_SAMPLE / 2; t += SEL_THREADS) {
+                const unsigned int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));       // lower index of the pair
+                const unsigned int l = i | j;
+                const bool up = ((i & k) == 0);
+                const unsigned int a = keys[i], b = keys[l];
+                if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x != 0) return;
+    SelWork w;
+    w.data = nullptr; w.n = 0; w.kind = SEL_KIND_KEYS; w.done = 0; w.lo_key = 0u; w.hi_key = 0xFFFFFFFFu;
+    w.rank[0] = w.rank[1] = 0; w.resolved[0] = w.resolved[1] = 0; w.resolved_key[0] = w.resolved_key[1] = 0;
+    w.n_valid = 0; w.gamma = 0.0f; w.overflow = 0; w.c_valid = w.c_less = w.c_eqlo = w.c_eqhi = w.c_cand = 0ull;
+    w.prefix[0] = w.prefix[1] = 0;
+    const long long mv = (long long)n_ok;
+    if (n <= SEL_SAMPLE) {
+        // the sample is the whole segment: answer now
+        long long k0, k1; float gamma;
+        sel_ranks(mv, seg.stat, seg.percent, k0, k1, gamma);
+        sel_finish(seg, mv, gamma, mv == 0, mv ? keys[k0] : 0u, mv ? keys[k1] : 0u, out + seg_id);
+        w.done = 1; w.n_valid = mv; w.gamma = gamma;
+    } else if (mv > 0) {
+        // bracket the wanted quantile of the VALID elements: +-5 sigma of the binomial sampling error
+        const double q = (seg.stat == DA3S_SEL_MEDIAN) ? 0.5 : fmin(fmax((double)seg.percent / 100.0, 0.0), 1.0);
+        const double c = q * (double)(mv - 1);
+        const double margin = 5.0 * sqrt((double)mv * q * (1.0 - q)) + 8.0;
+        const long long lo_i = (long long)floor(c - margin), hi_i = (long long)ceil(c + margin);
+        w.lo_key = lo_i <= 0 ? 0u : keys[lo_i];
+        w.hi_key = hi_i >= mv - 1 ? 0xFFFFFFFFu : keys[hi_i];
+    }
+    work[seg_id] = w;
+}
+
+// ---------------------------------------------------------------------------------
+// B: one streaming pass — count below / at the pivots, collect the candidates
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, unsigned int* cand, long long cand_cap,
+                    unsigned int* tickets) {
+    __shared__ unsigned long long blk[4];
+    __shared__ unsigned int warp_tot[SEL_THREADS / 32];
+    __shared__ unsigned long long cand_base;
     __shared__ bool is_last;
-    __shared__ long long scan_tot[SEL_THREADS];
-    __shared__ unsigned int new_prefix[2];
-    __shared__ long long new_rank[2];
-    __shared__ long long sh_rank[2];
-    __shared__ int sh_empty;
     const int seg_id = blockIdx.y;
     const da3s_select_seg seg = segs[seg_id];
-    SelState st;
-    if (PASS > 0) st = state[seg_id];
-    const bool two = PASS > 0 && (st.prefix[0] != st.prefix[1]);       // queries diverged
-    for (int i = threadIdx.x; i < 2 * SEL_BINS; i += SEL_THREADS) (&hist[0][0])[i] = 0;
-    __syncthreads();
-
-    const int shift = sel_shift(PASS), bits = sel_bits(PASS);
-    const unsigned int dmask = (1u << bits) - 1u;
+    SelWork* w = work + seg_id;
+    if (w->done) return;                                             // block-uniform
+    const unsigned int lo = w->lo_key, hi = w->hi_key;
     const long long base = (long long)blockIdx.x * (SEL_THREADS * SEL_ITEMS);
-    const bool skip = (PASS > 0 && st.empty);
-    if (!skip && base < seg.n) {
+    if (threadIdx.x < 4) blk[threadIdx.x] = 0ull;
+    __syncthreads();
+    unsigned int keys[SEL_ITEMS];
+    unsigned int okmask = 0, candmask = 0;
+    unsigned int n_valid = 0, n_less = 0, n_eqlo = 0, n_eqhi = 0;
+    if (base < seg.n) {
         const bool vec = (seg.kind != DA3S_SEL_RATIO) && aligned16(seg.a);
-        unsigned int keys[SEL_ITEMS];
-        unsigned int okmask = 0;
-        // all loads first (4 x 128-bit in flight per thread), then the histogram updates
         if (vec && base + (long long)SEL_THREADS * SEL_ITEMS <= seg.n) {
             float4 v[SEL_ITEMS / 4];
 #pragma unroll
@@ -103,24 +210,174 @@ select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* state,
         }
 #pragma unroll
         for (int e = 0; e < SEL_ITEMS; ++e) {
-            const unsigned int digit = (keys[e] >> shift) & dmask;
             const bool ok = (okmask >> e) & 1u;
-            if (PASS == 0) {
-                hist_add(hist[0], digit, ok);                    // every element counts: aggregate per warp
-            } else {
-                // only the elements inside a query's prefix class count (a small fraction): plain atomics
-                const unsigned int hi = keys[e] >> (shift + bits);
-                if (ok && hi == st.prefix[0]) atomicAdd(&hist[0][digit], 1u);
-                if (two && ok && hi == st.prefix[1]) atomicAdd(&hist[1][digit], 1u);
-            }
+            const unsigned int k = keys[e];
+            n_valid += ok;
+            n_less += ok && (k < lo);
+            n_eqlo += ok && (k == lo);
+            n_eqhi += ok && (k == hi) && (hi != lo);
+            if (ok && k > lo && k < hi) candmask |= 1u << e;
         }
     }
+    // block totals of the four counters
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int r0 = __reduce_add_sync(0xffffffffu, n_valid), r1 = __reduce_add_sync(0xffffffffu, n_less);
+    unsigned int r2 = __reduce_add_sync(0xffffffffu, n_eqlo), r3 = __reduce_add_sync(0xffffffffu, n_eqhi);
+    if (lane == 0) {
+        if (r0) atomicAdd(&blk[0], (unsigned long long)r0);
+        if (r1) atomicAdd(&blk[1], (unsigned long long)r1);
+        if (r2) atomicAdd(&blk[2], (unsigned long long)r2);
+        if (r3) atomicAdd(&blk[3], (unsigned long long)r3);
+    }
+    // candidate append: block prefix sum, one global atomic per block
+    const unsigned int mine = __popc(candmask);
+    unsigned int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned int before = 0, total = 0;
+#pragma unroll
+    for (int x = 0; x < SEL_THREADS / 32; ++x) { if (x < (int)warp) before += warp_tot[x]; total += warp_tot[x]; }
+    if (threadIdx.x == 0) {
+        cand_base = total ? atomicAdd(&w->c_cand, (unsigned long long)total) : 0ull;
+        if (blk[0]) atomicAdd(&w->c_valid, blk[0]);
+        if (blk[1]) atomicAdd(&w->c_less, blk[1]);
+        if (blk[2]) atomicAdd(&w->c_eqlo, blk[2]);
+        if (blk[3]) atomicAdd(&w->c_eqhi, blk[3]);
+    }
+    __syncthreads();
+    if (total) {
+        unsigned long long pos = cand_base + before + (incl - mine);
+        unsigned int* dst = cand + (size_t)seg_id * cand_cap;
+        bool over = false;
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e)
+            if ((candmask >> e) & 1u) {
+                if ((long long)pos < cand_cap) dst[pos] = keys[e]; else over = true;
+                ++pos;
+            }
+        if (over) w->overflow = 1;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(&tickets[seg_id], 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    __threadfence();
+    // ---- last block of the segment: exact ranks, map into the candidates (or fall back) ----
+    tickets[seg_id] = 0;
+    volatile SelWork* vw = w;
+    const long long nv = (long long)vw->c_valid, nl = (long long)vw->c_less, ne0 = (long long)vw->c_eqlo;
+    const long long ne1 = (long long)vw->c_eqhi, nc = (long long)vw->c_cand;
+    long long k[2]; float gamma;
+    sel_ranks(nv, seg.stat, seg.percent, k[0], k[1], gamma);
+    w->n_valid = nv; w->gamma = gamma;
+    if (nv == 0) { w->done = 2; return; }                            // empty: stage C's last pass writes NaN
+    bool fallback = vw->overflow != 0;
+    for (int q = 0; q < 2; ++q) fallback = fallback || (k[q] < nl) || (k[q] >= nl + ne0 + nc + ne1);
+    if (fallback) {
+        w->data = seg.a; w->n = seg.n; w->kind = seg.kind;
+        for (int q = 0; q < 2; ++q) { w->rank[q] = k[q]; w->resolved[q] = 0; }
+        return;
+    }
+    w->data = cand + (size_t)seg_id * cand_cap; w->n = nc; w->kind = SEL_KIND_KEYS;
+    for (int q = 0; q < 2; ++q) {
+        if (k[q] < nl + ne0) { w->resolved[q] = 1; w->resolved_key[q] = lo; }
+        else if (k[q] < nl + ne0 + nc) { w->resolved[q] = 0; w->rank[q] = k[q] - nl - ne0; }
+        else { w->resolved[q] = 1; w->resolved_key[q] = hi; }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// C: radix select over SelWork (candidate keys, or the original segment on fallback)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void hist_add(unsigned int* hist, unsigned int digit, bool pred) {
+    // warp-aggregated shared-memory atomic: one atomic per distinct digit in the warp
+    unsigned int act = __ballot_sync(0xffffffffu, pred);
+    if (!pred) return;
+    unsigned int peers = __match_any_sync(act, digit);
+    if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(SEL_THREADS)
+select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, unsigned int* ghist /* [n_segs][2][SEL_BINS] */,
+                   unsigned int* tickets, da3s_select_out* out) {
+    __shared__ unsigned int hist[2][SEL_BINS];
+    __shared__ bool is_last;
+    __shared__ long long scan_tot[SEL_THREADS];
+    __shared__ unsigned int new_prefix[2];
+    __shared__ long long new_rank[2];
+    const int seg_id = blockIdx.y;
+    SelWork* wp = work + seg_id;
+    const int done = wp->done;
+    if (done == 1) return;                                           // answered by the sample stage
+    const da3s_select_seg seg = segs[seg_id];
+    const bool empty = (done == 2);
+    const long long n = empty ? 0 : wp->n;
+    const int kind = wp->kind;
+    const long long rank0 = wp->rank[0], rank1 = wp->rank[1];
+    const bool res0 = wp->resolved[0] != 0, res1 = wp->resolved[1] != 0;
+    const unsigned int pre0 = wp->prefix[0], pre1 = wp->prefix[1];
+    // query 1 needs its own histogram when the live queries diverged, or when query 0 is already resolved
+    const bool q1_own = PASS > 0 && !res1 && (res0 || pre0 != pre1);
+    for (int i = threadIdx.x; i < 2 * SEL_BINS; i += SEL_THREADS) (&hist[0][0])[i] = 0;
+    __syncthreads();
+
+    const int shift = sel_shift(PASS), bits = sel_bits(PASS);
+    const unsigned int dmask = (1u << bits) - 1u;
+    const bool any_live = !(res0 && res1) && n > 0;
+    da3s_select_seg src = seg;                                       // element source for this stage
+    src.n = n; src.kind = kind;
+    if (kind != SEL_KIND_KEYS) src.a = (const float*)wp->data;
+    const unsigned int* kdata = (const unsigned int*)wp->data;
+    const long long chunk = (long long)SEL_THREADS * SEL_ITEMS;
+    if (any_live)
+        for (long long base = (long long)blockIdx.x * chunk; base < n; base += (long long)gridDim.x * chunk) {   // block-uniform
+            unsigned int keys[SEL_ITEMS];
+            unsigned int okmask = 0;
+            if (kind == SEL_KIND_KEYS) {
+#pragma unroll
+                for (int it = 0; it < SEL_ITEMS; ++it) {
+                    const long long i = base + (long long)it * SEL_THREADS + threadIdx.x;
+                    keys[it] = 0;
+                    if (i < n) { keys[it] = kdata[i]; okmask |= 1u << it; }
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < SEL_ITEMS; ++it) {
+                    const long long i = base + (long long)it * SEL_THREADS + threadIdx.x;
+                    keys[it] = 0;
+                    if (i < n && sel_key(src, i, keys[it])) okmask |= 1u << it;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < SEL_ITEMS; ++e) {
+                const unsigned int digit = (keys[e] >> shift) & dmask;
+                const bool ok = (okmask >> e) & 1u;
+                if (PASS == 0) {
+                    hist_add(hist[0], digit, ok);                    // one shared histogram serves both queries
+                } else {
+                    const unsigned int hi = keys[e] >> (shift + bits);
+                    if (ok && !res0 && hi == pre0) atomicAdd(&hist[0][digit], 1u);
+                    if (ok && q1_own && hi == pre1) atomicAdd(&hist[1][digit], 1u);
+                }
+            }
+        }
     __syncthreads();
     unsigned int* gh = ghist + (size_t)seg_id * 2 * SEL_BINS;
-    for (int i = threadIdx.x; i < 2 * SEL_BINS; i += SEL_THREADS) {
-        unsigned int c = (&hist[0][0])[i];
-        if (c) atomicAdd(&gh[i], c);
-    }
+    if (any_live)
+        for (int i = threadIdx.x; i < 2 * SEL_BINS; i += SEL_THREADS) {
+            unsigned int c = (&hist[0][0])[i];
+            if (c) atomicAdd(&gh[i], c);
+        }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -131,56 +388,37 @@ select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* state,
     if (!is_last) return;
     __threadfence();
 
-    // ---- last block of this segment: narrow the two queries ----
+    // ---- last block of this segment: narrow the live queries ----
     const int nb = 1 << bits;
-    const int per = SEL_BINS / SEL_THREADS;                    // 8 bins per thread
+    const int per = SEL_BINS / SEL_THREADS;                          // 8 bins per thread
+    if (threadIdx.x < 2) { new_prefix[threadIdx.x] = threadIdx.x ? pre1 : pre0; new_rank[threadIdx.x] = threadIdx.x ? rank1 : rank0; }
+    __syncthreads();
     for (int q = 0; q < 2; ++q) {
-        const unsigned int* src = gh + ((PASS > 0 && two) ? q : 0) * SEL_BINS;
+        const bool live = any_live && !(q == 0 ? res0 : res1);
+        const int hsel = (q == 1 && q1_own) ? 1 : 0;
+        const unsigned int* srch = gh + hsel * SEL_BINS;
         long long loc[per], tot = 0;
 #pragma unroll
         for (int k = 0; k < per; ++k) {
             int b = threadIdx.x * per + k;
-            loc[k] = b < nb ? (long long)__ldcg(&src[b]) : 0;
+            loc[k] = (live && b < nb) ? (long long)__ldcg(&srch[b]) : 0;
             tot += loc[k];
         }
         scan_tot[threadIdx.x] = tot;
         __syncthreads();
-        if (threadIdx.x == 0) {                                // 256-entry serial exclusive scan
+        if (threadIdx.x == 0) {                                      // 256-entry serial exclusive scan
             long long run = 0;
             for (int i = 0; i < SEL_THREADS; ++i) { long long v = scan_tot[i]; scan_tot[i] = run; run += v; }
-            if (PASS == 0 && q == 0) {
-                // ranks from the count (total = number of participating elements)
-                st.n_valid = run; st.empty = (run == 0); st.gamma = 0.0f;
-                st.prefix[0] = st.prefix[1] = 0;
-                long long n = run;
-                if (n > 0) {
-                    if (seg.stat == DA3S_SEL_MEDIAN) { st.rank[0] = (n - 1) / 2; st.rank[1] = n / 2; }
-                    else {
-                        // numpy: q = p / float32(100); virt = (n-1) * q in float32; floor; clamp
-                        float qf = __fdiv_rn(seg.percent, 100.0f);
-                        float virt = __fmul_rn((float)(n - 1), qf);
-                        float prev = floorf(virt);
-                        if (virt >= (float)(n - 1)) { st.rank[0] = st.rank[1] = n - 1; }
-                        else if (virt < 0.0f) { st.rank[0] = st.rank[1] = 0; }
-                        else { st.rank[0] = (long long)prev; st.rank[1] = (long long)prev + 1; }
-                        st.gamma = __fsub_rn(virt, prev);
-                    }
-                } else { st.rank[0] = st.rank[1] = 0; }
-                state[seg_id].n_valid = st.n_valid; state[seg_id].empty = st.empty; state[seg_id].gamma = st.gamma;
-                sh_rank[0] = st.rank[0]; sh_rank[1] = st.rank[1]; sh_empty = st.empty;
-            }
         }
         __syncthreads();
-        if (PASS == 0) { st.rank[0] = sh_rank[0]; st.rank[1] = sh_rank[1]; st.empty = sh_empty; }
-        __syncthreads();
-        const long long want = st.rank[q];
+        const long long want = (q == 0) ? rank0 : rank1;
         long long run = scan_tot[threadIdx.x];
-        if (!st.empty) {
+        if (live) {
 #pragma unroll
             for (int k = 0; k < per; ++k) {
-                if (want >= run && want < run + loc[k]) {      // exactly one (thread, k) matches
+                if (want >= run && want < run + loc[k]) {            // exactly one (thread, k) matches
                     unsigned int b = threadIdx.x * per + k;
-                    unsigned int old = PASS == 0 ? 0u : st.prefix[q];
+                    unsigned int old = PASS == 0 ? 0u : (q == 0 ? pre0 : pre1);
                     new_prefix[q] = (old << bits) | b;
                     new_rank[q] = want - run;
                 }
@@ -193,35 +431,13 @@ select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelState* state,
     for (int i = threadIdx.x; i < 2 * SEL_BINS; i += SEL_THREADS) gh[i] = 0;
     if (threadIdx.x == 0) {
         tickets[seg_id] = 0;
-        if (!st.empty) {                                       // thread 0 alone publishes the narrowed state
-            state[seg_id].prefix[0] = new_prefix[0]; state[seg_id].prefix[1] = new_prefix[1];
-            state[seg_id].rank[0] = new_rank[0];     state[seg_id].rank[1] = new_rank[1];
+        wp->prefix[0] = new_prefix[0]; wp->prefix[1] = new_prefix[1];
+        wp->rank[0] = new_rank[0];     wp->rank[1] = new_rank[1];
+        if (PASS == 2) {
+            const unsigned int key0 = res0 ? wp->resolved_key[0] : new_prefix[0];
+            const unsigned int key1 = res1 ? wp->resolved_key[1] : new_prefix[1];
+            sel_finish(seg, wp->n_valid, wp->gamma, empty, key0, key1, out + seg_id);
         }
-    }
-    if (PASS == 2 && threadIdx.x == 0) {
-        SelState f;
-        f.prefix[0] = new_prefix[0]; f.prefix[1] = new_prefix[1];
-        f.n_valid = st.n_valid; f.gamma = st.gamma; f.empty = st.empty;
-        da3s_select_out o;
-        o.n_valid = f.n_valid;
-        o.gamma = f.gamma;
-        if (f.empty) {
-            o.lo = o.hi = o.value = __int_as_float(0x7fc00000);
-        } else {
-            float a = key_to_f32(f.prefix[0]), b = key_to_f32(f.prefix[1]);
-            o.lo = a; o.hi = b;
-            if (seg.stat == DA3S_SEL_MEDIAN) {
-                // np.median: odd -> the element; even -> np.mean of the two = (a+b)/2 in float32
-                o.value = (f.n_valid & 1) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);
-            } else {
-                // numpy _lerp in float32
-                float diff = __fsub_rn(b, a);
-                float v = __fadd_rn(a, __fmul_rn(diff, f.gamma));
-                if (f.gamma >= 0.5f) v = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, f.gamma)));
-                o.value = v;
-            }
-        }
-        out[seg_id] = o;
     }
 }
 
@@ -231,24 +447,32 @@ int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, lon
     if (n_segs <= 0) return DA3S_OK;
     if (n_segs > 65535) return DA3S_EINVAL;
     size_t save_top = ctx->ws_top;
-    WS_ALLOC(ctx, SelState, state, n_segs);
+    const long long per_block = (long long)SEL_THREADS * SEL_ITEMS;
+    // candidate capacity per segment: 1/8 of the largest segment (the bracket holds ~8 % on average)
+    long long cand_cap = (max_n / 8 + per_block - 1) / per_block * per_block;
+    if (cand_cap < per_block) cand_cap = per_block;
+    WS_ALLOC(ctx, SelWork, work, n_segs);
     WS_ALLOC(ctx, unsigned int, ghist, (size_t)n_segs * 2 * SEL_BINS);
     WS_ALLOC(ctx, unsigned int, tickets, n_segs);
+    WS_ALLOC(ctx, unsigned int, cand, (size_t)n_segs * (size_t)cand_cap);
     DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(ghist, 0, sizeof(unsigned int) * (size_t)n_segs * 2 * SEL_BINS, st));
     DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(tickets, 0, sizeof(unsigned int) * n_segs, st));
-    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(state, 0, sizeof(SelState) * n_segs, st));
-    long long per_block = (long long)SEL_THREADS * SEL_ITEMS;
-    long long bx = (max_n + per_block - 1) / per_block;
-    if (bx < 1) bx = 1;
-    if (bx > 2147483647LL) return DA3S_EINVAL;
-    dim3 grid((unsigned int)bx, n_segs);
-    select_pass_kernel<0><<<grid, SEL_THREADS, 0, st>>>(segs, state, ghist, tickets, out);
+    select_sample_kernel<<<n_segs, SEL_THREADS, 0, st>>>(segs, work, out);
     DA3S_LAUNCH_CHECK(ctx);
-    select_pass_kernel<1><<<grid, SEL_THREADS, 0, st>>>(segs, state, ghist, tickets, out);
-    DA3S_LAUNCH_CHECK(ctx);
-    select_pass_kernel<2><<<grid, SEL_THREADS, 0, st>>>(segs, state, ghist, tickets, out);
-    DA3S_LAUNCH_CHECK(ctx);
-    ctx->ws_top = save_top;     // scratch is free again once the three passes are queued (stream order)
+    if (max_n > SEL_SAMPLE) {
+        long long bx = (max_n + per_block - 1) / per_block;
+        if (bx > 2147483647LL) return DA3S_EINVAL;
+        select_count_kernel<<<dim3((unsigned int)bx, n_segs), SEL_THREADS, 0, st>>>(segs, work, cand, cand_cap, tickets);
+        DA3S_LAUNCH_CHECK(ctx);
+        dim3 grid((unsigned int)(cand_cap / per_block), n_segs);
+        select_pass_kernel<0><<<grid, SEL_THREADS, 0, st>>>(segs, work, ghist, tickets, out);
+        DA3S_LAUNCH_CHECK(ctx);
+        select_pass_kernel<1><<<grid, SEL_THREADS, 0, st>>>(segs, work, ghist, tickets, out);
+        DA3S_LAUNCH_CHECK(ctx);
+        select_pass_kernel<2><<<grid, SEL_THREADS, 0, st>>>(segs, work, ghist, tickets, out);
+        DA3S_LAUNCH_CHECK(ctx);
+    }
+    ctx->ws_top = save_top;     // scratch is free again once the passes are queued (stream order)
     return DA3S_OK;
 }
 

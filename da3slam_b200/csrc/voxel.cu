@@ -163,10 +163,15 @@ voxel_compact_kernel(unsigned long long* __restrict__ table, long long slots, un
                     xyz_out[3 * oo + q] = (float)__dmul_rn(__dadd_rn(k[q], mf), vd);
                 }
                 if (rgb_out) {
-                    unsigned long long r = cr & 0xFFFFFFFFull, g = gb >> 32, bl = gb & 0xFFFFFFFFull;
-                    rgb_out[3 * oo]     = (uint8_t)((2 * r + cnt) / (2 * cnt));
-                    rgb_out[3 * oo + 1] = (uint8_t)((2 * g + cnt) / (2 * cnt));
-                    rgb_out[3 * oo + 2] = (uint8_t)((2 * bl + cnt) / (2 * cnt));
+                    // (2*sum + n) / (2*n) = floor(sum/n) + (2*rem >= n), in 32-bit arithmetic (64-bit integer
+                    // division is emulated and was a large part of this kernel)
+                    const unsigned int n32 = (unsigned int)cnt;
+                    const unsigned int ch[3] = {(unsigned int)(cr & 0xFFFFFFFFull), (unsigned int)(gb >> 32), (unsigned int)(gb & 0xFFFFFFFFull)};
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const unsigned int d = ch[q] / n32, rem = ch[q] - d * n32;
+                        rgb_out[3 * oo + q] = (uint8_t)(d + ((rem >= n32 - rem) ? 1u : 0u));
+                    }
                 }
                 count_out[oo] = (int32_t)cnt;
                 if (key_out) key_out[oo] = (long long)key;

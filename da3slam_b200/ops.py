@@ -47,7 +47,7 @@ def context(device=None, workspace_bytes: int | None = None) -> Context:
     if device.index is None:
         device = torch.device(f"cuda:{torch.cuda.current_device()}")
     ctx = _contexts.get(device.index)
-    want = workspace_bytes or (256 << 20)
+    want = workspace_bytes or (1 << 30)
     if ctx is None or ctx.workspace_bytes < want:
         if ctx is not None:
             torch.cuda.synchronize(device)
