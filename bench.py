@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # BASELINE.json configs[1]: 300 frames, 16-frame submaps (solver.py deque semantics -> 19 submaps / 18 pairs)
     "c3vd300": dict(n_submaps=19, frames=16, H=518, W=518, overlap=1, n_hyp=0, outlier=0.0, export=True,
-                    table_slots=1 << 25, voxel=0.02, desc="300 frames, 19 submaps x 16 x 518x518, 18 pairs"),
+                    table_slots=1 << 24, voxel=0.02, desc="300 frames, 19 submaps x 16 x 518x518, 18 pairs"),
     # configs[2]: 2000 frames, 32-frame submaps, RANSAC 1024 hypotheses (make_image_chunks -> 65 submaps / 64 pairs)
     "seq2000": dict(n_submaps=65, frames=32, H=518, W=518, overlap=1, n_hyp=1024, outlier=0.3, export=True,
                     table_slots=1 << 27, voxel=0.02, desc="2000 frames, 65 submaps x 32 x 518x518, 64 pairs, RANSAC 1024"),
@@ -360,8 +360,9 @@ def gpu_arm(args, w, rank, world):
                                "21 B/pixel (4 depth + 4 conf read, 12 xyz + 1 mask written)")
         single["voxel_insert"] = ("voxel_insert_kernel", (12.0 + 1.0 + 3.0) * px_export, w["n_submaps"],
                                   "16 B/point read (12 xyz + 3 rgb + 1 mask); hash-table traffic not counted")
-        single["voxel_clear"] = ("voxel_clear_kernel", 64.0 * plan.grid.table_slots, 1, "64 B/slot written")
-        single["voxel_compact"] = ("voxel_compact_kernel", 64.0 * plan.grid.table_slots, 1, "64 B/slot read")
+        single["voxel_clear"] = ("voxel_clear_kernel (first use only)", 72.0 * plan.grid.table_slots, 1, "72 B/slot written")
+        single["voxel_compact"] = ("voxel_count/scan/emit_kernel", 16.0 * plan.grid.table_slots + (128.0 + 27.0) * n_vox, 3,
+                                   "2 x 8 B/slot key scans + per voxel 64 B record read, 64 B reset, 27 B output")
     passes = float(np.sum(iters))
     align_bytes = (passes * 16.0 + 3 * 8.0) * M + (w["n_hyp"] > 0) * n_pairs * 16.0 * M
     single["align"] = ("pair_moments_kernel (+select, +RANSAC)", align_bytes, 1,

@@ -358,7 +358,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.app
 // (ticket) solves it, a grid-wide barrier separates iterations, and the kernel ends as soon as
 // no pair is active — no empty launches, no host involvement between iterations.
 template <bool VEC, bool WORLD_UNUSED, bool HUBER>
-__global__ void __launch_bounds__(PM_THREADS, 3)
+__global__ void __launch_bounds__(PM_THREADS, 4)
 pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     __shared__ double red[MOM_LEN][PM_THREADS];     // block reduction scratch (25.6 KB)
     __shared__ FrameConst fc;
@@ -421,21 +421,24 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     const float delta = (float)a.huber_delta, delta2 = delta * delta;
     const float Wf = (float)a.W;
 
-    double acc[PM_NMOM];
+    // per-thread float64 accumulators live in the reduction scratch (column = thread): keeps the
+    // kernel at <= 128 registers (4 blocks/SM) and the final block reduction reads them in place
 #pragma unroll
-    for (int k = 0; k < PM_NMOM; ++k) acc[k] = 0.0;
+    for (int k = 0; k < MOM_LEN; ++k) red[k][threadIdx.x] = 0.0;
     float m[PM_NMOM];
 #pragma unroll
     for (int k = 0; k < PM_NMOM; ++k) m[k] = 0.0f;
     float wmax = 0.0f, r2sum = 0.0f;
-    double r2acc = 0.0;
     int cnt = 0;
 
     // one correspondence, branch-free: a rejected pixel contributes weight 0 on sanitised depths
     auto accumulate = [&](float uf, float vf, float da, float ca, float db, float cb) {
-        const float dbs = __fmul_rn(db, ds);
+        float dbs = __fmul_rn(db, ds);
         bool keep = (ca > thr) && (cb > thr);
         if (valid_depth) keep = keep && (da > eps) && (dbs > eps) && is_finite_f(da) && is_finite_f(dbs);
+        // sanitise the depths of a rejected pixel (its points become finite zeros): nothing
+        // non-finite can reach the sums through 0 * x
+        da = keep ? da : 0.0f; dbs = keep ? dbs : 0.0f;
         float x0, x1, y0, y1;
         cam_fast(uf, vf, da, cuA, cvA, ifuA, ifvA, y0, y1);
         cam_fast(uf, vf, dbs, cuB, cvB, ifuB, ifvB, x0, x1);
@@ -444,9 +447,7 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
             ransac_points(fc, a.world, x, y, xs, ys);
             keep = keep && (residual2_f32(fc.gate, xs, ys) < a.gate_thr2);
         }
-        // sanitise: a rejected pixel must not inject NaN/Inf through 0 * x
-        x0 = keep ? x0 : 0.0f; x1 = keep ? x1 : 0.0f; y0 = keep ? y0 : 0.0f; y1 = keep ? y1 : 0.0f;
-        const float x2 = keep ? dbs : 0.0f, y2 = keep ? da : 0.0f;
+        const float x2 = dbs, y2 = da;
         float w = keep ? sqrt_approx(ca * cb) : 0.0f;           // utils/align.py:166 (<= 1 ulp from sqrt_f32)
         if (HUBER) {
             const float r0 = fmaf(B[0], x0, fmaf(B[1], x1, fmaf(B[2], x2, y0 + c3[0])));
@@ -473,13 +474,10 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     };
     auto flush = [&]() {
 #pragma unroll
-        for (int k = 0; k < PM_NMOM; ++k) { acc[k] += (double)m[k]; m[k] = 0.0f; }
-        r2acc += (double)r2sum; r2sum = 0.0f;
+        for (int k = 0; k < PM_NMOM; ++k) { red[k][threadIdx.x] += (double)m[k]; m[k] = 0.0f; }
+        red[MOM_SR][threadIdx.x] += (double)r2sum; r2sum = 0.0f;
     };
-    auto group = [&](long long g, const float4& da, const float4& ca, const float4& db, const float4& cb) {
-        const long long pix = g << 2;
-        const int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
-        float uf = (float)u, vf = (float)v;
+    auto group = [&](float uf, float vf, const float4& da, const float4& ca, const float4& db, const float4& cb) {
         accumulate(uf, vf, da.x, ca.x, db.x, cb.x); uf += 1.0f; if (uf == Wf) { uf = 0.0f; vf += 1.0f; }
         accumulate(uf, vf, da.y, ca.y, db.y, cb.y); uf += 1.0f; if (uf == Wf) { uf = 0.0f; vf += 1.0f; }
         accumulate(uf, vf, da.z, ca.z, db.z, cb.z); uf += 1.0f; if (uf == Wf) { uf = 0.0f; vf += 1.0f; }
@@ -493,17 +491,26 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
         if (g_end > n_groups) g_end = n_groups;
         const float4* dA4 = reinterpret_cast<const float4*>(dA); const float4* cA4 = reinterpret_cast<const float4*>(cA);
         const float4* dB4 = reinterpret_cast<const float4*>(dB); const float4* cB4 = reinterpret_cast<const float4*>(cB);
+        // pixel coordinates are carried incrementally (float): one division per thread per tile
+        const int step_px = PM_THREADS * 4, step_vi = step_px / a.W;
+        const float step_v = (float)step_vi, step_u = (float)(step_px - step_vi * a.W);
+        float u0f, v0f;
+        { const long long p0 = (g_begin + threadIdx.x) << 2; const int v0 = (int)(p0 / a.W); v0f = (float)v0; u0f = (float)(int)(p0 - (long long)v0 * a.W); }
         // micro-batch = 2 groups (8 correspondences): all 8 loads issued before any arithmetic
         for (long long g0 = g_begin + threadIdx.x; g0 < g_end; g0 += 2 * PM_THREADS) {
             const long long g1 = g0 + PM_THREADS;
             const bool has1 = g1 < g_end;
+            float u1f = u0f + step_u, v1f = v0f + step_v;
+            if (u1f >= Wf) { u1f -= Wf; v1f += 1.0f; }
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 da0 = ldg_stream(dA4 + g0), ca0 = ldg_stream(cA4 + g0), db0 = ldg_stream(dB4 + g0), cb0 = ldg_stream(cB4 + g0);
             float4 da1 = z4, ca1 = z4, db1 = z4, cb1 = z4;
             if (has1) { da1 = ldg_stream(dA4 + g1); ca1 = ldg_stream(cA4 + g1); db1 = ldg_stream(dB4 + g1); cb1 = ldg_stream(cB4 + g1); }
-            group(g0, da0, ca0, db0, cb0);
-            if (has1) group(g1, da1, ca1, db1, cb1);
+            group(u0f, v0f, da0, ca0, db0, cb0);
+            if (has1) group(u1f, v1f, da1, ca1, db1, cb1);
             flush();
+            u0f = u1f + step_u; v0f = v1f + step_v;
+            if (u0f >= Wf) { u0f -= Wf; v0f += 1.0f; }
         }
     } else {
         int since = 0;
@@ -516,9 +523,6 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     }
 
     // ---- block reduction through shared memory (float64), fixed order ----
-#pragma unroll
-    for (int k = 0; k < PM_NMOM; ++k) red[k][threadIdx.x] = acc[k];
-    red[MOM_SR][threadIdx.x] = r2acc;
     red[MOM_WMAX][threadIdx.x] = (double)wmax;
     red[MOM_N][threadIdx.x] = (double)cnt;
     __syncthreads();

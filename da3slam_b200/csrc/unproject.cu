@@ -179,15 +179,15 @@ unproject_filter_kernel(K1Args a) {
     unsigned int kept = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    // block-uniform switches, evaluated once; the per-pixel test below is branch-free
+    const bool f_gt = conf && (a.flags & DA3S_MASK_CONF_GT), f_ge = conf && (a.flags & DA3S_MASK_CONF_GE);
+    const bool f_floor = conf && (a.flags & DA3S_MASK_CONF_FLOOR), f_depth = a.flags & DA3S_MASK_DEPTH;
+    const bool f_wz = a.flags & DA3S_MASK_WORLD_Z;
+    const float cfloor = a.conf_floor, deps = a.depth_eps;
     auto keep_of = [&](float d, float c, double X, double Y, double Z) -> bool {
-        bool k = true;
-        if (conf) {
-            if (a.flags & DA3S_MASK_CONF_GT) k = k && (c > thr);
-            if (a.flags & DA3S_MASK_CONF_GE) k = k && (c >= thr);
-            if (a.flags & DA3S_MASK_CONF_FLOOR) k = k && (c > a.conf_floor);
-        }
-        if (a.flags & DA3S_MASK_DEPTH) k = k && (d > a.depth_eps) && is_finite_f(d);
-        if (a.flags & DA3S_MASK_WORLD_Z)
+        bool k = (!f_gt || c > thr) & (!f_ge || c >= thr) & (!f_floor || c > cfloor);
+        k = k & (!f_depth || ((d > deps) & is_finite_f(d)));
+        if (f_wz)
             k = k && (Z > 0.1) && (Z < 50.0) && (fabs(X) < INFINITY) && (fabs(Y) < INFINITY) && (fabs(Z) < INFINITY);
         return k;
     };
@@ -200,9 +200,8 @@ unproject_filter_kernel(K1Args a) {
         const float4* d4 = reinterpret_cast<const float4*>(depth);
         const float4* c4 = reinterpret_cast<const float4*>(conf);
         // one float4 group = 4 pixels -> 12 output values; staged per warp so every store is coalesced
-        auto emit = [&](long long gb, long long g, bool active, const float* dv, const float* cv) {
-            long long pix = g << 2;
-            int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+        auto emit = [&](long long gb, long long g, int u, int v, bool active, const float* dv, const float* cv) {
+            const long long pix = g << 2;
             unsigned int mbits = 0;
             OutT o[12];
 #pragma unroll
@@ -238,8 +237,15 @@ unproject_filter_kernel(K1Args a) {
                 for (int j = 0; j < 12; ++j) out[j] = (double)o[j];
             }
         };
+        // pixel coordinates are carried incrementally: one division per thread, then adds with carry
+        const int W = a.W;
+        const int step_px = K1_THREADS * 4, step_v = step_px / W, step_u = step_px - step_v * W;
+        int v0, u0;
+        { const long long p0 = (g_begin + threadIdx.x) << 2; v0 = (int)(p0 / W); u0 = (int)(p0 - (long long)v0 * W); }
         for (long long gb = g_begin; gb < g_end; gb += 2 * K1_THREADS) {  // block-uniform; two groups in flight per thread
             const long long g0 = gb + threadIdx.x, g1 = g0 + K1_THREADS;
+            int u1 = u0 + step_u, v1 = v0 + step_v;
+            if (u1 >= W) { u1 -= W; ++v1; }
             const bool a0 = g0 < g_end, a1 = g1 < g_end;
             float d0[4] = {0, 0, 0, 0}, c0[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
             float4 t0, t1, q0, q1;
@@ -251,8 +257,10 @@ unproject_filter_kernel(K1Args a) {
             if (a1) { d1[0] = t1.x; d1[1] = t1.y; d1[2] = t1.z; d1[3] = t1.w; }
             if (conf && a0) { c0[0] = q0.x; c0[1] = q0.y; c0[2] = q0.z; c0[3] = q0.w; }
             if (conf && a1) { c1[0] = q1.x; c1[1] = q1.y; c1[2] = q1.z; c1[3] = q1.w; }
-            emit(gb, g0, a0, d0, c0);
-            if (gb + K1_THREADS < g_end) emit(gb + K1_THREADS, g1, a1, d1, c1);
+            emit(gb, g0, u0, v0, a0, d0, c0);
+            if (gb + K1_THREADS < g_end) emit(gb + K1_THREADS, g1, u1, v1, a1, d1, c1);
+            u0 = u1 + step_u; v0 = v1 + step_v;
+            if (u0 >= W) { u0 -= W; ++v0; }
         }
     } else {
         const long long p_begin = (long long)blockIdx.x * a.groups_per_block * 4;

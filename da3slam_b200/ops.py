@@ -444,7 +444,7 @@ class VoxelGrid:
         self.device = device
         self.table_slots = table_slots
         self.max_voxels = max_voxels
-        self.ctx = context(device, table_slots * 64 + (256 << 20))
+        self.ctx = context(device, table_slots * 73 + (256 << 20))
         self.xyz = torch.empty((max_voxels, 3), dtype=torch.float32, device=device)
         self.rgb = torch.empty((max_voxels, 3), dtype=torch.uint8, device=device) if with_rgb else None
         self.count = torch.empty((max_voxels,), dtype=torch.int32, device=device)
@@ -492,7 +492,7 @@ def voxel_downsample(clouds, voxel: float, table_slots: int | None = None, max_v
     if table_slots is None:
         table_slots = 1 << max(10, int(math.ceil(math.log2(max(2 * total, 1024)))))
         table_slots = min(table_slots, 1 << 28)
-    need = table_slots * 64 + (64 << 20)
+    need = table_slots * 73 + (64 << 20)
     ctx = context(dev, need)
     if max_voxels is None:
         max_voxels = min(total, table_slots)

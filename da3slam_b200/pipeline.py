@@ -182,7 +182,7 @@ class SequencePlan:
                 table_slots = 1 << max(12, int(np.ceil(np.log2(max(total // 4, 4096)))))
                 table_slots = min(table_slots, 1 << 27)
             if max_voxels is None:
-                max_voxels = table_slots // 2
+                max_voxels = table_slots
             self.grid = ops.VoxelGrid(self.dev, table_slots, max_voxels, submaps[0].images is not None)
             self.points_per_step = total
         else:
