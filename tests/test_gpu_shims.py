@@ -1,0 +1,185 @@
+"""GPU tests of the reference-named shim modules (align_geometry, utils.*, solver, viewer):
+same call signatures as the reference, results against the reference's golden outputs
+(tests/golden, written from the unmodified reference) and the oracle."""
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_port as rp
+from oracle import spec_port as sp
+
+pytestmark = pytest.mark.gpu
+REL = 1e-6
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(1e-30, np.max(np.abs(b))))
+
+
+def close_sim3(got, s, R, t, tol=REL):
+    assert isinstance(got[0], float) and got[1].shape == (3, 3) and got[1].dtype == np.float64 and got[2].shape == (3,)
+    assert abs(got[0] - s) <= tol * abs(s) and rel_err(got[1], R) <= tol
+    assert np.abs(got[2] - t).max() <= tol * max(1.0, np.abs(t).max())
+
+
+def test_unprojection_shims(golden, cuda):
+    import align_geometry as ag
+    import utils.align_geometry_single as ags
+    import utils.geometry as ug
+    g = golden("unproject")
+    d, K, E = g["depth"], g["K"], g["E"]
+    w = ug.depth_to_point_cloud_vectorized(d, K, E)
+    assert w.dtype == np.float64 and w.shape == d.shape + (3,) and rel_err(w, g["u2_world"]) < REL
+    for mod in (ag, ags):
+        c = mod.depth_to_point_cloud_vectorized(d, K, E, in_coords="camera")
+        assert isinstance(c, np.ndarray) and c.dtype == np.float32 and rel_err(c, g["u1_camera"]) < REL
+        ww = mod.depth_to_point_cloud_vectorized(d, K, E, in_coords="world")
+        assert rel_err(ww, g["u1_world"]) < 2e-6
+    t = ag.depth_to_point_cloud_vectorized(torch.from_numpy(d), torch.from_numpy(K), torch.from_numpy(E))
+    assert isinstance(t, torch.Tensor) and rel_err(t.numpy(), g["u1_camera"]) < REL
+    with pytest.raises(AssertionError):
+        ag.depth_to_point_cloud_vectorized(d, K, E, in_coords="sideways")
+
+
+def test_overlap_and_depth_scale_shims(golden, cuda):
+    import align_geometry as ag
+    import utils.align as ua
+    import utils.align_geometry_single as ags
+    g = golden("overlap")
+    prev = {k[5:]: g[k] for k in g.files if k.startswith("prev_")}
+    cur = {k[4:]: g[k] for k in g.files if k.startswith("cur_")}
+    a, b = ag.extract_overlap_point_cloud(types.SimpleNamespace(**prev), types.SimpleNamespace(**cur))
+    assert a.shape == g["X_root_prev"].shape and rel_err(a, g["X_root_prev"]) < REL and rel_err(b, g["X_root_cur"]) < REL
+    a, b = ags.extract_single_overlap_point_cloud(prev, cur)
+    assert rel_err(a, g["X_single_prev"]) < REL and rel_err(b, g["X_single_cur"]) < REL
+    pm1, pm2, c1, c2 = ua.extract_overlap_chunk_prediction(prev, cur, 2)
+    assert c1 is None and c2 is None and rel_err(pm1, g["X_align_pm1"]) < REL and rel_err(pm2, g["X_align_pm2"]) < REL
+    g = golden("depth_scale")
+    for case in range(4):
+        p = dict(depth=g[f"dA{case}"], conf=g[f"cA{case}"]); c = dict(depth=g[f"dB{case}"], conf=g[f"cB{case}"])
+        po, co = types.SimpleNamespace(**p), types.SimpleNamespace(**c)
+        got = ag.estimate_depth_scale(po, co, conf_th=0.2)
+        assert isinstance(got, float) and np.float64(got) == g[f"plain{case}"]          # exact selection: bit-exact
+        assert np.float64(ags.estimate_depth_scale(p, c, conf_th=0.2)) == g[f"guard{case}"]
+        assert np.float64(ags.estimate_depth_scale(po, co)) == g[f"guard_obj{case}"]
+    assert np.float64(ags.estimate_depth_scale(dict(depth=g["dA3"]), dict(depth=g["dB3"]))) == g["noconf"]
+
+
+def test_umeyama_and_irls_shims(golden, cuda):
+    import align_geometry as ag
+    import utils.align as ua
+    import utils.geometry as ug
+    g = golden("umeyama")
+    close_sim3(ua.weighted_umeyama_alignment(g["src"], g["dst"], g["w"]), float(g["W_s"]), g["W_R"], g["W_t"])
+    close_sim3(ag._umeyama_sim3(g["src"], g["dst"]), float(g["U_s"]), g["U_R"], g["U_t"])
+    close_sim3(ua.align_two_point_clouds_umeyama(g["pm1"], g["pm2"]), float(g["N_s"]), g["N_R"], g["N_t"])
+    close_sim3(ua.align_two_point_clouds(g["pm1"], g["pm2"]), float(g["Napi_s"]), g["Napi_R"], g["Napi_t"])
+    # pixel-correspondence registration: exact data -> exact recovery
+    close_sim3(ag.align_two_point_clouds_umeyama(g["src"], g["dst"]), float(g["U_s"]), g["U_R"], g["U_t"])
+    s, R, t = ag.align_two_point_clouds_icp(g["src"], g["dst"])
+    assert s == 1.0 and rel_err(R, g["U_R"]) < REL
+    gi = golden("irls")
+    for tag, (a1, a2) in {"same": (gi["c1"], gi["c1"]), "indep": (gi["c1"], gi["c2"])}.items():
+        for seed in (0, 1):
+            np.random.seed(seed)                      # the reference draws its subsample from the global RNG
+            got = ua.align_two_point_clouds_irls(gi["pm1"], gi["pm2"], a1, a2)
+            close_sim3(got, float(gi[f"{tag}{seed}_s"]), gi[f"{tag}{seed}_R"], gi[f"{tag}{seed}_t"])
+    got = ua.align_two_point_clouds_irls(gi["pm1"][:, :5, :10], gi["pm2"][:, :5, :10], gi["c1"][:, :5, :10], gi["c1"][:, :5, :10])
+    assert got[0] == 1.0 and np.array_equal(got[1], np.eye(3)) and not got[2].any()      # utils/align.py:154-156
+    gs = golden("sim3_chain")
+    out = ug.apply_sim3_transform(gs["P4"], float(gs["s"]), gs["R"], gs["t"])
+    assert out.dtype == np.float64 and out.shape == gs["P4"].shape and rel_err(out, gs["S4"]) < 1e-14
+    assert rel_err(ug.apply_sim3_transform(gs["P2"], float(gs["s"]), gs["R"], gs["t"]), gs["S2"]) < 1e-14
+
+
+class _FakeDA3:
+    """Stands in for depth_anything_3.api.DepthAnything3: returns synthetic Predictions."""
+    def __init__(self, subs):
+        self.subs, self.calls = subs, 0
+
+    @classmethod
+    def from_pretrained(cls, path):
+        return cls(_FakeDA3.SUBS)
+
+    def to(self, device):
+        return self
+
+    def eval(self):
+        return self
+
+    def inference(self, image=None, **kw):
+        s = self.subs[self.calls]
+        self.calls += 1
+        return types.SimpleNamespace(processed_images=s["processed_images"], depth=s["depth"].copy(), conf=s["conf"],
+                                     extrinsics=s["extrinsics"], intrinsics=s["intrinsics"])
+
+
+def test_solver_runs_on_fake_network(cuda, monkeypatch, tmp_path):
+    from da3slam_b200 import synth
+    H, W, F, n_chunks = 40, 52, 4, 3
+    subs, gt = synth.make_sequence(n_chunks, F, H, W, overlap=1, seed=3, with_images=True)
+    _FakeDA3.SUBS = subs
+    mod = types.ModuleType("depth_anything_3"); api = types.ModuleType("depth_anything_3.api")
+    api.DepthAnything3 = _FakeDA3; mod.api = api
+    monkeypatch.setitem(sys.modules, "depth_anything_3", mod)
+    monkeypatch.setitem(sys.modules, "depth_anything_3.api", api)
+    n_frames = F + (n_chunks - 1) * (F - 1)
+    for i in range(n_frames):
+        (tmp_path / f"{i:04d}.png").write_bytes(b"x")
+    import solver
+    monkeypatch.setattr(solver.time, "sleep", lambda s: None)
+    cfg = {"Model": {"chunk_size": F, "overlap_size": 1, "keyframe_interval": 1, "sleep_between_chunk": 0, "port": 8080},
+           "Weights": {"DA3": "unused"}}
+    sv = solver.SLAMSolver(str(tmp_path), cfg)
+    sv.run()
+    assert sv.chunk_count == n_chunks and len(sv.chunk_prediction_list) == n_chunks
+    # every chunk got global extrinsics; the overlap frame's global pose is continuous across chunks
+    for k in range(1, n_chunks):
+        Eg = sv.chunk_prediction_list[k]["extrinsics_global"]
+        assert Eg.shape == (F, 3, 4) and Eg.dtype == np.float64
+        prev_last = np.asarray(sv.chunk_prediction_list[k - 1]["extrinsics_global"][-1], np.float64)
+        # chain consistency against the oracle's restatement with the same registration result
+        prev, cur = sv.chunk_prediction_list[k - 1], sv.chunk_prediction_list[k]
+        pc_prev = rp.unproject_f32(prev["depth"][-1:], prev["intrinsics"][-1:], prev["extrinsics"][-1:]).reshape(-1, 3)
+        pc_cur = rp.unproject_f32(cur["depth"][:1], cur["intrinsics"][:1], cur["extrinsics"][:1]).reshape(-1, 3)
+        s, R, t = rp.umeyama_sim3(pc_cur.astype(np.float64), pc_prev.astype(np.float64))
+        t_rigid = pc_prev.mean(0) - R @ pc_cur.mean(0)
+        ref = rp.chain_extrinsics_single_overlap(prev_last, np.asarray(cur["extrinsics"]), R, t_rigid)
+        assert rel_err(Eg, ref) < 1e-5
+    # the viewer holds every frame of every chunk (the overlap frame twice, as in the reference)
+    assert sv.viewer.next_frame_id == n_chunks * F
+    pts, cols = sv.viewer.visible_points()
+    assert pts.shape[1] == 3 and len(pts) == len(cols) > 0
+
+
+def test_viewer_against_restated_reference(cuda):
+    from da3slam_b200 import synth
+    import viewer
+    rng = np.random.default_rng(5)
+    H, W, n = 30, 40, 3
+    depth = synth.smooth_depth(rng, n, H, W)
+    depth[0, :3] = 0.02
+    conf = synth.da3_like_conf(rng, n, H, W)
+    K = synth.make_intrinsics(n, H, W)
+    E = synth.trajectory_w2c(rng, n).astype(np.float32)
+    img = rng.random((n, 3, H, W))
+    v = viewer.SLAMViewer(port=0, vis_stride=2)
+    ref_pts, ref_conf = [], []
+    for f in range(n):
+        v.add_frame(img[f], depth[f], conf[f], E[f], K[f])
+        p, c, _ = rp.viewer_frame_points(depth[f], conf[f], E[f], K[f], vis_stride=2)     # viewer.py:198-218
+        ref_pts.append(p); ref_conf.append(c)
+    ref_pts, ref_conf = np.vstack(ref_pts), np.hstack(ref_conf)
+    mask, thr = rp.viewer_conf_mask(ref_conf, 65.0)                                        # viewer.py:333-336
+    assert v.total_points == len(ref_conf)
+    assert v._threshold() == thr                                                            # exact percentile: bit-exact
+    pts, cols = v.visible_points()
+    assert len(pts) == int(mask.sum()) and rel_err(pts, ref_pts[mask]) < 2e-6
+    v.frame_selector = "1"
+    assert 0 < len(v.visible_points()[0]) < len(pts)
+    v.clear()
+    assert v.total_points == 0 and len(v.visible_points()[0]) == 0
