@@ -162,13 +162,19 @@ select_sample_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, da
 }
 
 // ---------------------------------------------------------------------------------
-// B: one streaming pass — count below / at the pivots, collect the candidates
+// B: one streaming pass — count below / at the pivots, collect the candidates.
+// ~15 instructions per element: key, three predicated counters, one range test; the rare
+// candidates are staged in shared memory (warp-aggregated) and flushed with one global
+// atomic per block.
 // ---------------------------------------------------------------------------------
+#define SEL_STAGE (SEL_THREADS * SEL_ITEMS)          // a block can never stage more than it reads
+
 __global__ void __launch_bounds__(SEL_THREADS)
 select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, unsigned int* cand, long long cand_cap,
                     unsigned int* tickets) {
+    __shared__ unsigned int stage[SEL_STAGE];
+    __shared__ unsigned int n_stage;
     __shared__ unsigned long long blk[4];
-    __shared__ unsigned int warp_tot[SEL_THREADS / 32];
     __shared__ unsigned long long cand_base;
     __shared__ bool is_last;
     const int seg_id = blockIdx.y;
@@ -176,51 +182,53 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
     SelWork* w = work + seg_id;
     if (w->done) return;                                             // block-uniform
     const unsigned int lo = w->lo_key, hi = w->hi_key;
+    const unsigned int span = hi - lo - 1u;                          // lo < k < hi  <=>  (k - lo - 1) < span  (unsigned; lo==hi wraps to none)
+    const bool lo_ne_hi = hi != lo;
     const long long base = (long long)blockIdx.x * (SEL_THREADS * SEL_ITEMS);
     if (threadIdx.x < 4) blk[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) n_stage = 0;
     __syncthreads();
-    unsigned int keys[SEL_ITEMS];
-    unsigned int okmask = 0, candmask = 0;
+    const unsigned int lane = threadIdx.x & 31;
     unsigned int n_valid = 0, n_less = 0, n_eqlo = 0, n_eqhi = 0;
+    auto visit = [&](unsigned int k, bool ok) {
+        n_valid += ok;
+        n_less += ok && (k < lo);
+        n_eqlo += ok && (k == lo);
+        n_eqhi += ok && (k == hi) && lo_ne_hi;
+        const bool c = ok && ((k - lo - 1u) < span) && lo_ne_hi;
+        const unsigned int m = __ballot_sync(0xffffffffu, c);
+        if (m) {                                                     // warp-uniform, rare
+            unsigned int pos = 0;
+            if (lane == 0) pos = atomicAdd(&n_stage, (unsigned int)__popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (c) stage[pos + __popc(m & ((1u << lane) - 1u))] = k;
+        }
+    };
     if (base < seg.n) {
-        const bool vec = (seg.kind != DA3S_SEL_RATIO) && aligned16(seg.a);
-        if (vec && base + (long long)SEL_THREADS * SEL_ITEMS <= seg.n) {
+        const bool vec = (seg.kind != DA3S_SEL_RATIO) && aligned16(seg.a) && base + (long long)SEL_THREADS * SEL_ITEMS <= seg.n;
+        if (vec) {
             float4 v[SEL_ITEMS / 4];
 #pragma unroll
             for (int it = 0; it < SEL_ITEMS / 4; ++it)
                 v[it] = ldg_stream(reinterpret_cast<const float4*>(seg.a + base + ((long long)it * SEL_THREADS + threadIdx.x) * 4));
+            const bool all_ok = seg.kind == DA3S_SEL_VALUES;
 #pragma unroll
             for (int it = 0; it < SEL_ITEMS / 4; ++it) {
-                const float f[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    keys[it * 4 + j] = f32_to_key(f[j]);
-                    if (seg.kind == DA3S_SEL_VALUES || f[j] > 0.0f) okmask |= 1u << (it * 4 + j);
-                }
+                visit(f32_to_key(v[it].x), all_ok || v[it].x > 0.0f);
+                visit(f32_to_key(v[it].y), all_ok || v[it].y > 0.0f);
+                visit(f32_to_key(v[it].z), all_ok || v[it].z > 0.0f);
+                visit(f32_to_key(v[it].w), all_ok || v[it].w > 0.0f);
             }
         } else {
-#pragma unroll
-            for (int it = 0; it < SEL_ITEMS / 4; ++it)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const long long i = base + ((long long)it * SEL_THREADS + threadIdx.x) * 4 + j;
-                    keys[it * 4 + j] = 0;
-                    if (i < seg.n && sel_key(seg, i, keys[it * 4 + j])) okmask |= 1u << (it * 4 + j);
-                }
-        }
-#pragma unroll
-        for (int e = 0; e < SEL_ITEMS; ++e) {
-            const bool ok = (okmask >> e) & 1u;
-            const unsigned int k = keys[e];
-            n_valid += ok;
-            n_less += ok && (k < lo);
-            n_eqlo += ok && (k == lo);
-            n_eqhi += ok && (k == hi) && (hi != lo);
-            if (ok && k > lo && k < hi) candmask |= 1u << e;
+#pragma unroll 4
+            for (int e = 0; e < SEL_ITEMS; ++e) {                    // every lane calls visit (ballot inside)
+                const long long i = base + ((long long)(e >> 2) * SEL_THREADS + threadIdx.x) * 4 + (e & 3);
+                unsigned int k = 0;
+                const bool ok = i < seg.n && sel_key(seg, i, k);
+                visit(k, ok);
+            }
         }
     }
-    // block totals of the four counters
-    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int r0 = __reduce_add_sync(0xffffffffu, n_valid), r1 = __reduce_add_sync(0xffffffffu, n_less);
     unsigned int r2 = __reduce_add_sync(0xffffffffu, n_eqlo), r3 = __reduce_add_sync(0xffffffffu, n_eqhi);
     if (lane == 0) {
@@ -229,19 +237,8 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
         if (r2) atomicAdd(&blk[2], (unsigned long long)r2);
         if (r3) atomicAdd(&blk[3], (unsigned long long)r3);
     }
-    // candidate append: block prefix sum, one global atomic per block
-    const unsigned int mine = __popc(candmask);
-    unsigned int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    unsigned int before = 0, total = 0;
-#pragma unroll
-    for (int x = 0; x < SEL_THREADS / 32; ++x) { if (x < (int)warp) before += warp_tot[x]; total += warp_tot[x]; }
+    const unsigned int total = n_stage;
     if (threadIdx.x == 0) {
         cand_base = total ? atomicAdd(&w->c_cand, (unsigned long long)total) : 0ull;
         if (blk[0]) atomicAdd(&w->c_valid, blk[0]);
@@ -251,15 +248,12 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
     }
     __syncthreads();
     if (total) {
-        unsigned long long pos = cand_base + before + (incl - mine);
         unsigned int* dst = cand + (size_t)seg_id * cand_cap;
         bool over = false;
-#pragma unroll
-        for (int e = 0; e < SEL_ITEMS; ++e)
-            if ((candmask >> e) & 1u) {
-                if ((long long)pos < cand_cap) dst[pos] = keys[e]; else over = true;
-                ++pos;
-            }
+        for (unsigned int i = threadIdx.x; i < total; i += SEL_THREADS) {
+            const unsigned long long pos = cand_base + i;
+            if ((long long)pos < cand_cap) dst[pos] = stage[i]; else over = true;
+        }
         if (over) w->overflow = 1;
     }
     __threadfence();

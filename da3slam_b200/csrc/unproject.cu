@@ -71,41 +71,45 @@ struct UnprojFrame {            // per-frame constants, staged in shared memory
     float Mf[9], mf[3];
 };
 
+template <int MODE> struct K1Val { typedef double type; };
+template <> struct K1Val<DA3S_UNPROJ_FAST> { typedef float type; };      // the fast path never leaves float32
+
 template <int MODE>             // DA3S_UNPROJ_CLOSED / KINV / FAST
 __device__ __forceinline__ void unproject_pixel(const UnprojFrame& f, int u, int v, float d, bool xform,
-                                                double& X, double& Y, double& Z) {
-    if (MODE == DA3S_UNPROJ_FAST) {
+                                                typename K1Val<MODE>::type& X, typename K1Val<MODE>::type& Y,
+                                                typename K1Val<MODE>::type& Z) {
+    if constexpr (MODE == DA3S_UNPROJ_FAST) {
         float x, y;
         cam_fast((float)u, (float)v, d, f.cuf, f.cvf, f.ifu, f.ifv, x, y);
         if (xform) {
-            X = (double)fmaf(f.Mf[0], x, fmaf(f.Mf[1], y, fmaf(f.Mf[2], d, f.mf[0])));
-            Y = (double)fmaf(f.Mf[3], x, fmaf(f.Mf[4], y, fmaf(f.Mf[5], d, f.mf[1])));
-            Z = (double)fmaf(f.Mf[6], x, fmaf(f.Mf[7], y, fmaf(f.Mf[8], d, f.mf[2])));
+            X = fmaf(f.Mf[0], x, fmaf(f.Mf[1], y, fmaf(f.Mf[2], d, f.mf[0])));
+            Y = fmaf(f.Mf[3], x, fmaf(f.Mf[4], y, fmaf(f.Mf[5], d, f.mf[1])));
+            Z = fmaf(f.Mf[6], x, fmaf(f.Mf[7], y, fmaf(f.Mf[8], d, f.mf[2])));
         } else {
             X = x; Y = y; Z = d;
         }
-        return;
-    }
-    double x, y, z;
-    if (MODE == DA3S_UNPROJ_CLOSED) {
-        // src/vggt/utils/geometry.py:109-114: float64 sub, mul, div (each rounded once), then float32
-        double dd = (double)d;
-        x = (double)__double2float_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)u, f.cu), dd), f.fu));
-        y = (double)__double2float_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)v, f.cv), dd), f.fv));
-        z = dd;
     } else {
-        // utils/geometry.py:26-28: K^-1 [u, v, 1] then * depth, float64 throughout
-        double uu = (double)u, vv = (double)v, dd = (double)d;
-        x = (f.kinv[0] * uu + f.kinv[1] * vv + f.kinv[2]) * dd;
-        y = (f.kinv[3] * uu + f.kinv[4] * vv + f.kinv[5]) * dd;
-        z = (f.kinv[6] * uu + f.kinv[7] * vv + f.kinv[8]) * dd;
-    }
-    if (xform) {
-        X = f.M[0] * x + f.M[1] * y + f.M[2] * z + f.m[0];
-        Y = f.M[3] * x + f.M[4] * y + f.M[5] * z + f.m[1];
-        Z = f.M[6] * x + f.M[7] * y + f.M[8] * z + f.m[2];
-    } else {
-        X = x; Y = y; Z = z;
+        double x, y, z;
+        if (MODE == DA3S_UNPROJ_CLOSED) {
+            // src/vggt/utils/geometry.py:109-114: float64 sub, mul, div (each rounded once), then float32
+            double dd = (double)d;
+            x = (double)__double2float_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)u, f.cu), dd), f.fu));
+            y = (double)__double2float_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)v, f.cv), dd), f.fv));
+            z = dd;
+        } else {
+            // utils/geometry.py:26-28: K^-1 [u, v, 1] then * depth, float64 throughout
+            double uu = (double)u, vv = (double)v, dd = (double)d;
+            x = (f.kinv[0] * uu + f.kinv[1] * vv + f.kinv[2]) * dd;
+            y = (f.kinv[3] * uu + f.kinv[4] * vv + f.kinv[5]) * dd;
+            z = (f.kinv[6] * uu + f.kinv[7] * vv + f.kinv[8]) * dd;
+        }
+        if (xform) {
+            X = f.M[0] * x + f.M[1] * y + f.M[2] * z + f.m[0];
+            Y = f.M[3] * x + f.M[4] * y + f.M[5] * z + f.m[1];
+            Z = f.M[6] * x + f.M[7] * y + f.M[8] * z + f.m[2];
+        } else {
+            X = x; Y = y; Z = z;
+        }
     }
 }
 
@@ -124,7 +128,7 @@ struct K1Args {
 };
 
 template <int MODE, typename OutT, bool VEC>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, (MODE == DA3S_UNPROJ_FAST && sizeof(OutT) == 4) ? 4 : 2)
 unproject_filter_kernel(K1Args a) {
     __shared__ UnprojFrame fr;
     __shared__ __align__(16) float stage[VEC ? (K1_THREADS / 32) * 32 * 12 : 4];     // per-warp staging for f32 xyz
@@ -184,11 +188,13 @@ unproject_filter_kernel(K1Args a) {
     const bool f_floor = conf && (a.flags & DA3S_MASK_CONF_FLOOR), f_depth = a.flags & DA3S_MASK_DEPTH;
     const bool f_wz = a.flags & DA3S_MASK_WORLD_Z;
     const float cfloor = a.conf_floor, deps = a.depth_eps;
-    auto keep_of = [&](float d, float c, double X, double Y, double Z) -> bool {
+    typedef typename K1Val<MODE>::type CT;
+    auto keep_of = [&](float d, float c, CT X, CT Y, CT Z) -> bool {
         bool k = (!f_gt || c > thr) & (!f_ge || c >= thr) & (!f_floor || c > cfloor);
         k = k & (!f_depth || ((d > deps) & is_finite_f(d)));
         if (f_wz)
-            k = k && (Z > 0.1) && (Z < 50.0) && (fabs(X) < INFINITY) && (fabs(Y) < INFINITY) && (fabs(Z) < INFINITY);
+            k = k && (Z > (CT)0.1) && (Z < (CT)50.0) && (fabs((double)X) < INFINITY) && (fabs((double)Y) < INFINITY) &&
+                (fabs((double)Z) < INFINITY);
         return k;
     };
 
@@ -206,7 +212,7 @@ unproject_filter_kernel(K1Args a) {
             OutT o[12];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                double X, Y, Z;
+                CT X, Y, Z;
                 unproject_pixel<MODE>(fr, u, v, dv[j], xform, X, Y, Z);
                 o[3 * j] = (OutT)X; o[3 * j + 1] = (OutT)Y; o[3 * j + 2] = (OutT)Z;
                 if (active && keep_of(dv[j], cv[j], X, Y, Z)) mbits |= (1u << (8 * j));
@@ -269,7 +275,7 @@ unproject_filter_kernel(K1Args a) {
         for (long long pix = p_begin + threadIdx.x; pix < p_end; pix += K1_THREADS) {
             float d = depth[pix], c = conf ? conf[pix] : 0.0f;
             int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
-            double X, Y, Z;
+            CT X, Y, Z;
             unproject_pixel<MODE>(fr, u, v, d, xform, X, Y, Z);
             bool k = keep_of(d, c, X, Y, Z);
             kept += k;
