@@ -1,9 +1,10 @@
 // select.cu — exact, batched order statistics (median / percentile) of float32 data.
 //
 // One full pass over the data instead of three:
-//   A  sample    one block per segment sorts a 4096-element strided sample in shared memory
-//                (bitonic) and brackets the wanted rank between two sample keys [lo, hi]
-//                (+-5 sigma of the sampling error).  Segments of <= 4096 elements are answered here.
+//   A  sample    one block per segment takes a 4096-element strided sample into shared memory and
+//                radix-selects (in shared memory) the two sample keys [lo, hi] that bracket the
+//                wanted rank (+-5 sigma of the sampling error).  Segments of <= 4096 elements are
+//                answered here.
 //   B  count     ONE streaming pass: per element 2 compares; counts elements below / equal to
 //                the pivots and appends the few (~8 %) strictly inside the bracket to a
 //                candidate buffer (block-aggregated append).  The last block of a segment
@@ -11,12 +12,12 @@
 //                candidates — or, if the bracket missed or the buffer overflowed (heavy ties,
 //                adversarial data), redirects the next stage to the full segment.  Exactness
 //                never depends on the sample; only the amount of work does.
-//   C  radix     3-pass MSD radix select (11+11+10 bits) over the candidates (or, on fallback,
-//                over the whole segment with the same grid looping).  The final pass
-//                reproduces numpy >= 2's float32 finishing arithmetic bit for bit
+//   C  resolve   one block per segment: 4-pass MSD radix select (8 bits each, shared-memory
+//                histograms) over the candidates (or, on fallback, over the whole segment).
+//                The end reproduces numpy >= 2's float32 finishing arithmetic bit for bit
 //                (SURVEY.md appendix A): median of an even count = (a + b) / 2; percentile =
 //                float32 virtual index (n-1) * (p / 100f), lerp with the gamma >= 0.5 branch.
-// Everything is device-side: no host round trip, fixed launch sequence (5 kernels).
+// Everything is device-side: no host round trip, fixed launch sequence (3 kernels).
 //
 // Algorithmic bytes: 4 B per element (16 B for the depth-ratio kind) read once.
 #include "common.cuh"
@@ -41,7 +42,7 @@ struct SelWork {                           // per segment, device resident
     int overflow;
     // stage B counters
     unsigned long long c_valid, c_less, c_eqlo, c_eqhi, c_cand;
-    // stage C state
+    // multi-block stage C state
     unsigned int prefix[2];
 };
 
@@ -100,11 +101,84 @@ __device__ __forceinline__ void sel_finish(const da3s_select_seg& seg, long long
 }
 
 // ---------------------------------------------------------------------------------
-// A: sample, sort, bracket
+// block-level exact selection of TWO ranks in one sweep per digit: the keys of rank r[0] and r[1]
+// among the keys produced by `get(i, k)`, i in [0, n) (get returns false for elements that do not
+// take part).  MSD radix, 8 bits per pass, histograms in shared memory; keys are known to be
+// < 2^(32-lz), so only ceil((32-lz)/8) passes run and the leading pass already spreads over all
+// 256 bins.  While both ranks share a prefix one histogram serves both.  Every thread of the
+// block must call it.
+// ---------------------------------------------------------------------------------
+struct SelScratch { unsigned int hist[2][256]; unsigned int digit[2]; unsigned int rest[2]; };
+
+template <typename Get>
+__device__ void block_select2(long long n, long long r0, long long r1, Get get, SelScratch& sc, int lz,
+                              unsigned int& key0, unsigned int& key1) {
+    unsigned int prefix0 = 0, prefix1 = 0;
+    const int passes = (32 - lz + 7) / 8;
+    const unsigned int lane = threadIdx.x & 31;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const bool same = prefix0 == prefix1;
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sc.hist[0][0])[i] = 0;
+        __syncthreads();
+        auto visit = [&](unsigned int k, bool ok) {                  // whole warps call it
+            const unsigned int kk = k << lz;
+            const unsigned int top = pass == 0 ? 0u : (kk >> (shift + 8));
+            const unsigned int digit = (kk >> shift) & 255u;
+            const bool in0 = ok && top == prefix0;
+            int uniform;
+            __match_all_sync(0xffffffffu, in0 ? digit : 0xFFFFu, &uniform);
+            if (uniform) { if (in0 && lane == 0) atomicAdd(&sc.hist[0][digit], 32u); }   // typical for un-bracketed keys in the leading pass
+            else if (in0) atomicAdd(&sc.hist[0][digit], 1u);
+            if (!same && ok && top == prefix1) atomicAdd(&sc.hist[1][digit], 1u);
+        };
+        const long long step = (long long)blockDim.x * 4;
+        const long long n_round = (n + step - 1) / step * step;
+        for (long long i0 = threadIdx.x; i0 < n_round; i0 += step) {  // 4 independent loads in flight per thread
+            unsigned int k[4]; bool ok[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const long long i = i0 + (long long)j * blockDim.x; k[j] = 0; ok[j] = i < n && get(i, k[j]); }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) visit(k[j], ok[j]);
+        }
+        __syncthreads();
+        if (threadIdx.x < 64) {                                      // warp q locates rank q: 8 bins per lane, exclusive scan
+            const int q = threadIdx.x >> 5;
+            const unsigned int* h = sc.hist[(q == 1 && !same) ? 1 : 0];
+            long long rank = q ? r1 : r0;
+            unsigned int loc[8], tot = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { loc[b] = h[lane * 8 + b]; tot += loc[b]; }
+            unsigned int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (unsigned int)o) incl += t;
+            }
+            long long run = (long long)(incl - tot);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (rank >= run && rank < run + (long long)loc[b]) { sc.digit[q] = lane * 8 + b; sc.rest[q] = (unsigned int)(rank - run); }
+                run += loc[b];
+            }
+        }
+        __syncthreads();
+        prefix0 = (prefix0 << 8) | sc.digit[0]; r0 = (long long)sc.rest[0];
+        prefix1 = (prefix1 << 8) | sc.digit[1]; r1 = (long long)sc.rest[1];
+        __syncthreads();
+    }
+    const int drop = 32 - 8 * passes;                                // digits not visited are zero
+    key0 = (drop >= 0 ? prefix0 << drop : prefix0) >> lz;
+    key1 = (drop >= 0 ? prefix1 << drop : prefix1) >> lz;
+}
+
+// ---------------------------------------------------------------------------------
+// A: sample, bracket
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SEL_THREADS)
 select_sample_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, da3s_select_out* out) {
     __shared__ unsigned int keys[SEL_SAMPLE];
+    __shared__ SelScratch sc;
     __shared__ unsigned int n_ok;
     const int seg_id = blockIdx.x;
     const da3s_select_seg seg = segs[seg_id];
@@ -124,41 +198,41 @@ select_sample_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, da
     }
     atomicAdd(&n_ok, mine);
     __syncthreads();
-    // bitonic sort, ascending; rejected samples (0xFFFFFFFF) sink to the end
-    for (unsigned int k = 2; k <= SEL_SAMPLE; k <<= 1)
-        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned int t = threadIdx.x; t < SEL_SAMPLE / 2; t += SEL_THREADS) {
-                const unsigned int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));       // lower index of the pair
-                const unsigned int l = i | j;
-                const bool up = ((i & k) == 0);
-                const unsigned int a = keys[i], b = keys[l];
-                if ((a > b) == up) { keys[i] = b; keys[l] = a; }
-            }
-            __syncthreads();
-        }
-    if (threadIdx.x != 0) return;
+    const long long mv = (long long)n_ok;
+    // valid samples are the ones != 0xFFFFFFFF; a real key 0xFFFFFFFF (a NaN pattern) among them is counted as rejected,
+    // which only widens the bracket (exactness comes from stage B/C, never from the sample)
+    auto get = [&](long long i, unsigned int& k) -> bool { k = keys[i]; return k != 0xFFFFFFFFu; };
     SelWork w;
     w.data = nullptr; w.n = 0; w.kind = SEL_KIND_KEYS; w.done = 0; w.lo_key = 0u; w.hi_key = 0xFFFFFFFFu;
     w.rank[0] = w.rank[1] = 0; w.resolved[0] = w.resolved[1] = 0; w.resolved_key[0] = w.resolved_key[1] = 0;
-    w.n_valid = 0; w.gamma = 0.0f; w.overflow = 0; w.c_valid = w.c_less = w.c_eqlo = w.c_eqhi = w.c_cand = 0ull;
     w.prefix[0] = w.prefix[1] = 0;
-    const long long mv = (long long)n_ok;
+    w.n_valid = 0; w.gamma = 0.0f; w.overflow = 0; w.c_valid = w.c_less = w.c_eqlo = w.c_eqhi = w.c_cand = 0ull;
     if (n <= SEL_SAMPLE) {
-        // the sample is the whole segment: answer now
+        // the sample is the whole segment: answer now (count the valid ones exactly, incl. NaN-pattern keys)
         long long k0, k1; float gamma;
         sel_ranks(mv, seg.stat, seg.percent, k0, k1, gamma);
-        sel_finish(seg, mv, gamma, mv == 0, mv ? keys[k0] : 0u, mv ? keys[k1] : 0u, out + seg_id);
-        w.done = 1; w.n_valid = mv; w.gamma = gamma;
-    } else if (mv > 0) {
+        auto get_all = [&](long long i, unsigned int& k) -> bool { unsigned int kk; bool ok = i < m && sel_key(seg, i, kk); k = kk; return ok; };
+        unsigned int a = 0, b = 0;
+        if (mv > 0) block_select2(m, k0, k1, get_all, sc, 0, a, b);  // block-uniform
+        if (threadIdx.x == 0) {
+            sel_finish(seg, mv, gamma, mv == 0, a, b, out + seg_id);
+            w.done = 1; w.n_valid = mv; w.gamma = gamma;
+            work[seg_id] = w;
+        }
+        return;
+    }
+    if (mv > 0) {                                                // block-uniform
         // bracket the wanted quantile of the VALID elements: +-5 sigma of the binomial sampling error
         const double q = (seg.stat == DA3S_SEL_MEDIAN) ? 0.5 : fmin(fmax((double)seg.percent / 100.0, 0.0), 1.0);
         const double c = q * (double)(mv - 1);
         const double margin = 5.0 * sqrt((double)mv * q * (1.0 - q)) + 8.0;
         const long long lo_i = (long long)floor(c - margin), hi_i = (long long)ceil(c + margin);
-        w.lo_key = lo_i <= 0 ? 0u : keys[lo_i];
-        w.hi_key = hi_i >= mv - 1 ? 0xFFFFFFFFu : keys[hi_i];
+        unsigned int klo, khi;
+        block_select2(SEL_SAMPLE, lo_i > 0 ? lo_i : 0, hi_i < mv - 1 ? hi_i : mv - 1, get, sc, 0, klo, khi);
+        if (lo_i > 0) w.lo_key = klo;
+        if (hi_i < mv - 1) w.hi_key = khi;
     }
-    work[seg_id] = w;
+    if (threadIdx.x == 0) work[seg_id] = w;
 }
 
 // ---------------------------------------------------------------------------------
@@ -167,7 +241,9 @@ select_sample_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, da
 // candidates are staged in shared memory (warp-aggregated) and flushed with one global
 // atomic per block.
 // ---------------------------------------------------------------------------------
-#define SEL_STAGE (SEL_THREADS * SEL_ITEMS)          // a block can never stage more than it reads
+#define SEL_SINGLE_MAX (1ll << 21)                   // up to here one block per segment resolves the candidates
+#define SEL_CHUNKS 8                                 // chunks of 4096 elements per block: amortises the block epilogue
+#define SEL_STAGE (2 * SEL_THREADS * SEL_ITEMS)      // candidate staging; flushed whenever another chunk might not fit
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, unsigned int* cand, long long cand_cap,
@@ -182,30 +258,69 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
     SelWork* w = work + seg_id;
     if (w->done) return;                                             // block-uniform
     const unsigned int lo = w->lo_key, hi = w->hi_key;
-    const unsigned int span = hi - lo - 1u;                          // lo < k < hi  <=>  (k - lo - 1) < span  (unsigned; lo==hi wraps to none)
     const bool lo_ne_hi = hi != lo;
-    const long long base = (long long)blockIdx.x * (SEL_THREADS * SEL_ITEMS);
+    const unsigned int span = lo_ne_hi ? hi - lo - 1u : 0u;          // lo < k < hi  <=>  (k - lo - 1) < span  (unsigned)
     if (threadIdx.x < 4) blk[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) n_stage = 0;
     __syncthreads();
     const unsigned int lane = threadIdx.x & 31;
     unsigned int n_valid = 0, n_less = 0, n_eqlo = 0, n_eqhi = 0;
-    auto visit = [&](unsigned int k, bool ok) {
-        n_valid += ok;
-        n_less += ok && (k < lo);
-        n_eqlo += ok && (k == lo);
-        n_eqhi += ok && (k == hi) && lo_ne_hi;
-        const bool c = ok && ((k - lo - 1u) < span) && lo_ne_hi;
-        const unsigned int m = __ballot_sync(0xffffffffu, c);
-        if (m) {                                                     // warp-uniform, rare
+    // 16 keys of one thread: count, then stage the candidates with ONE warp scan + one shared atomic per
+    // warp (a warp almost always holds a candidate, so per-element voting would cost more than the counting)
+    auto visit16 = [&](const unsigned int (&keys)[SEL_ITEMS], unsigned int okmask) {
+        unsigned int cmask = 0;
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; ++e) {
+            const unsigned int k = keys[e];
+            const bool ok = (okmask >> e) & 1u;
+            n_valid += ok;
+            n_less += ok && (k < lo);
+            n_eqlo += ok && (k == lo);
+            n_eqhi += ok && (k == hi);
+            if (ok && ((k - lo - 1u) < span)) cmask |= 1u << e;
+        }
+        const unsigned int cnt = __popc(cmask);
+        unsigned int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned int)o) incl += t;
+        }
+        const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {                                                 // warp-uniform
             unsigned int pos = 0;
-            if (lane == 0) pos = atomicAdd(&n_stage, (unsigned int)__popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (c) stage[pos + __popc(m & ((1u << lane) - 1u))] = k;
+            if (lane == 31) pos = atomicAdd(&n_stage, total);
+            pos = __shfl_sync(0xffffffffu, pos, 31) + incl - cnt;
+#pragma unroll
+            for (int e = 0; e < SEL_ITEMS; ++e)
+                if ((cmask >> e) & 1u) stage[pos++] = keys[e];
         }
     };
-    if (base < seg.n) {
-        const bool vec = (seg.kind != DA3S_SEL_RATIO) && aligned16(seg.a) && base + (long long)SEL_THREADS * SEL_ITEMS <= seg.n;
+    auto flush = [&]() {                                             // every thread of the block calls it
+        __syncthreads();
+        const unsigned int total = n_stage;
+        if (threadIdx.x == 0) cand_base = total ? atomicAdd(&w->c_cand, (unsigned long long)total) : 0ull;
+        __syncthreads();
+        if (total) {
+            unsigned int* dst = cand + (size_t)seg_id * cand_cap;
+            bool over = false;
+            for (unsigned int i = threadIdx.x; i < total; i += SEL_THREADS) {
+                const unsigned long long pos = cand_base + i;
+                if ((long long)pos < cand_cap) dst[pos] = stage[i]; else over = true;
+            }
+            if (over) w->overflow = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) n_stage = 0;
+        __syncthreads();
+    };
+    const long long chunk = (long long)SEL_THREADS * SEL_ITEMS;
+    for (int ch = 0; ch < SEL_CHUNKS; ++ch) {                        // block-uniform
+        const long long base = ((long long)blockIdx.x * SEL_CHUNKS + ch) * chunk;
+        if (base >= seg.n) break;
+        const bool vec = (seg.kind != DA3S_SEL_RATIO) && aligned16(seg.a) && base + chunk <= seg.n;
+        unsigned int keys[SEL_ITEMS];
+        unsigned int okmask = 0;
         if (vec) {
             float4 v[SEL_ITEMS / 4];
 #pragma unroll
@@ -214,21 +329,29 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
             const bool all_ok = seg.kind == DA3S_SEL_VALUES;
 #pragma unroll
             for (int it = 0; it < SEL_ITEMS / 4; ++it) {
-                visit(f32_to_key(v[it].x), all_ok || v[it].x > 0.0f);
-                visit(f32_to_key(v[it].y), all_ok || v[it].y > 0.0f);
-                visit(f32_to_key(v[it].z), all_ok || v[it].z > 0.0f);
-                visit(f32_to_key(v[it].w), all_ok || v[it].w > 0.0f);
+                const float f[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    keys[it * 4 + j] = f32_to_key(f[j]);
+                    if (all_ok || f[j] > 0.0f) okmask |= 1u << (it * 4 + j);
+                }
             }
         } else {
-#pragma unroll 4
-            for (int e = 0; e < SEL_ITEMS; ++e) {                    // every lane calls visit (ballot inside)
+#pragma unroll
+            for (int e = 0; e < SEL_ITEMS; ++e) {
                 const long long i = base + ((long long)(e >> 2) * SEL_THREADS + threadIdx.x) * 4 + (e & 3);
-                unsigned int k = 0;
-                const bool ok = i < seg.n && sel_key(seg, i, k);
-                visit(k, ok);
+                keys[e] = 0;
+                if (i < seg.n && sel_key(seg, i, keys[e])) okmask |= 1u << e;
             }
         }
+        visit16(keys, okmask);
+        __syncthreads();
+        const unsigned int staged = n_stage;
+        __syncthreads();                                             // everyone has read it before the next chunk appends
+        if (staged + (unsigned int)chunk > SEL_STAGE) flush();       // block-uniform
     }
+    flush();
+    if (!lo_ne_hi) n_eqhi = 0;
     unsigned int r0 = __reduce_add_sync(0xffffffffu, n_valid), r1 = __reduce_add_sync(0xffffffffu, n_less);
     unsigned int r2 = __reduce_add_sync(0xffffffffu, n_eqlo), r3 = __reduce_add_sync(0xffffffffu, n_eqhi);
     if (lane == 0) {
@@ -238,23 +361,11 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
         if (r3) atomicAdd(&blk[3], (unsigned long long)r3);
     }
     __syncthreads();
-    const unsigned int total = n_stage;
     if (threadIdx.x == 0) {
-        cand_base = total ? atomicAdd(&w->c_cand, (unsigned long long)total) : 0ull;
         if (blk[0]) atomicAdd(&w->c_valid, blk[0]);
         if (blk[1]) atomicAdd(&w->c_less, blk[1]);
         if (blk[2]) atomicAdd(&w->c_eqlo, blk[2]);
         if (blk[3]) atomicAdd(&w->c_eqhi, blk[3]);
-    }
-    __syncthreads();
-    if (total) {
-        unsigned int* dst = cand + (size_t)seg_id * cand_cap;
-        bool over = false;
-        for (unsigned int i = threadIdx.x; i < total; i += SEL_THREADS) {
-            const unsigned long long pos = cand_base + i;
-            if ((long long)pos < cand_cap) dst[pos] = stage[i]; else over = true;
-        }
-        if (over) w->overflow = 1;
     }
     __threadfence();
     __syncthreads();
@@ -290,7 +401,8 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
 }
 
 // ---------------------------------------------------------------------------------
-// C: radix select over SelWork (candidate keys, or the original segment on fallback)
+// C (large segments): multi-block 3-pass MSD radix select (11+11+10 bits) over SelWork with a
+// global histogram per segment; the last block of a segment (ticket) narrows the live ranks.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void hist_add(unsigned int* hist, unsigned int digit, bool pred) {
     // warp-aggregated shared-memory atomic: one atomic per distinct digit in the warp
@@ -435,6 +547,43 @@ select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, unsi
     }
 }
 
+// ---------------------------------------------------------------------------------
+// C: resolve — one block per segment selects the live ranks among the candidates (a few
+// per cent of the segment, L2 resident) or, on fallback, in the whole segment.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+select_resolve_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, da3s_select_out* out) {
+    __shared__ SelScratch sc;
+    const int seg_id = blockIdx.x;
+    const SelWork w = work[seg_id];
+    if (w.done == 1) return;                                         // answered by the sample stage
+    const da3s_select_seg seg = segs[seg_id];
+    const bool empty = (w.done == 2);
+    unsigned int key[2] = {w.resolved_key[0], w.resolved_key[1]};
+    if (!empty) {
+        da3s_select_seg src = seg;
+        src.n = w.n; src.kind = w.kind;
+        if (w.kind != SEL_KIND_KEYS) src.a = (const float*)w.data;
+        const unsigned int* kdata = (const unsigned int*)w.data;
+        // candidates lie strictly inside (lo_key, hi_key): select on k - lo_key, whose leading zero bits are known
+        const bool rel = (w.kind == SEL_KIND_KEYS);
+        const unsigned int base = rel ? w.lo_key : 0u;
+        const int lz = rel ? __clz((w.hi_key - w.lo_key) | 1u) : 0;
+        auto get = [&](long long i, unsigned int& k) -> bool {
+            if (rel) { k = kdata[i] - base; return true; }
+            return sel_key(src, i, k);
+        };
+        if (!w.resolved[0] || !w.resolved[1]) {                       // block-uniform
+            const long long r0 = w.resolved[0] ? w.rank[1] : w.rank[0], r1 = w.resolved[1] ? w.rank[0] : w.rank[1];
+            unsigned int k0, k1;
+            block_select2(w.n, r0, r1, get, sc, lz, k0, k1);
+            if (!w.resolved[0]) key[0] = base + k0;
+            if (!w.resolved[1]) key[1] = base + k1;
+        }
+    }
+    if (threadIdx.x == 0) sel_finish(seg, w.n_valid, w.gamma, empty, key[0], key[1], out + seg_id);
+}
+
 // internal entry used by pair_align.cu as well
 int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, long long max_n,
                      da3s_select_out* out, cudaStream_t st) {
@@ -446,27 +595,33 @@ int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, lon
     long long cand_cap = (max_n / 8 + per_block - 1) / per_block * per_block;
     if (cand_cap < per_block) cand_cap = per_block;
     WS_ALLOC(ctx, SelWork, work, n_segs);
-    WS_ALLOC(ctx, unsigned int, ghist, (size_t)n_segs * 2 * SEL_BINS);
+    const bool big = max_n > SEL_SINGLE_MAX;                     // candidates too many for one block per segment
     WS_ALLOC(ctx, unsigned int, tickets, n_segs);
+    WS_ALLOC(ctx, unsigned int, ghist, big ? (size_t)n_segs * 2 * SEL_BINS : 1);
     WS_ALLOC(ctx, unsigned int, cand, (size_t)n_segs * (size_t)cand_cap);
-    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(ghist, 0, sizeof(unsigned int) * (size_t)n_segs * 2 * SEL_BINS, st));
     DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(tickets, 0, sizeof(unsigned int) * n_segs, st));
+    if (big) DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(ghist, 0, sizeof(unsigned int) * (size_t)n_segs * 2 * SEL_BINS, st));
     select_sample_kernel<<<n_segs, SEL_THREADS, 0, st>>>(segs, work, out);
     DA3S_LAUNCH_CHECK(ctx);
     if (max_n > SEL_SAMPLE) {
-        long long bx = (max_n + per_block - 1) / per_block;
+        long long bx = (max_n + per_block * SEL_CHUNKS - 1) / (per_block * SEL_CHUNKS);
         if (bx > 2147483647LL) return DA3S_EINVAL;
         select_count_kernel<<<dim3((unsigned int)bx, n_segs), SEL_THREADS, 0, st>>>(segs, work, cand, cand_cap, tickets);
         DA3S_LAUNCH_CHECK(ctx);
-        dim3 grid((unsigned int)(cand_cap / per_block), n_segs);
-        select_pass_kernel<0><<<grid, SEL_THREADS, 0, st>>>(segs, work, ghist, tickets, out);
-        DA3S_LAUNCH_CHECK(ctx);
-        select_pass_kernel<1><<<grid, SEL_THREADS, 0, st>>>(segs, work, ghist, tickets, out);
-        DA3S_LAUNCH_CHECK(ctx);
-        select_pass_kernel<2><<<grid, SEL_THREADS, 0, st>>>(segs, work, ghist, tickets, out);
-        DA3S_LAUNCH_CHECK(ctx);
+        if (!big) {
+            select_resolve_kernel<<<n_segs, SEL_THREADS, 0, st>>>(segs, work, out);
+            DA3S_LAUNCH_CHECK(ctx);
+        } else {
+            dim3 grid((unsigned int)(cand_cap / per_block), n_segs);
+            select_pass_kernel<0><<<grid, SEL_THREADS, 0, st>>>(segs, work, ghist, tickets, out);
+            DA3S_LAUNCH_CHECK(ctx);
+            select_pass_kernel<1><<<grid, SEL_THREADS, 0, st>>>(segs, work, ghist, tickets, out);
+            DA3S_LAUNCH_CHECK(ctx);
+            select_pass_kernel<2><<<grid, SEL_THREADS, 0, st>>>(segs, work, ghist, tickets, out);
+            DA3S_LAUNCH_CHECK(ctx);
+        }
     }
-    ctx->ws_top = save_top;     // scratch is free again once the passes are queued (stream order)
+    ctx->ws_top = save_top;     // scratch is free again once the kernels are queued (stream order)
     return DA3S_OK;
 }
 
