@@ -49,6 +49,7 @@ struct PairArgs {
     int* done_count;                        // [max_iterations] pairs finished during pass p (persistent kernel's exit test)
     unsigned long long* work_counter;       // [max_iterations] next (pair, tile) item of pass p
     double huber_delta, tol;
+    float delta_f, delta2_f, W_f;           // float32 copies read straight from the constant bank in the inner loop
     int max_iterations, min_points, precise;
     double* rows;                           // [n_pairs][16]
     da3s_pair_aux* aux;
@@ -357,7 +358,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.app
 // (pair, tile) work items of the pairs that have not converged, the last block of a pair
 // (ticket) solves it, a grid-wide barrier separates iterations, and the kernel ends as soon as
 // no pair is active — no empty launches, no host involvement between iterations.
-template <bool VEC, bool WORLD_UNUSED, bool HUBER>
+template <bool VEC, bool GATE, bool HUBER>
 __global__ void __launch_bounds__(PM_THREADS, 4)
 pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     __shared__ double red[MOM_LEN][PM_THREADS];     // block reduction scratch (25.6 KB)
@@ -412,15 +413,12 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     const float px0 = piv[0], px1 = piv[1], px2 = piv[2], py0 = piv[3], py1 = piv[4], py2 = piv[5];
     const float cuA = fc.cuA, cvA = fc.cvA, ifuA = fc.ifuA, ifvA = fc.ifvA, cuB = fc.cuB, cvB = fc.cvB, ifuB = fc.ifuB, ifvB = fc.ifvB;
     const float thr = fc.thr, ds = fc.ds, eps = a.depth_eps;
-    const bool valid_depth = a.valid_depth, gate_on = fc.gate_on;
+    const bool any_depth = !a.valid_depth, gate_on = GATE && fc.gate_on;
     float B[9], c3[3];
 #pragma unroll
     for (int k = 0; k < 9; ++k) B[k] = fc.Bpf[k];
 #pragma unroll
     for (int k = 0; k < 3; ++k) c3[k] = fc.cpf[k];
-    const float delta = (float)a.huber_delta, delta2 = delta * delta;
-    const float Wf = (float)a.W;
-
     // per-thread float64 accumulators live in the reduction scratch (column = thread): keeps the
     // kernel at <= 128 registers (4 blocks/SM) and the final block reduction reads them in place
 #pragma unroll
@@ -434,28 +432,29 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     // one correspondence, branch-free: a rejected pixel contributes weight 0 on sanitised depths
     auto accumulate = [&](float uf, float vf, float da, float ca, float db, float cb) {
         float dbs = __fmul_rn(db, ds);
-        bool keep = (ca > thr) && (cb > thr);
-        if (valid_depth) keep = keep && (da > eps) && (dbs > eps) && is_finite_f(da) && is_finite_f(dbs);
+        // predicate logic only (no short-circuit): a data-dependent branch here diverges in every warp
+        const bool depth_ok = (da > eps) & (dbs > eps) & is_finite_f(da) & is_finite_f(dbs);
+        bool keep = (ca > thr) & (cb > thr) & (depth_ok | any_depth);
         // sanitise the depths of a rejected pixel (its points become finite zeros): nothing
         // non-finite can reach the sums through 0 * x
         da = keep ? da : 0.0f; dbs = keep ? dbs : 0.0f;
         float x0, x1, y0, y1;
         cam_fast(uf, vf, da, cuA, cvA, ifuA, ifvA, y0, y1);
         cam_fast(uf, vf, dbs, cuB, cvB, ifuB, ifvB, x0, x1);
-        if (gate_on) {                                          // block-uniform
+        if (GATE && gate_on) {                                  // block-uniform
             float x[3] = {x0, x1, dbs}, y[3] = {y0, y1, da}, xs[3], ys[3];
             ransac_points(fc, a.world, x, y, xs, ys);
-            keep = keep && (residual2_f32(fc.gate, xs, ys) < a.gate_thr2);
+            keep = keep & (residual2_f32(fc.gate, xs, ys) < a.gate_thr2);
         }
         const float x2 = dbs, y2 = da;
-        float w = keep ? sqrt_approx(ca * cb) : 0.0f;           // utils/align.py:166 (<= 1 ulp from sqrt_f32)
+        float w = sqrt_approx(keep ? ca * cb : 0.0f);           // utils/align.py:166 (<= 1 ulp from sqrt_f32); sqrt(0) = 0
         if (HUBER) {
             const float r0 = fmaf(B[0], x0, fmaf(B[1], x1, fmaf(B[2], x2, y0 + c3[0])));
             const float r1 = fmaf(B[3], x0, fmaf(B[4], x1, fmaf(B[5], x2, y1 + c3[1])));
             const float r2 = fmaf(B[6], x0, fmaf(B[7], x1, fmaf(B[8], x2, y2 + c3[2])));
             const float rr = fmaf(r0, r0, fmaf(r1, r1, r2 * r2));
-            const float hub = delta * rsqrt_approx(rr);          // Huber: delta / r  (utils/align.py:94-109)
-            w = (rr > delta2) ? w * hub : w;
+            const float hub = a.delta_f * rsqrt_approx(rr);      // Huber: delta / r  (utils/align.py:94-109)
+            w = (rr > a.delta2_f) ? w * hub : w;
             r2sum += keep ? rr : 0.0f;
         }
         const float xc0 = x0 - px0, xc1 = x1 - px1, xc2 = x2 - px2;
@@ -478,9 +477,9 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
         red[MOM_SR][threadIdx.x] += (double)r2sum; r2sum = 0.0f;
     };
     auto group = [&](float uf, float vf, const float4& da, const float4& ca, const float4& db, const float4& cb) {
-        accumulate(uf, vf, da.x, ca.x, db.x, cb.x); uf += 1.0f; if (uf == Wf) { uf = 0.0f; vf += 1.0f; }
-        accumulate(uf, vf, da.y, ca.y, db.y, cb.y); uf += 1.0f; if (uf == Wf) { uf = 0.0f; vf += 1.0f; }
-        accumulate(uf, vf, da.z, ca.z, db.z, cb.z); uf += 1.0f; if (uf == Wf) { uf = 0.0f; vf += 1.0f; }
+        accumulate(uf, vf, da.x, ca.x, db.x, cb.x); uf += 1.0f; if (uf == a.W_f) { uf = 0.0f; vf += 1.0f; }
+        accumulate(uf, vf, da.y, ca.y, db.y, cb.y); uf += 1.0f; if (uf == a.W_f) { uf = 0.0f; vf += 1.0f; }
+        accumulate(uf, vf, da.z, ca.z, db.z, cb.z); uf += 1.0f; if (uf == a.W_f) { uf = 0.0f; vf += 1.0f; }
         accumulate(uf, vf, da.w, ca.w, db.w, cb.w);
     };
 
@@ -496,21 +495,26 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
         const float step_v = (float)step_vi, step_u = (float)(step_px - step_vi * a.W);
         float u0f, v0f;
         { const long long p0 = (g_begin + threadIdx.x) << 2; const int v0 = (int)(p0 / a.W); v0f = (float)v0; u0f = (float)(int)(p0 - (long long)v0 * a.W); }
-        // micro-batch = 2 groups (8 correspondences): all 8 loads issued before any arithmetic
-        for (long long g0 = g_begin + threadIdx.x; g0 < g_end; g0 += 2 * PM_THREADS) {
+        // micro-batch = 2 groups (8 correspondences): all 8 loads issued before any arithmetic;
+        // two micro-batches (16 correspondences) per float64 flush
+        auto batch = [&](long long g0) {
             const long long g1 = g0 + PM_THREADS;
             const bool has1 = g1 < g_end;
             float u1f = u0f + step_u, v1f = v0f + step_v;
-            if (u1f >= Wf) { u1f -= Wf; v1f += 1.0f; }
+            if (u1f >= a.W_f) { u1f -= a.W_f; v1f += 1.0f; }
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 da0 = ldg_stream(dA4 + g0), ca0 = ldg_stream(cA4 + g0), db0 = ldg_stream(dB4 + g0), cb0 = ldg_stream(cB4 + g0);
             float4 da1 = z4, ca1 = z4, db1 = z4, cb1 = z4;
             if (has1) { da1 = ldg_stream(dA4 + g1); ca1 = ldg_stream(cA4 + g1); db1 = ldg_stream(dB4 + g1); cb1 = ldg_stream(cB4 + g1); }
             group(u0f, v0f, da0, ca0, db0, cb0);
             if (has1) group(u1f, v1f, da1, ca1, db1, cb1);
-            flush();
             u0f = u1f + step_u; v0f = v1f + step_v;
-            if (u0f >= Wf) { u0f -= Wf; v0f += 1.0f; }
+            if (u0f >= a.W_f) { u0f -= a.W_f; v0f += 1.0f; }
+        };
+        for (long long g0 = g_begin + threadIdx.x; g0 < g_end; g0 += 4 * PM_THREADS) {
+            batch(g0);
+            if (g0 + 2 * PM_THREADS < g_end) batch(g0 + 2 * PM_THREADS);
+            flush();
         }
     } else {
         int since = 0;
@@ -1071,6 +1075,7 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     a.gate = opts->n_hyp > 0 ? gate : nullptr;
     a.gate_thr2 = (float)((double)opts->ransac_thr * (double)opts->ransac_thr);
     a.partials = partials; a.tickets = tickets; a.n_active = n_active; a.done_count = done_count; a.work_counter = work_counter; a.huber_delta = opts->huber_delta; a.tol = opts->tol;
+    a.delta_f = (float)opts->huber_delta; a.delta2_f = a.delta_f * a.delta_f; a.W_f = (float)W;
     a.max_iterations = opts->max_iterations; a.min_points = opts->min_points; a.precise = opts->precise;
     a.rows = sim3_rows; a.aux = aux;
 
@@ -1108,8 +1113,13 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
         return DA3S_OK;
     }
     // persistent cooperative launch: as many blocks as can be co-resident, never more than there are items
-    const void* fn = opts->huber ? (vec ? (const void*)pair_moments_mixed_kernel<true, true, true> : (const void*)pair_moments_mixed_kernel<false, true, true>)
-                                 : (vec ? (const void*)pair_moments_mixed_kernel<true, true, false> : (const void*)pair_moments_mixed_kernel<false, true, false>);
+    const bool use_gate = a.gate != nullptr;
+    static const void* const table[8] = {
+        (const void*)pair_moments_mixed_kernel<false, false, false>, (const void*)pair_moments_mixed_kernel<false, false, true>,
+        (const void*)pair_moments_mixed_kernel<false, true, false>,  (const void*)pair_moments_mixed_kernel<false, true, true>,
+        (const void*)pair_moments_mixed_kernel<true, false, false>,  (const void*)pair_moments_mixed_kernel<true, false, true>,
+        (const void*)pair_moments_mixed_kernel<true, true, false>,   (const void*)pair_moments_mixed_kernel<true, true, true>};
+    const void* fn = table[(vec ? 4 : 0) | (use_gate ? 2 : 0) | (opts->huber ? 1 : 0)];
     int per_sm = 0;
     DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PM_THREADS, 0));
     if (per_sm < 1) return DA3S_ECUDA;
