@@ -22,7 +22,7 @@ int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, lon
                      da3s_select_out* out, cudaStream_t st);
 
 #define PA_THREADS 256
-#define PA_GROUPS_PER_BLOCK 2048            // 8192 pixels per block; depends on nothing but this constant
+#define PA_GROUPS_PER_BLOCK 4096            // 16384 pixels per block; depends on nothing but this constant
 
 struct PairState {
     double s, R[9], t[3];
@@ -373,22 +373,30 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     cooperative_groups::grid_group grid_g = cooperative_groups::this_grid();
     const int n_tiles_all = a.overlap * a.tiles_per_frame;
     const long long n_items = (long long)a.n_pairs * n_tiles_all;
+  __shared__ float fcm[32];                         // per-item constants, filled by warp 0 (one value per lane)
+  // with few items per block an early request would take work away from idle blocks
+  const bool prefetch = n_items >= 4ll * gridDim.x;
   for (int pass = 0; pass < max_passes; ++pass) {
+   // dynamic work distribution: the block that happens to solve a pair (serial epilogue) simply
+   // takes fewer tiles, instead of delaying a fixed share of them.  The NEXT item is requested
+   // while the current one is processed, so the atomic's round trip is never waited for.
+   __syncthreads();
+   if (threadIdx.x == 0) {
+       const long long it = (long long)atomicAdd(&a.work_counter[pass], 1ull);
+       cur_item = it;
+       pair_done = (it < n_items) ? *((volatile int*)&a.state[(int)(it / n_tiles_all)].done) : 1;
+   }
+   __syncthreads();
    for (;;) {
-    // dynamic work distribution: the block that happens to solve a pair (serial epilogue) simply
-    // takes fewer tiles, instead of delaying a fixed share of them
-    __syncthreads();                                // shared scratch of the previous item is free
-    if (threadIdx.x == 0) {
-        long long it = (long long)atomicAdd(&a.work_counter[pass], 1ull);
-        cur_item = it;
-        pair_done = (it < n_items) ? *((volatile int*)&a.state[(int)(it / n_tiles_all)].done) : 1;
-    }
-    __syncthreads();
     const long long item = cur_item;
+    const bool skip = pair_done != 0;
     if (item >= n_items) break;
+    long long next_item = 0;
+    if (prefetch && threadIdx.x == 0) next_item = (long long)atomicAdd(&a.work_counter[pass], 1ull);
+   do {
     const int pair = (int)(item / n_tiles_all);
     const int item_tile = (int)(item - (long long)pair * n_tiles_all);
-    if (pair_done) continue;                        // block-uniform: converged pairs cost nothing
+    if (skip) continue;                             // block-uniform: converged pairs cost nothing
     const da3s_pair pr = a.pairs[pair];
     const int frame = item_tile / a.tiles_per_frame;
     const int tile = item_tile - frame * a.tiles_per_frame;
@@ -398,27 +406,48 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     const long long p_begin = (long long)tile * PA_GROUPS_PER_BLOCK * 4;
     long long p_end = p_begin + (long long)PA_GROUPS_PER_BLOCK * 4;
     if (p_end > a.P) p_end = a.P;
-    if (threadIdx.x == 0) {
-        load_frame_const(fc, pr, frame, a, pair);
-        // pivot = the correspondence at the frame's centre pixel: the same for every tile of the
-        // frame, so per-tile partials add directly and are un-pivoted once per frame by the last block
+    if (threadIdx.x < 32) {
+        // item constants, one independent load per lane (a single round trip instead of a serial prologue)
+        const int t = threadIdx.x;
         const int vc = a.H / 2, uc = a.W / 2;
         const long long pc = (long long)vc * a.W + uc;
-        float x[3], y[3], dbs;
-        corr_points(fc, false, 0.0f, uc, vc, dA[pc], 1.0f, dB[pc], 1.0f, x, y, dbs);
-        for (int k = 0; k < 3; ++k) { piv[k] = is_finite_f(x[k]) ? x[k] : 0.0f; piv[3 + k] = is_finite_f(y[k]) ? y[k] : 0.0f; }
+        const double* e = a.eff + ((size_t)pair * a.overlap + frame) * EFF_LEN;     // written in the previous pass: read through L2
+        float val = 0.0f;
+        if (t < 8) val = reinterpret_cast<const float*>(t < 4 ? &pr.cam_a[frame] : &pr.cam_b[frame])[2 + (t & 3)];   // cu cv 1/fu 1/fv
+        else if (t < 17) val = (float)__ldcg(e + 21 + (t - 8));
+        else if (t < 20) val = (float)__ldcg(e + 30 + (t - 17));
+        else if (t == 20) val = a.thr[pair];
+        else if (t == 21) val = a.dscale ? a.dscale[pair] : 1.0f;
+        else if (t == 22) val = dA[pc];
+        else if (t == 23) val = dB[pc];
+        else if (t == 24) val = (GATE && a.gate && *((volatile int*)&a.state[pair].gate_on)) ? 1.0f : 0.0f;
+        fcm[t] = val;
+        __syncwarp();
+        // pivot = the correspondence at the frame's centre pixel (corr_points arithmetic): the same for every tile of
+        // the frame, so per-tile partials add directly and are un-pivoted once per frame by the last block
+        if (t < 6) {
+            const bool is_x = t < 3;
+            const float d = is_x ? __fmul_rn(fcm[23], fcm[21]) : fcm[22];
+            const float* in = is_x ? &fcm[4] : &fcm[0];
+            float p0, p1;
+            cam_fast((float)uc, (float)vc, d, in[0], in[1], in[2], in[3], p0, p1);
+            const float v = (t % 3 == 0) ? p0 : ((t % 3 == 1) ? p1 : d);
+            piv[t] = is_finite_f(v) ? v : 0.0f;
+        }
+    } else if (GATE && threadIdx.x == 32) {
+        load_frame_const(fc, pr, frame, a, pair);    // float32 c2w + winning hypothesis for the RANSAC gate
     }
     __syncthreads();
     // block-uniform constants into registers
     const float px0 = piv[0], px1 = piv[1], px2 = piv[2], py0 = piv[3], py1 = piv[4], py2 = piv[5];
-    const float cuA = fc.cuA, cvA = fc.cvA, ifuA = fc.ifuA, ifvA = fc.ifvA, cuB = fc.cuB, cvB = fc.cvB, ifuB = fc.ifuB, ifvB = fc.ifvB;
-    const float thr = fc.thr, ds = fc.ds, eps = a.depth_eps;
-    const bool any_depth = !a.valid_depth, gate_on = GATE && fc.gate_on;
+    const float cuA = fcm[0], cvA = fcm[1], ifuA = fcm[2], ifvA = fcm[3], cuB = fcm[4], cvB = fcm[5], ifuB = fcm[6], ifvB = fcm[7];
+    const float thr = fcm[20], ds = fcm[21], eps = a.depth_eps;
+    const bool any_depth = !a.valid_depth, gate_on = GATE && fcm[24] != 0.0f;
     float B[9], c3[3];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) B[k] = fc.Bpf[k];
+    for (int k = 0; k < 9; ++k) B[k] = fcm[8 + k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) c3[k] = fc.cpf[k];
+    for (int k = 0; k < 3; ++k) c3[k] = fcm[17 + k];
     // per-thread float64 accumulators live in the reduction scratch (column = thread): keeps the
     // kernel at <= 128 registers (4 blocks/SM) and the final block reduction reads them in place
 #pragma unroll
@@ -495,25 +524,25 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
         const float step_v = (float)step_vi, step_u = (float)(step_px - step_vi * a.W);
         float u0f, v0f;
         { const long long p0 = (g_begin + threadIdx.x) << 2; const int v0 = (int)(p0 / a.W); v0f = (float)v0; u0f = (float)(int)(p0 - (long long)v0 * a.W); }
-        // micro-batch = 2 groups (8 correspondences): all 8 loads issued before any arithmetic;
-        // two micro-batches (16 correspondences) per float64 flush
-        auto batch = [&](long long g0) {
-            const long long g1 = g0 + PM_THREADS;
-            const bool has1 = g1 < g_end;
-            float u1f = u0f + step_u, v1f = v0f + step_v;
-            if (u1f >= a.W_f) { u1f -= a.W_f; v1f += 1.0f; }
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 da0 = ldg_stream(dA4 + g0), ca0 = ldg_stream(cA4 + g0), db0 = ldg_stream(dB4 + g0), cb0 = ldg_stream(cB4 + g0);
-            float4 da1 = z4, ca1 = z4, db1 = z4, cb1 = z4;
-            if (has1) { da1 = ldg_stream(dA4 + g1); ca1 = ldg_stream(cA4 + g1); db1 = ldg_stream(dB4 + g1); cb1 = ldg_stream(cB4 + g1); }
-            group(u0f, v0f, da0, ca0, db0, cb0);
-            if (has1) group(u1f, v1f, da1, ca1, db1, cb1);
-            u0f = u1f + step_u; v0f = v1f + step_v;
-            if (u0f >= a.W_f) { u0f -= a.W_f; v0f += 1.0f; }
-        };
-        for (long long g0 = g_begin + threadIdx.x; g0 < g_end; g0 += 4 * PM_THREADS) {
-            batch(g0);
-            if (g0 + 2 * PM_THREADS < g_end) batch(g0 + 2 * PM_THREADS);
+        // software pipeline: the 4 loads (64 B) of the thread's NEXT group are in flight while the current
+        // group (4 correspondences) is accumulated; float64 flush every 4 groups (16 correspondences)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 nda = z4, nca = z4, ndb = z4, ncb = z4;
+        long long g = g_begin + threadIdx.x;
+        if (g < g_end) { nda = ldg_stream(dA4 + g); nca = ldg_stream(cA4 + g); ndb = ldg_stream(dB4 + g); ncb = ldg_stream(cB4 + g); }
+        while (g < g_end) {                                          // 4 groups per trip
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (g < g_end) {
+                    const float4 da = nda, ca = nca, db = ndb, cb = ncb;
+                    const long long gn = g + PM_THREADS;
+                    if (gn < g_end) { nda = ldg_stream(dA4 + gn); nca = ldg_stream(cA4 + gn); ndb = ldg_stream(dB4 + gn); ncb = ldg_stream(cB4 + gn); }
+                    group(u0f, v0f, da, ca, db, cb);
+                    u0f += step_u; v0f += step_v;
+                    if (u0f >= a.W_f) { u0f -= a.W_f; v0f += 1.0f; }
+                    g = gn;
+                }
+            }
             flush();
         }
     } else {
@@ -534,12 +563,16 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     if (threadIdx.x < MOM_LEN * (PM_THREADS / 32)) {               // 100 threads: (moment k, 32-thread slice)
         const int k = threadIdx.x / (PM_THREADS / 32), sl = threadIdx.x % (PM_THREADS / 32);
         const double* src = &red[k][sl * 32];
-        double v = 0.0;
-        // rotated start index per lane avoids bank conflicts; each thread's summation order is fixed
-        for (int j = 0; j < 32; ++j) {
-            const double p = src[(j + lane) & 31];
-            v = (k == MOM_WMAX) ? fmax(v, p) : v + p;
+        // rotated start index per lane avoids bank conflicts; four independent chains, fixed order
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        const bool is_max = (k == MOM_WMAX);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const double p0 = src[(j + lane) & 31], p1 = src[(j + 1 + lane) & 31], p2 = src[(j + 2 + lane) & 31], p3 = src[(j + 3 + lane) & 31];
+            v0 = is_max ? fmax(v0, p0) : v0 + p0; v1 = is_max ? fmax(v1, p1) : v1 + p1;
+            v2 = is_max ? fmax(v2, p2) : v2 + p2; v3 = is_max ? fmax(v3, p3) : v3 + p3;
         }
+        const double v = is_max ? fmax(fmax(v0, v1), fmax(v2, v3)) : (v0 + v1) + (v2 + v3);
         part[k][sl] = v;
     }
     __syncthreads();
@@ -604,6 +637,14 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
         solve_pair(a, pair, mm, pass);
         a.tickets[pair] = 0;
     }
+   } while (0);
+    __syncthreads();                                // everyone is done with cur_item and the shared scratch
+    if (threadIdx.x == 0) {
+        if (!prefetch) next_item = (long long)atomicAdd(&a.work_counter[pass], 1ull);
+        cur_item = next_item;
+        pair_done = (next_item < n_items) ? *((volatile int*)&a.state[(int)(next_item / n_tiles_all)].done) : 1;
+    }
+    __syncthreads();
    }   // items
    grid_g.sync();                                   // every solve of this pass is visible everywhere
    // pairs still active = active at start - finished in passes <= this one.  Only counters of
