@@ -525,25 +525,37 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
         float u0f, v0f;
         { const long long p0 = (g_begin + threadIdx.x) << 2; const int v0 = (int)(p0 / a.W); v0f = (float)v0; u0f = (float)(int)(p0 - (long long)v0 * a.W); }
         // software pipeline: the 4 loads (64 B) of the thread's NEXT group are in flight while the current
-        // group (4 correspondences) is accumulated; float64 flush every 4 groups (16 correspondences)
+        // group (4 correspondences) is accumulated; two register buffers alternate (no copies), running
+        // pointers (no per-group address arithmetic); float64 flush every 4 groups (16 correspondences)
+        const long long g_first = g_begin + threadIdx.x;
+        int left = g_first < g_end ? (int)((g_end - g_first + PM_THREADS - 1) / PM_THREADS) : 0;
+        const float4* pdA = dA4 + g_first; const float4* pcA = cA4 + g_first;
+        const float4* pdB = dB4 + g_first; const float4* pcB = cB4 + g_first;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 nda = z4, nca = z4, ndb = z4, ncb = z4;
-        long long g = g_begin + threadIdx.x;
-        if (g < g_end) { nda = ldg_stream(dA4 + g); nca = ldg_stream(cA4 + g); ndb = ldg_stream(dB4 + g); ncb = ldg_stream(cB4 + g); }
-        while (g < g_end) {                                          // 4 groups per trip
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (g < g_end) {
-                    const float4 da = nda, ca = nca, db = ndb, cb = ncb;
-                    const long long gn = g + PM_THREADS;
-                    if (gn < g_end) { nda = ldg_stream(dA4 + gn); nca = ldg_stream(cA4 + gn); ndb = ldg_stream(dB4 + gn); ncb = ldg_stream(cB4 + gn); }
-                    group(u0f, v0f, da, ca, db, cb);
-                    u0f += step_u; v0f += step_v;
-                    if (u0f >= a.W_f) { u0f -= a.W_f; v0f += 1.0f; }
-                    g = gn;
-                }
+        float4 a0 = z4, a1 = z4, a2 = z4, a3 = z4, b0 = z4, b1 = z4, b2 = z4, b3 = z4;
+        if (left > 0) { a0 = ldg_stream(pdA); a1 = ldg_stream(pcA); a2 = ldg_stream(pdB); a3 = ldg_stream(pcB); }
+        auto advance = [&]() {
+            u0f += step_u; v0f += step_v;
+            if (u0f >= a.W_f) { u0f -= a.W_f; v0f += 1.0f; }
+        };
+        while (left > 0) {                                           // 4 groups per trip
+            if (left > 1) { b0 = ldg_stream(pdA + PM_THREADS); b1 = ldg_stream(pcA + PM_THREADS); b2 = ldg_stream(pdB + PM_THREADS); b3 = ldg_stream(pcB + PM_THREADS); }
+            group(u0f, v0f, a0, a1, a2, a3); advance();
+            if (left > 1) {
+                if (left > 2) { a0 = ldg_stream(pdA + 2 * PM_THREADS); a1 = ldg_stream(pcA + 2 * PM_THREADS); a2 = ldg_stream(pdB + 2 * PM_THREADS); a3 = ldg_stream(pcB + 2 * PM_THREADS); }
+                group(u0f, v0f, b0, b1, b2, b3); advance();
+            }
+            if (left > 2) {
+                if (left > 3) { b0 = ldg_stream(pdA + 3 * PM_THREADS); b1 = ldg_stream(pcA + 3 * PM_THREADS); b2 = ldg_stream(pdB + 3 * PM_THREADS); b3 = ldg_stream(pcB + 3 * PM_THREADS); }
+                group(u0f, v0f, a0, a1, a2, a3); advance();
+            }
+            if (left > 3) {
+                if (left > 4) { a0 = ldg_stream(pdA + 4 * PM_THREADS); a1 = ldg_stream(pcA + 4 * PM_THREADS); a2 = ldg_stream(pdB + 4 * PM_THREADS); a3 = ldg_stream(pcB + 4 * PM_THREADS); }
+                group(u0f, v0f, b0, b1, b2, b3); advance();
             }
             flush();
+            pdA += 4 * PM_THREADS; pcA += 4 * PM_THREADS; pdB += 4 * PM_THREADS; pcB += 4 * PM_THREADS;
+            left -= 4;
         }
     } else {
         int since = 0;
