@@ -1,9 +1,12 @@
 // voxel.cu — K6: voxel-grid downsample on a GPU hash grid (oracle/SPEC.md section 5).
 //
 // key    = floor(f64(p) / f64(voxel)) per axis, 21 bits per axis, bias 2^20
-// table  = keys[slots] u64, DENSE (compaction scans 8 B per slot instead of a 64-B DRAM atom)
-//        + acc[slots] 64-byte records: sum_qx | sum_qy | sum_qz | (count,sum_r) | (sum_g,sum_b) | pad
+// table  = rec[slots], one 64-byte record (= one DRAM atom) per slot:
+//          key | sum_qx | sum_qy | sum_qz | (count,sum_r) | (sum_g,sum_b) | pad | pad
 //          sum_q = sum of llrint(frac * 2^32), frac = p/voxel - floor(p/voxel)  (exact int64)
+//          The key lives INSIDE the record: probe, claim and the five additions of a point touch one
+//          DRAM atom (a separate key array cost a second random atom per point, and the insert stage
+//          is bound by exactly that random traffic: profiles/r1_*).
 // Integer accumulation makes the result independent of insertion order (bit-identical
 // run to run and across GPUs), which floating-point atomics would not be.
 //
@@ -27,74 +30,164 @@ __device__ __forceinline__ unsigned long long vox_hash(unsigned long long k) {
     return k;
 }
 
-__global__ void voxel_clear_kernel(unsigned long long* keys, unsigned long long* acc, long long slots) {
+__global__ void voxel_clear_kernel(unsigned long long* acc, long long slots) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one u64 word per thread
     const long long words = slots * (VOX_REC + 1);
+    unsigned long long* keys = acc + (size_t)slots * VOX_REC;
     for (; i < words; i += (long long)gridDim.x * blockDim.x) {
         if (i < slots) keys[i] = VOX_EMPTY; else acc[i - slots] = 0ull;
     }
 }
 
-__global__ void __launch_bounds__(256)
-voxel_insert_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ mask,
-                    long long n, float voxel, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ acc,
-                    long long slots, unsigned long long* __restrict__ counters /* [0]=voxels (set by finish) [1]=dropped */) {
-    const double vd = (double)voxel;
+// One launch inserts any number of clouds (a job table) — e.g. every submap of a sequence.  Each
+// warp streams 128 mask bytes at a time (one 4-byte load per lane), queues the indices of the
+// points that pass in shared memory, and runs the expensive part — coordinates, float64
+// quantisation, hash probe, atomics — only on full batches of 32 queued points: with a 35 %
+// confidence keep rate that is ~3x fewer trips through the dependent load chain
+// (mask -> xyz -> key -> record) that bounds this kernel.
+#define VI_THREADS 256
+#define VI_QUEUE 256                        // per-warp ring of point indices (>= 31 left over + 128 new)
+
+__device__ __forceinline__ void voxel_insert_point(bool active, long long i, const da3s_voxel_job& job, double vd,
+                                                   unsigned long long* __restrict__ acc,
+                                                   long long slots, unsigned long long* __restrict__ counters) {
     const unsigned int lane = threadIdx.x & 31;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        if (mask && mask[i] == 0) continue;                    // masked points never touch their coordinates
-        const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
-        if (!(is_finite_f(px) && is_finite_f(py) && is_finite_f(pz))) continue;
-        double qx = __ddiv_rn((double)px, vd), qy = __ddiv_rn((double)py, vd), qz = __ddiv_rn((double)pz, vd);
-        double kx = floor(qx), ky = floor(qy), kz = floor(qz);
-        if (!((fabs(kx) < (double)VOX_BIAS) && (fabs(ky) < (double)VOX_BIAS) && (fabs(kz) < (double)VOX_BIAS))) continue;
-        unsigned long long key = ((unsigned long long)((long long)kx + VOX_BIAS) << 42) |
-                                 ((unsigned long long)((long long)ky + VOX_BIAS) << 21) |
-                                 (unsigned long long)((long long)kz + VOX_BIAS);
-        unsigned long long sx = (unsigned long long)__double2ll_rn((qx - kx) * 4294967296.0);
-        unsigned long long sy = (unsigned long long)__double2ll_rn((qy - ky) * 4294967296.0);
-        unsigned long long sz = (unsigned long long)__double2ll_rn((qz - kz) * 4294967296.0);
-        unsigned long long cr = 1ull << 32, gb = 0ull;
-        if (rgb) {
-            cr |= (unsigned long long)rgb[3 * i];
-            gb = ((unsigned long long)rgb[3 * i + 1] << 32) | (unsigned long long)rgb[3 * i + 2];
-        }
-        // combine the lanes of this warp that hit the same voxel; a lane alone in its voxel (the
-        // common case) skips the exchange entirely
-        const unsigned int act = __activemask();
-        const unsigned int peers = __match_any_sync(act, key);
-        const unsigned int leader = __ffs(peers) - 1;
-        if (peers != (1u << lane)) {
-            unsigned int rest = peers & ~(1u << leader);            // identical for every lane of the group
-            while (rest) {
-                const int src = __ffs(rest) - 1;
-                rest &= rest - 1;
-                const unsigned long long ax = __shfl_sync(peers, sx, src), ay = __shfl_sync(peers, sy, src);
-                const unsigned long long az = __shfl_sync(peers, sz, src), ac = __shfl_sync(peers, cr, src);
-                const unsigned long long ag = __shfl_sync(peers, gb, src);
-                if (lane == leader) { sx += ax; sy += ay; sz += az; cr += ac; gb += ag; }
+    unsigned long long key = 0, sx = 0, sy = 0, sz = 0, cr = 1ull << 32, gb = 0ull;
+    if (active) {
+        const float px = job.xyz[3 * i], py = job.xyz[3 * i + 1], pz = job.xyz[3 * i + 2];
+        active = is_finite_f(px) && is_finite_f(py) && is_finite_f(pz);
+        const double qx = __ddiv_rn((double)px, vd), qy = __ddiv_rn((double)py, vd), qz = __ddiv_rn((double)pz, vd);
+        const double kx = floor(qx), ky = floor(qy), kz = floor(qz);
+        active = active && (fabs(kx) < (double)VOX_BIAS) && (fabs(ky) < (double)VOX_BIAS) && (fabs(kz) < (double)VOX_BIAS);
+        if (active) {
+            key = ((unsigned long long)((long long)kx + VOX_BIAS) << 42) | ((unsigned long long)((long long)ky + VOX_BIAS) << 21) |
+                  (unsigned long long)((long long)kz + VOX_BIAS);
+            sx = (unsigned long long)__double2ll_rn((qx - kx) * 4294967296.0);
+            sy = (unsigned long long)__double2ll_rn((qy - ky) * 4294967296.0);
+            sz = (unsigned long long)__double2ll_rn((qz - kz) * 4294967296.0);
+            if (job.rgb) {
+                cr |= (unsigned long long)job.rgb[3 * i];
+                gb = ((unsigned long long)job.rgb[3 * i + 1] << 32) | (unsigned long long)job.rgb[3 * i + 2];
             }
-            if (lane != leader) continue;
         }
-        unsigned long long slot = vox_hash(key) & (unsigned long long)(slots - 1);
-        bool placed = false;
-        for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
-            unsigned long long cur = *((volatile unsigned long long*)(keys + slot));
-            if (cur == VOX_EMPTY) {
-                cur = atomicCAS(keys + slot, VOX_EMPTY, key);
-                if (cur == VOX_EMPTY) cur = key;
-            }
-            if (cur == key) {
-                unsigned long long* rec = acc + slot * VOX_REC;
-                atomicAdd(rec + 0, sx); atomicAdd(rec + 1, sy); atomicAdd(rec + 2, sz);
-                atomicAdd(rec + 3, cr);
-                if (rgb) atomicAdd(rec + 4, gb);
-                placed = true;
-                break;
-            }
-            slot = (slot + 1) & (unsigned long long)(slots - 1);
+    }
+    const unsigned int act = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    // combine the lanes of this warp that hit the same voxel; a lane alone in its voxel skips the exchange
+    const unsigned int peers = __match_any_sync(act, key);
+    const unsigned int leader = __ffs(peers) - 1;
+    if (peers != (1u << lane)) {
+        unsigned int rest = peers & ~(1u << leader);                // identical for every lane of the group
+        while (rest) {
+            const int src = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const unsigned long long ax = __shfl_sync(peers, sx, src), ay = __shfl_sync(peers, sy, src);
+            const unsigned long long az = __shfl_sync(peers, sz, src), ac = __shfl_sync(peers, cr, src);
+            const unsigned long long ag = __shfl_sync(peers, gb, src);
+            if (lane == leader) { sx += ax; sy += ay; sz += az; cr += ac; gb += ag; }
         }
-        if (!placed) atomicAdd(&counters[1], cr >> 32);
+        if (lane != leader) return;
+    }
+    unsigned long long slot = vox_hash(key) & (unsigned long long)(slots - 1);
+    for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
+        unsigned long long* rec = acc + slot * VOX_REC;
+        unsigned long long* kp = acc + (size_t)slots * VOX_REC + slot;
+        unsigned long long cur = *((volatile unsigned long long*)kp);
+        if (cur == VOX_EMPTY) {
+            cur = atomicCAS(kp, VOX_EMPTY, key);
+            if (cur == VOX_EMPTY) cur = key;
+        }
+        if (cur == key) {
+            atomicAdd(rec + 1, sx); atomicAdd(rec + 2, sy); atomicAdd(rec + 3, sz);
+            atomicAdd(rec + 4, cr);
+            if (job.rgb) atomicAdd(rec + 5, gb);
+            return;
+        }
+        slot = (slot + 1) & (unsigned long long)(slots - 1);
+    }
+    atomicAdd(&counters[1], cr >> 32);                              // table full: reported by finish
+}
+
+// Work unit of a warp = a TILE of 128 points: 128 consecutive points of an unstructured cloud, or — when
+// the cloud is an image sequence of row length `width` — 8 rows x 16 pixels.  The 2-D tile matters:
+// a voxel's footprint is a patch of pixels, and the in-warp combination (match.any) only sees the
+// batch of 32 queued points; with row-major tiles it merged ~2 points per voxel, with patches several
+// times more, and every merged point saves one probe and five L2 atomics (what bounds this stage:
+// ablation in profiles/r1_voxel_insert_ablation.md).
+// Blocks sweep the tiles of all jobs in order (block b takes block-chunks b, b + G, ...).
+#define VI_TILES_PER_WARP 2
+#define VI_TILES_PER_BLOCK (VI_TILES_PER_WARP * VI_THREADS / 32)
+
+__global__ void __launch_bounds__(VI_THREADS)
+voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job single, int n_jobs, long long chunks_per_job,
+                    int width, float voxel, unsigned long long* __restrict__ acc,
+                    long long slots, unsigned long long* __restrict__ counters /* [0]=voxels (set by finish) [1]=dropped */) {
+    __shared__ long long queue[VI_THREADS / 32][VI_QUEUE];
+    const double vd = (double)voxel;
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long* q = queue[warp];
+    const long long total = chunks_per_job * n_jobs;
+    const int tiles_per_band = width > 0 ? (width + 15) / 16 : 1;
+    for (long long c = blockIdx.x; c < total; c += gridDim.x) {
+        const long long j = c / chunks_per_job;
+        const da3s_voxel_job job = jobs ? jobs[j] : single;
+        const long long n = job.n;
+        const long long t_begin = (c - j * chunks_per_job) * VI_TILES_PER_BLOCK + (long long)warp * VI_TILES_PER_WARP;
+        unsigned int head = 0, count = 0;                           // warp-uniform ring state
+#pragma unroll 1
+        for (int tt = 0; tt < VI_TILES_PER_WARP; ++tt) {
+            const long long t = t_begin + tt;
+            // the 4 consecutive points of this lane: [i0, i0 + lim)
+            long long i0; int lim = 4;
+            if (width > 0) {
+                const long long band = t / tiles_per_band;
+                const int tx = (int)(t - band * tiles_per_band);
+                const int col = tx * 16 + (int)(lane & 3) * 4;
+                i0 = (band * 8 + (lane >> 2)) * (long long)width + col;
+                lim = width - col;                                  // the last tile of a band is narrower
+            } else {
+                i0 = t * 128 + (long long)lane * 4;
+            }
+            if (lim > 4) lim = 4;
+            if (n - i0 < lim) lim = (int)(n - i0 < 0 ? 0 : n - i0);
+            if (__ballot_sync(0xffffffffu, lim > 0) == 0) break;    // past the end of this job (warp-uniform)
+            unsigned int flags = 0;
+            if (lim > 0) {
+                if (!job.mask) flags = (1u << lim) - 1u;
+                else if (lim == 4 && ((reinterpret_cast<uintptr_t>(job.mask + i0) & 3) == 0)) {
+                    const uchar4 m = *reinterpret_cast<const uchar4*>(job.mask + i0);
+                    flags = (m.x ? 1u : 0u) | (m.y ? 2u : 0u) | (m.z ? 4u : 0u) | (m.w ? 8u : 0u);
+                } else {
+                    for (int b = 0; b < lim; ++b) flags |= job.mask[i0 + b] ? (1u << b) : 0u;
+                }
+            }
+            const unsigned int cnt = __popc(flags);
+            unsigned int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (unsigned int)o) incl += v;
+            }
+            const unsigned int total_new = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned int pos = head + count + incl - cnt;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if ((flags >> b) & 1u) { q[pos & (VI_QUEUE - 1)] = i0 + b; ++pos; }
+            count += total_new;
+            __syncwarp();
+            while (count >= 32) {
+                const long long i = q[(head + lane) & (VI_QUEUE - 1)];
+                voxel_insert_point(true, i, job, vd, acc, slots, counters);
+                __syncwarp();
+                head += 32; count -= 32;
+            }
+        }
+        if (count) {                                                // the queue never crosses a job boundary
+            const bool active = lane < count;
+            const long long i = active ? q[(head + lane) & (VI_QUEUE - 1)] : 0;
+            voxel_insert_point(active, i, job, vd, acc, slots, counters);
+            __syncwarp();
+        }
     }
 }
 
@@ -113,19 +206,16 @@ voxel_insert_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ r
 #define VC_PER_BLOCK (VC_PER_WARP * VC_THREADS / 32)
 
 __global__ void __launch_bounds__(VC_THREADS)
-voxel_count_kernel(const unsigned long long* __restrict__ keys, long long slots, unsigned int* __restrict__ warp_counts) {
+voxel_count_kernel(const unsigned long long* __restrict__ acc, long long slots, unsigned int* __restrict__ warp_counts) {
     const unsigned int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
     const long long base = wid * VC_PER_WARP;
     if (base >= slots) return;
     unsigned int c = 0;
 #pragma unroll
-    for (int j = 0; j < VC_ROUNDS / 2; ++j) {
-        const long long s = base + ((long long)j * 32 + lane) * 2;       // two keys = one 16-byte load
-        if (s + 1 < slots) {
-            const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(keys + s);
-            c += (k.x != VOX_EMPTY) + (k.y != VOX_EMPTY);
-        } else if (s < slots) c += keys[s] != VOX_EMPTY;
+    for (int j = 0; j < VC_ROUNDS; ++j) {                       // 16 independent loads per lane, one key per record
+        const long long s = base + (long long)j * 32 + lane;
+        if (s < slots) c += __ldcs(acc + (size_t)slots * VOX_REC + s) != VOX_EMPTY;
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) warp_counts[wid] = c;
@@ -161,7 +251,7 @@ voxel_scan_kernel(const unsigned int* __restrict__ counts, int n, unsigned long 
 }
 
 __global__ void __launch_bounds__(VC_THREADS)
-voxel_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __restrict__ acc, long long slots,
+voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
                   const unsigned long long* __restrict__ warp_offsets, float voxel, long long max_voxels,
                   float* __restrict__ xyz_out, uint8_t* __restrict__ rgb_out, int32_t* __restrict__ count_out,
                   long long* __restrict__ key_out) {
@@ -174,13 +264,13 @@ voxel_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __r
 #pragma unroll
     for (int j = 0; j < VC_ROUNDS; ++j) {                       // 16 independent coalesced loads per lane
         const long long s = base + (long long)j * 32 + lane;
-        key[j] = s < slots ? keys[s] : VOX_EMPTY;
+        key[j] = s < slots ? acc[(size_t)slots * VOX_REC + s] : VOX_EMPTY;
     }
     unsigned long long out = warp_offsets[wid];
 #pragma unroll
     for (int j0 = 0; j0 < VC_ROUNDS; j0 += 4) {                 // 4 rounds at a time: their record loads overlap
-        ulonglong2 ra[4], rb[4];
-        unsigned long long rg[4], oo[4];
+        ulonglong2 ra[4], rb[4];                                // (sum_y, sum_z), ((n, sum_r), (sum_g, sum_b))
+        unsigned long long rx[4], oo[4];
         bool occ[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -192,9 +282,9 @@ voxel_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __r
             if (occ[q]) {
                 const long long s = base + (long long)j * 32 + lane;
                 unsigned long long* rec = acc + (size_t)s * VOX_REC;
-                ra[q] = *reinterpret_cast<const ulonglong2*>(rec);          // sum_x, sum_y
-                rb[q] = *reinterpret_cast<const ulonglong2*>(rec + 2);      // sum_z, (n, sum_r)
-                rg[q] = rec[4];                                              // (sum_g, sum_b)
+                rx[q] = rec[1];
+                ra[q] = *reinterpret_cast<const ulonglong2*>(rec + 2);
+                rb[q] = *reinterpret_cast<const ulonglong2*>(rec + 4);
             }
         }
 #pragma unroll
@@ -203,14 +293,14 @@ voxel_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __r
             const int j = j0 + q;
             const long long s = base + (long long)j * 32 + lane;
             unsigned long long* rec = acc + (size_t)s * VOX_REC;
-            *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2(0ull, 0ull);
+            *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2(VOX_EMPTY, 0ull);
+            acc[(size_t)slots * VOX_REC + s] = VOX_EMPTY;
             *reinterpret_cast<ulonglong2*>(rec + 2) = make_ulonglong2(0ull, 0ull);
-            rec[4] = 0ull;
-            keys[s] = VOX_EMPTY;
+            *reinterpret_cast<ulonglong2*>(rec + 4) = make_ulonglong2(0ull, 0ull);
             if ((long long)oo[q] >= max_voxels) continue;
-            const unsigned long long k64 = key[j], cr = rb[q].y, gb = rg[q], cnt = cr >> 32, o = oo[q];
+            const unsigned long long k64 = key[j], cr = rb[q].x, gb = rb[q].y, cnt = cr >> 32, o = oo[q];
             const double inv = 1.0 / 4294967296.0;
-            const unsigned long long sq[3] = {ra[q].x, ra[q].y, rb[q].x};
+            const unsigned long long sq[3] = {rx[q], ra[q].x, ra[q].y};
             const double k[3] = {(double)((long long)((k64 >> 42) & 0x1FFFFF) - VOX_BIAS),
                                  (double)((long long)((k64 >> 21) & 0x1FFFFF) - VOX_BIAS),
                                  (double)((long long)(k64 & 0x1FFFFF) - VOX_BIAS)};
@@ -239,7 +329,7 @@ voxel_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __r
 extern "C" int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots, void* stream) {
     if (!ctx || table_slots < 1024 || (table_slots & (table_slots - 1)) || table_slots > (1ll << 31)) return DA3S_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    // layout of the reserved tail: keys [slots] u64 | acc [slots][8] u64 | counters [4] u64 (256 B) |
+    // layout of the reserved tail: records [slots][8] u64 | counters [4] u64 (256 B) |
     // warp counts [slots/512] u32 | warp offsets [slots/512] u64
     const long long n_cblocks = (table_slots + VC_PER_WARP - 1) / VC_PER_WARP;
     size_t bytes = (size_t)table_slots * (VOX_REC + 1) * 8 + 256 + (size_t)n_cblocks * 16 + 512;
@@ -250,14 +340,14 @@ extern "C" int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots, void* stre
         ws_reset(ctx);
         size_t start = (ctx->ws_bytes - bytes) & ~(size_t)255;
         ctx->vox_bytes = ctx->ws_bytes - start;               // stays reserved until a different size is requested
-        ctx->vox_keys = (unsigned long long*)(ctx->ws + start);
-        ctx->vox_acc = ctx->vox_keys + (size_t)table_slots;
-        ctx->vox_dropped = ctx->vox_acc + (size_t)table_slots * VOX_REC;       // counters[4]
+        ctx->vox_acc = (unsigned long long*)(ctx->ws + start);
+        ctx->vox_keys = ctx->vox_acc;                          // the key is word 0 of each record
+        ctx->vox_dropped = ctx->vox_acc + (size_t)table_slots * (VOX_REC + 1);       // counters[4]
         ctx->vox_occ = (unsigned int*)(ctx->vox_dropped + 32);                 // block counts, then block offsets
         ctx->vox_slots = table_slots;
         long long words = table_slots * (VOX_REC + 1);
         long long want = (words + 255) / 256, cap = (long long)ctx->sm_count * 32;
-        voxel_clear_kernel<<<(int)(want > cap ? cap : want), 256, 0, st>>>(ctx->vox_keys, ctx->vox_acc, table_slots);
+        voxel_clear_kernel<<<(int)(want > cap ? cap : want), 256, 0, st>>>(ctx->vox_acc, table_slots);
         DA3S_LAUNCH_CHECK(ctx);
     }
     DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->vox_dropped, 0, 32, st));
@@ -266,17 +356,41 @@ extern "C" int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots, void* stre
     return DA3S_OK;
 }
 
+static int voxel_insert_launch(da3s_ctx* ctx, const da3s_voxel_job* jobs_dev, int n_jobs, long long max_n, int width,
+                               const da3s_voxel_job& single, float voxel, void* stream) {
+    long long tiles;
+    if (width > 0) {
+        const long long rows = (max_n + width - 1) / width;
+        tiles = ((rows + 7) / 8) * ((width + 15) / 16);
+    } else {
+        tiles = (max_n + 127) / 128;
+    }
+    const long long chunks_per_job = (tiles + VI_TILES_PER_BLOCK - 1) / VI_TILES_PER_BLOCK;
+    const long long total = chunks_per_job * n_jobs, cap = (long long)ctx->sm_count * 8;     // 8 resident blocks per SM
+    voxel_insert_kernel<<<(unsigned int)(total > cap ? cap : total), VI_THREADS, 0, (cudaStream_t)stream>>>(
+        jobs_dev, single, n_jobs, chunks_per_job, width, voxel, ctx->vox_acc, ctx->vox_slots, ctx->vox_dropped);
+    DA3S_LAUNCH_CHECK(ctx);
+    return DA3S_OK;
+}
+
 extern "C" int da3s_voxel_insert(da3s_ctx* ctx, const float* xyz, const uint8_t* rgb, const uint8_t* mask,
                                  long long n, float voxel, void* stream) {
     if (!ctx || !xyz || n < 0 || !(voxel > 0.0f)) return DA3S_EINVAL;
     if (!ctx->vox_active) return DA3S_EINVAL;
     if (n == 0) return DA3S_OK;
-    long long want = (n + 255) / 256, cap = (long long)ctx->sm_count * 32;
-    int blocks = (int)(want > cap ? cap : want);
-    voxel_insert_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(xyz, rgb, mask, n, voxel, ctx->vox_keys, ctx->vox_acc,
-                                                                  ctx->vox_slots, ctx->vox_dropped);
-    DA3S_LAUNCH_CHECK(ctx);
-    return DA3S_OK;
+    da3s_voxel_job single;
+    single.xyz = xyz; single.rgb = rgb; single.mask = mask; single.n = n;
+    return voxel_insert_launch(ctx, nullptr, 1, n, 0, single, voxel, stream);
+}
+
+extern "C" int da3s_voxel_insert_jobs(da3s_ctx* ctx, const da3s_voxel_job* jobs_dev, int n_jobs, long long max_n,
+                                      int width, float voxel, void* stream) {
+    if (!ctx || !jobs_dev || n_jobs < 0 || n_jobs > 65535 || max_n < 0 || width < 0 || !(voxel > 0.0f)) return DA3S_EINVAL;
+    if (!ctx->vox_active) return DA3S_EINVAL;
+    if (n_jobs == 0 || max_n == 0) return DA3S_OK;
+    da3s_voxel_job none;
+    none.xyz = nullptr; none.rgb = nullptr; none.mask = nullptr; none.n = 0;
+    return voxel_insert_launch(ctx, jobs_dev, n_jobs, max_n, width, none, voxel, stream);
 }
 
 extern "C" int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxels, float* xyz_out, uint8_t* rgb_out,
@@ -289,11 +403,11 @@ extern "C" int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxel
     const int n_cblocks = (n_warps + VC_THREADS / 32 - 1) / (VC_THREADS / 32);
     unsigned int* warp_counts = ctx->vox_occ;
     unsigned long long* warp_offsets = (unsigned long long*)(warp_counts + ((n_warps + 1) & ~1));
-    voxel_count_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_keys, ctx->vox_slots, warp_counts);
+    voxel_count_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_counts);
     DA3S_LAUNCH_CHECK(ctx);
     voxel_scan_kernel<<<1, 1024, 0, st>>>(warp_counts, n_warps, warp_offsets, ctx->vox_dropped);
     DA3S_LAUNCH_CHECK(ctx);
-    voxel_emit_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_keys, ctx->vox_acc, ctx->vox_slots, warp_offsets, voxel, max_voxels,
+    voxel_emit_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_offsets, voxel, max_voxels,
                                                        xyz_out, rgb_out, count_out, key_out);
     DA3S_LAUNCH_CHECK(ctx);
     DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_voxels, ctx->vox_dropped, 8, cudaMemcpyDeviceToDevice, st));

@@ -463,6 +463,26 @@ class VoxelGrid:
                                             _ptr(mask, "mask"), n, float(voxel), self._st())
         L.check(rc, "da3s_voxel_insert")
 
+    def make_jobs(self, clouds):
+        """clouds: list of (xyz, rgb or None, mask or None) CUDA tensors that stay alive.  Returns the device job
+        table (and the largest n) for insert_jobs: every cloud goes into the grid in ONE launch."""
+        arr = (L.VoxelJob * len(clouds))()
+        max_n = 0
+        for i, (xyz, rgb, mask) in enumerate(clouds):
+            arr[i].xyz = _ptr(xyz, "xyz", torch.float32).value
+            arr[i].rgb = _ptr(rgb, "rgb", torch.uint8).value if rgb is not None else None
+            arr[i].mask = _ptr(mask, "mask").value if mask is not None else None
+            arr[i].n = xyz.numel() // 3
+            max_n = max(max_n, arr[i].n)
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        return torch.from_numpy(raw).to(self.device), len(clouds), max_n
+
+    def insert_jobs(self, jobs, voxel, width=0):
+        """width > 0: the clouds are image sequences with rows of `width` points (patch-wise traversal)."""
+        table, n_jobs, max_n = jobs
+        rc = self.ctx.lib.da3s_voxel_insert_jobs(self.ctx.h, _ptr(table), n_jobs, max_n, int(width), float(voxel), self._st())
+        L.check(rc, "da3s_voxel_insert_jobs")
+
     def finish(self, voxel):
         rc = self.ctx.lib.da3s_voxel_finish(self.ctx.h, float(voxel), self.max_voxels, _ptr(self.xyz), _ptr(self.rgb),
                                             _ptr(self.count), _ptr(self.key), C.c_void_p(self.nv.data_ptr()),

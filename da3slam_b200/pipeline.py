@@ -184,6 +184,9 @@ class SequencePlan:
             if max_voxels is None:
                 max_voxels = table_slots
             self.grid = ops.VoxelGrid(self.dev, table_slots, max_voxels, submaps[0].images is not None)
+            # every submap's cloud goes into the grid in one launch
+            self.rgb_views = [sm.images[f0:] if sm.images is not None else None for sm, f0 in zip(submaps, self.first)]
+            self.voxel_jobs = self.grid.make_jobs(list(zip(self.xyz, self.rgb_views, self.mask)))
             self.points_per_step = total
         else:
             self.points_per_step = 0
@@ -206,9 +209,7 @@ class SequencePlan:
         mark("unproject")
         self.grid.begin()
         mark("voxel_clear")
-        for k, sm in enumerate(self.submaps):
-            rgb = sm.images[self.first[k]:] if sm.images is not None else None
-            self.grid.insert(self.xyz[k], rgb, self.mask[k], self.voxel)
+        self.grid.insert_jobs(self.voxel_jobs, self.voxel, width=self.W)
         mark("voxel_insert")
         self.grid.finish(self.voxel)
         mark("voxel_compact")

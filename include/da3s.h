@@ -286,6 +286,19 @@ int da3s_irls_points(da3s_ctx* ctx, const void* src, const void* dst, int points
 int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots /* power of two */, void* stream);
 int da3s_voxel_insert(da3s_ctx* ctx, const float* xyz, const uint8_t* rgb, const uint8_t* mask,
                       long long n, float voxel, void* stream);
+/* Same, for a DEVICE table of clouds in one launch (e.g. every submap of a sequence after
+ * da3s_unproject_filter_jobs); max_n = the largest job's n.  width > 0 declares the clouds to be
+ * image sequences with rows of `width` points ([frames,H,W,3]): warps then walk 8x16-pixel patches
+ * instead of runs of 128 points, which lets them merge the points of a voxel before they reach the
+ * table (same result — the sums are integers — fewer atomics); width = 0 for unstructured clouds. */
+typedef struct da3s_voxel_job {
+    const float*   xyz;         /* [n,3] float32                                  */
+    const uint8_t* rgb;         /* [n,3] uint8, nullable (all jobs alike)         */
+    const uint8_t* mask;        /* [n] uint8, nullable = every point              */
+    long long      n;
+} da3s_voxel_job;
+int da3s_voxel_insert_jobs(da3s_ctx* ctx, const da3s_voxel_job* jobs_dev, int n_jobs, long long max_n,
+                           int width, float voxel, void* stream);
 int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxels, float* xyz_out, uint8_t* rgb_out,
                       int32_t* count_out, long long* key_out, unsigned long long* n_voxels,
                       unsigned long long* n_dropped /* nullable: points lost to a full table */, void* stream);

@@ -405,6 +405,36 @@ def test_voxel_accumulates_across_clouds(cuda):
     assert np.array_equal(out[0].cpu().numpy(), xyz)
 
 
+def test_voxel_insert_jobs_one_launch(cuda):
+    """da3s_voxel_insert_jobs: ragged clouds (empty, unaligned mask, sparse and dense masks) in one launch
+    == the oracle on their concatenation."""
+    rng = np.random.default_rng(9)
+    sizes = [0, 1, 31, 129, 5000, 20011]
+    keep = [1.0, 1.0, 0.5, 0.05, 0.35, 0.9]
+    pts = [rng.normal(0, 0.4, (n, 3)).astype(np.float32) for n in sizes]
+    rgb = [rng.integers(0, 256, (n, 3), dtype=np.uint8) for n in sizes]
+    msk = [(rng.random(n) < k) for n, k in zip(sizes, keep)]
+    pts[4][:300] = pts[4][0] + rng.normal(0, 1e-4, (300, 3)).astype(np.float32)
+    pts[5][7] = [np.inf, 0, 0]
+    grid = ops.VoxelGrid(cuda, 1 << 16, 1 << 16, True)
+    backing = torch.zeros(sum(sizes) + 64, dtype=torch.uint8, device=cuda)
+    clouds, off = [], 1                                        # masks at odd offsets: the unaligned path
+    for p_, c_, m_ in zip(pts, rgb, msk):
+        mv = backing[off:off + len(m_)]
+        mv.copy_(torch.from_numpy(m_.astype(np.uint8)))
+        off += len(m_) + 1
+        clouds.append((dev_t(p_, cuda), dev_t(c_, cuda), mv))
+    jobs = grid.make_jobs(clouds)
+    for width in (0, 37):                                      # runs of 128 points / 8x16 patches of rows of 37
+        grid.begin()
+        grid.insert_jobs(jobs, 0.03, width=width)
+        grid.finish(0.03)
+        xyz, col, cnt, key = grid.read(sort=True)
+        e_xyz, e_col, e_cnt, e_key = sp.voxel_downsample(np.concatenate(pts), 0.03, np.concatenate(rgb), np.concatenate(msk))
+        assert np.array_equal(key.cpu().numpy(), e_key) and np.array_equal(cnt.cpu().numpy(), e_cnt)
+        assert np.array_equal(xyz.cpu().numpy(), e_xyz) and np.array_equal(col.cpu().numpy(), e_col)
+
+
 def test_errors_are_loud(cuda):
     with pytest.raises(RuntimeError):
         ops.unproject_filter(torch.zeros(1, 4, 4), None, torch.zeros(1, 200, dtype=torch.uint8))      # CPU tensor
