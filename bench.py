@@ -360,6 +360,10 @@ def gpu_arm(args, w, rank, world):
                                "21 B/pixel (4 depth + 4 conf read, 12 xyz + 1 mask written)")
         single["voxel_insert"] = ("voxel_insert_kernel", (12.0 + 1.0 + 3.0) * px_export, w["n_submaps"],
                                   "16 B/point read (12 xyz + 3 rgb + 1 mask); hash-table traffic not counted")
+        single["export_fused"] = ("export_voxel_kernel (unproject + Sim(3) + filter + voxel insert)",
+                                  (8.0 + 3.0 * (1.0 - CONF_PERCENTILE / 100.0)) * px_export, 1,
+                                  "8 B/pixel read (depth + conf) + 3 B rgb per kept point; hash-table traffic not counted "
+                                  "(random 64-B records: see roofline.traffic)")
         single["voxel_clear"] = ("voxel_clear_kernel (first use only)", 72.0 * plan.grid.table_slots, 1, "72 B/slot written")
         single["voxel_compact"] = ("voxel_count/scan/emit_kernel", 16.0 * plan.grid.table_slots + (128.0 + 27.0) * n_vox, 3,
                                    "2 x 8 B/slot key scans + per voxel 64 B record read, 64 B reset, 27 B output")

@@ -62,7 +62,12 @@ class VoxelJob(C.Structure):
     _fields_ = [("xyz", C.c_void_p), ("rgb", C.c_void_p), ("mask", C.c_void_p), ("n", C.c_longlong)]
 
 
-assert C.sizeof(FrameJob) == 56 and C.sizeof(VoxelJob) == 32
+class ExportJob(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("conf", C.c_void_p), ("cam", C.c_void_p), ("sim3", C.c_void_p),
+                ("conf_thr", C.c_void_p), ("rgb", C.c_void_p)]
+
+
+assert C.sizeof(FrameJob) == 56 and C.sizeof(VoxelJob) == 32 and C.sizeof(ExportJob) == 48
 assert C.sizeof(Pair) == PAIR_BYTES and C.sizeof(SelectSeg) == 64 and C.sizeof(SelectOut) == 24
 
 _P, _I, _L, _F, _D, _ULL = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_ulonglong
@@ -92,6 +97,7 @@ SIGNATURES = {
     "da3s_voxel_begin": (_I, [_P, _L, _P]),
     "da3s_voxel_insert": (_I, [_P, _P, _P, _P, _L, _F, _P]),
     "da3s_voxel_insert_jobs": (_I, [_P, _P, _I, _L, _I, _F, _P]),
+    "da3s_unproject_voxel_jobs": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P]),
     "da3s_voxel_finish": (_I, [_P, _F, _L, _P, _P, _P, _P, _P, _P, _P]),
     "da3s_align_pairs_host": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(AlignOpts), _P, _P, _P]),
 }

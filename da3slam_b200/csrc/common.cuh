@@ -83,6 +83,11 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ float2 ldg_stream(const float2* p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ float ldg_stream1(const float* p) {
     float r;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));

@@ -19,6 +19,7 @@
 // occupied voxel written.  Hash-table traffic (random 64 B records in L2/HBM) is what
 // actually bounds this kernel and is not counted as algorithmic.
 #include "common.cuh"
+#include "unproject_frame.cuh"
 
 #define VOX_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define VOX_BIAS (1 << 20)
@@ -48,27 +49,26 @@ __global__ void voxel_clear_kernel(unsigned long long* acc, long long slots) {
 #define VI_THREADS 256
 #define VI_QUEUE 256                        // per-warp ring of point indices (>= 31 left over + 128 new)
 
-__device__ __forceinline__ void voxel_insert_point(bool active, long long i, const da3s_voxel_job& job, double vd,
-                                                   unsigned long long* __restrict__ acc,
-                                                   long long slots, unsigned long long* __restrict__ counters) {
+// one batch of up to 32 points held in registers: float64 quantisation, in-warp merge of the lanes that fall
+// in the same voxel, then probe / claim / five additions by the merged lanes.  Every lane of the warp calls it.
+__device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py, float pz, unsigned int rgb, bool has_rgb, double vd,
+                                                 unsigned long long* __restrict__ acc, long long slots,
+                                                 unsigned long long* __restrict__ counters) {
     const unsigned int lane = threadIdx.x & 31;
     unsigned long long key = 0, sx = 0, sy = 0, sz = 0, cr = 1ull << 32, gb = 0ull;
+    active = active && is_finite_f(px) && is_finite_f(py) && is_finite_f(pz);
     if (active) {
-        const float px = job.xyz[3 * i], py = job.xyz[3 * i + 1], pz = job.xyz[3 * i + 2];
-        active = is_finite_f(px) && is_finite_f(py) && is_finite_f(pz);
         const double qx = __ddiv_rn((double)px, vd), qy = __ddiv_rn((double)py, vd), qz = __ddiv_rn((double)pz, vd);
         const double kx = floor(qx), ky = floor(qy), kz = floor(qz);
-        active = active && (fabs(kx) < (double)VOX_BIAS) && (fabs(ky) < (double)VOX_BIAS) && (fabs(kz) < (double)VOX_BIAS);
+        active = (fabs(kx) < (double)VOX_BIAS) && (fabs(ky) < (double)VOX_BIAS) && (fabs(kz) < (double)VOX_BIAS);
         if (active) {
             key = ((unsigned long long)((long long)kx + VOX_BIAS) << 42) | ((unsigned long long)((long long)ky + VOX_BIAS) << 21) |
                   (unsigned long long)((long long)kz + VOX_BIAS);
             sx = (unsigned long long)__double2ll_rn((qx - kx) * 4294967296.0);
             sy = (unsigned long long)__double2ll_rn((qy - ky) * 4294967296.0);
             sz = (unsigned long long)__double2ll_rn((qz - kz) * 4294967296.0);
-            if (job.rgb) {
-                cr |= (unsigned long long)job.rgb[3 * i];
-                gb = ((unsigned long long)job.rgb[3 * i + 1] << 32) | (unsigned long long)job.rgb[3 * i + 2];
-            }
+            cr |= (unsigned long long)(rgb & 0xFFu);
+            gb = ((unsigned long long)((rgb >> 8) & 0xFFu) << 32) | (unsigned long long)((rgb >> 16) & 0xFFu);
         }
     }
     const unsigned int act = __ballot_sync(0xffffffffu, active);
@@ -100,12 +100,24 @@ __device__ __forceinline__ void voxel_insert_point(bool active, long long i, con
         if (cur == key) {
             atomicAdd(rec + 1, sx); atomicAdd(rec + 2, sy); atomicAdd(rec + 3, sz);
             atomicAdd(rec + 4, cr);
-            if (job.rgb) atomicAdd(rec + 5, gb);
+            if (has_rgb) atomicAdd(rec + 5, gb);
             return;
         }
         slot = (slot + 1) & (unsigned long long)(slots - 1);
     }
     atomicAdd(&counters[1], cr >> 32);                              // table full: reported by finish
+}
+
+__device__ __forceinline__ void voxel_insert_point(bool active, long long i, const da3s_voxel_job& job, double vd,
+                                                   unsigned long long* __restrict__ acc,
+                                                   long long slots, unsigned long long* __restrict__ counters) {
+    float px = 0.0f, py = 0.0f, pz = 0.0f;
+    unsigned int rgb = 0u;
+    if (active) {
+        px = job.xyz[3 * i]; py = job.xyz[3 * i + 1]; pz = job.xyz[3 * i + 2];
+        if (job.rgb) rgb = (unsigned int)job.rgb[3 * i] | ((unsigned int)job.rgb[3 * i + 1] << 8) | ((unsigned int)job.rgb[3 * i + 2] << 16);
+    }
+    voxel_insert_xyz(active, px, py, pz, rgb, job.rgb != nullptr, vd, acc, slots, counters);
 }
 
 // Work unit of a warp = a TILE of 128 points: 128 consecutive points of an unstructured cloud, or — when
@@ -189,6 +201,177 @@ voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job sing
             __syncwarp();
         }
     }
+}
+
+// ---------------------------------------------------------------------------------
+// Fused export: depth -> world point (+ Sim(3)) -> confidence / validity filter -> voxel grid, without
+// ever writing the points.  Same arithmetic as K1's fast float32 path followed by the insert above
+// (shared device functions), so the grid is bit-identical to the two-kernel route; what disappears
+// is 13 B/pixel of K1 stores and ~16 B/kept point of insert loads.
+// ---------------------------------------------------------------------------------
+#define EX_CONST 20                         // floats per frame: cu cv 1/fu 1/fv | Mf[9] | mf[3] | thr | pad
+
+__global__ void export_frame_const_kernel(const da3s_export_job* __restrict__ jobs, int n_frames, int world, float conf_thr,
+                                          float* __restrict__ fcs) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const da3s_export_job j = jobs[f];
+    UnprojFrame fr;
+    compose_unproj_frame(*j.cam, j.sim3, world != 0, fr);
+    float* o = fcs + (size_t)f * EX_CONST;
+    o[0] = fr.cuf; o[1] = fr.cvf; o[2] = fr.ifu; o[3] = fr.ifv;
+    for (int k = 0; k < 9; ++k) o[4 + k] = fr.Mf[k];
+    for (int k = 0; k < 3; ++k) o[13 + k] = fr.mf[k];
+    o[16] = j.conf_thr ? *j.conf_thr : conf_thr;
+    o[17] = o[18] = o[19] = 0.0f;
+}
+
+struct ExportArgs {
+    const da3s_export_job* jobs; const float* fcs;
+    int n_frames, H, W, flags;
+    float conf_floor, depth_eps, voxel;
+    long long chunks_per_frame;
+    unsigned long long* acc; long long slots; unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(VI_THREADS)
+export_voxel_kernel(ExportArgs a) {
+    __shared__ unsigned long long queue[VI_THREADS / 32][VI_QUEUE];     // (depth bits << 32) | (v << 16) | u
+    __shared__ float fc_sh[VI_THREADS / 32][EX_CONST];
+    const double vd = (double)a.voxel;
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* q = queue[warp];
+    float* fc = fc_sh[warp];
+    const int W = a.W, H = a.H;
+    const int tiles_per_band = (W + 15) / 16;
+    const long long total = a.chunks_per_frame * a.n_frames;
+    const bool f_gt = a.flags & DA3S_MASK_CONF_GT, f_ge = a.flags & DA3S_MASK_CONF_GE;
+    const bool f_floor = a.flags & DA3S_MASK_CONF_FLOOR, f_depth = a.flags & DA3S_MASK_DEPTH;
+    const bool xform = true;
+    for (long long c = blockIdx.x; c < total; c += gridDim.x) {
+        const int f = (int)(c / a.chunks_per_frame);
+        const da3s_export_job job = a.jobs[f];
+        __syncwarp();
+        if (lane < EX_CONST) fc[lane] = a.fcs[(size_t)f * EX_CONST + lane];
+        __syncwarp();
+        const float thr = fc[16];
+        const long long t_begin = (c - (long long)f * a.chunks_per_frame) * VI_TILES_PER_BLOCK + (long long)warp * VI_TILES_PER_WARP;
+        unsigned int head = 0, count = 0;                           // warp-uniform ring state
+        auto batch = [&](bool active, unsigned long long e) {
+            const int u = (int)(e & 0xFFFFu), v = (int)((e >> 16) & 0xFFFFu);
+            const float d = __uint_as_float((unsigned int)(e >> 32));
+            unsigned int rgb = 0u;
+            if (active && job.rgb) {
+                const uint8_t* p = job.rgb + 3 * ((size_t)v * W + u);
+                rgb = (unsigned int)p[0] | ((unsigned int)p[1] << 8) | ((unsigned int)p[2] << 16);
+            }
+            // K1 fast path (unproject_pixel<DA3S_UNPROJ_FAST> with the composed float32 transform)
+            float x, y;
+            cam_fast((float)u, (float)v, d, fc[0], fc[1], fc[2], fc[3], x, y);
+            float X = x, Y = y, Z = d;
+            if (xform) {
+                X = fmaf(fc[4], x, fmaf(fc[5], y, fmaf(fc[6], d, fc[13])));
+                Y = fmaf(fc[7], x, fmaf(fc[8], y, fmaf(fc[9], d, fc[14])));
+                Z = fmaf(fc[10], x, fmaf(fc[11], y, fmaf(fc[12], d, fc[15])));
+            }
+            voxel_insert_xyz(active, X, Y, Z, rgb, job.rgb != nullptr, vd, a.acc, a.slots, a.counters);
+        };
+#pragma unroll 1
+        for (int tt = 0; tt < VI_TILES_PER_WARP; ++tt) {
+            const long long t = t_begin + tt;
+            const long long band = t / tiles_per_band;
+            const int tx = (int)(t - band * tiles_per_band);
+            const int col = tx * 16 + (int)(lane & 3) * 4;
+            const int row = (int)band * 8 + (int)(lane >> 2);
+            int lim = W - col;
+            if (lim > 4) lim = 4;
+            if (row >= H) lim = 0;
+            if (__ballot_sync(0xffffffffu, lim > 0) == 0) break;    // past the end of this frame (warp-uniform)
+            float d4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (lim > 0) {
+                const size_t i0 = (size_t)row * W + col;
+                if (lim == 4 && ((i0 & 1) == 0)) {                  // 8-byte aligned pairs (frames are 16-byte aligned)
+                    const float2 da = ldg_stream(reinterpret_cast<const float2*>(job.depth + i0));
+                    const float2 db = ldg_stream(reinterpret_cast<const float2*>(job.depth + i0 + 2));
+                    d4[0] = da.x; d4[1] = da.y; d4[2] = db.x; d4[3] = db.y;
+                    if (job.conf) {
+                        const float2 ca = ldg_stream(reinterpret_cast<const float2*>(job.conf + i0));
+                        const float2 cb = ldg_stream(reinterpret_cast<const float2*>(job.conf + i0 + 2));
+                        c4[0] = ca.x; c4[1] = ca.y; c4[2] = cb.x; c4[3] = cb.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (b < lim) { d4[b] = job.depth[i0 + b]; if (job.conf) c4[b] = job.conf[i0 + b]; }
+                }
+            }
+            unsigned int flags = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const float cc = c4[b], dd = d4[b];
+                bool k = b < lim;
+                if (job.conf) k = k & (!f_gt || cc > thr) & (!f_ge || cc >= thr) & (!f_floor || cc > a.conf_floor);
+                k = k & (!f_depth || ((dd > a.depth_eps) & is_finite_f(dd)));
+                flags |= k ? (1u << b) : 0u;
+            }
+            const unsigned int cnt = __popc(flags);
+            unsigned int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int w = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (unsigned int)o) incl += w;
+            }
+            const unsigned int total_new = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned int pos = head + count + incl - cnt;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if ((flags >> b) & 1u) {
+                    q[pos & (VI_QUEUE - 1)] = ((unsigned long long)__float_as_uint(d4[b]) << 32) | ((unsigned long long)row << 16) |
+                                              (unsigned long long)(col + b);
+                    ++pos;
+                }
+            count += total_new;
+            __syncwarp();
+            while (count >= 32) {
+                batch(true, q[(head + lane) & (VI_QUEUE - 1)]);
+                __syncwarp();
+                head += 32; count -= 32;
+            }
+        }
+        if (count) {                                                // the queue never crosses a frame boundary
+            const bool active = lane < count;
+            batch(active, active ? q[(head + lane) & (VI_QUEUE - 1)] : 0ull);
+            __syncwarp();
+        }
+    }
+}
+
+extern "C" int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* jobs_dev, int n_frames, int H, int W, int flags,
+                                         float conf_thr, float conf_floor, float depth_eps, float voxel, void* stream) {
+    if (!ctx || !jobs_dev || n_frames < 0 || H <= 0 || W <= 0 || H > 65535 || W > 65535 || !(voxel > 0.0f)) return DA3S_EINVAL;
+    if ((flags & DA3S_UNPROJ_MODEMASK) != DA3S_UNPROJ_FAST || (flags & (DA3S_UNPROJ_OUT_F64 | DA3S_MASK_WORLD_Z))) return DA3S_EINVAL;
+    if ((flags & DA3S_MASK_CONF_GT) && (flags & DA3S_MASK_CONF_GE)) return DA3S_EINVAL;
+    if (!ctx->vox_active) return DA3S_EINVAL;
+    if (n_frames == 0) return DA3S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t save_top = ctx->ws_top;
+    WS_ALLOC(ctx, float, fcs, (size_t)n_frames * EX_CONST);
+    export_frame_const_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(jobs_dev, n_frames, (flags & DA3S_UNPROJ_WORLD) ? 1 : 0, conf_thr, fcs);
+    DA3S_LAUNCH_CHECK(ctx);
+    ExportArgs a;
+    a.jobs = jobs_dev; a.fcs = fcs; a.n_frames = n_frames; a.H = H; a.W = W; a.flags = flags;
+    a.conf_floor = conf_floor; a.depth_eps = depth_eps; a.voxel = voxel;
+    const long long tiles = (long long)((H + 7) / 8) * ((W + 15) / 16);
+    a.chunks_per_frame = (tiles + VI_TILES_PER_BLOCK - 1) / VI_TILES_PER_BLOCK;
+    a.acc = ctx->vox_acc; a.slots = ctx->vox_slots; a.counters = ctx->vox_dropped;
+    int per_sm = 0;
+    DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, export_voxel_kernel, VI_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    const long long total = a.chunks_per_frame * n_frames, cap = (long long)ctx->sm_count * per_sm;
+    export_voxel_kernel<<<(unsigned int)(total > cap ? cap : total), VI_THREADS, 0, st>>>(a);
+    DA3S_LAUNCH_CHECK(ctx);
+    ctx->ws_top = save_top;     // the constants are consumed in stream order
+    return DA3S_OK;
 }
 
 // Compaction without atomics or barriers, two streaming passes over the DENSE key array:
@@ -366,7 +549,11 @@ static int voxel_insert_launch(da3s_ctx* ctx, const da3s_voxel_job* jobs_dev, in
         tiles = (max_n + 127) / 128;
     }
     const long long chunks_per_job = (tiles + VI_TILES_PER_BLOCK - 1) / VI_TILES_PER_BLOCK;
-    const long long total = chunks_per_job * n_jobs, cap = (long long)ctx->sm_count * 8;     // 8 resident blocks per SM
+    // exactly the blocks that are resident together, so that "block b takes chunks b, b + G, ..." is a sweep in order
+    int per_sm = 0;
+    DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxel_insert_kernel, VI_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    const long long total = chunks_per_job * n_jobs, cap = (long long)ctx->sm_count * per_sm;
     voxel_insert_kernel<<<(unsigned int)(total > cap ? cap : total), VI_THREADS, 0, (cudaStream_t)stream>>>(
         jobs_dev, single, n_jobs, chunks_per_job, width, voxel, ctx->vox_acc, ctx->vox_slots, ctx->vox_dropped);
     DA3S_LAUNCH_CHECK(ctx);

@@ -483,6 +483,34 @@ class VoxelGrid:
         rc = self.ctx.lib.da3s_voxel_insert_jobs(self.ctx.h, _ptr(table), n_jobs, max_n, int(width), float(voxel), self._st())
         L.check(rc, "da3s_voxel_insert_jobs")
 
+    def make_export_jobs(self, frames):
+        """frames: list of dicts(depth, conf, cam, sim3, conf_thr, rgb) of CUDA tensors / None that stay alive
+        (one per image frame).  Returns the device job table for insert_frames."""
+        arr = (L.ExportJob * len(frames))()
+        for i, j in enumerate(frames):
+            for name in ("depth", "conf", "cam", "sim3", "conf_thr", "rgb"):
+                t = j.get(name)
+                if t is None:
+                    continue
+                if not t.is_cuda or not t.is_contiguous():
+                    raise RuntimeError("export job tensors must be contiguous CUDA tensors")
+                if name in ("depth", "conf") and t.data_ptr() % 16:
+                    raise L.Da3sError(L.EALIGN, "make_export_jobs", f"{name} is not 16-byte aligned")
+                setattr(arr[i], name, t.data_ptr())
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        return torch.from_numpy(raw).to(self.device), len(frames)
+
+    def insert_frames(self, jobs, H, W, voxel, *, world=True, conf_cmp=None, conf_thr=0.0, conf_floor=None, depth_eps=None):
+        """Fused unproject (fast float32) + Sim(3) + filter + insert of every frame of the job table: the grid
+        receives exactly what unproject_filter_jobs + insert_jobs would give it, the points are never written."""
+        table, n_frames = jobs
+        flags = L.UNPROJ_FAST | (L.UNPROJ_WORLD if world else 0)
+        flags |= {None: 0, ">": L.MASK_CONF_GT, ">=": L.MASK_CONF_GE}[conf_cmp]
+        flags |= (L.MASK_CONF_FLOOR if conf_floor is not None else 0) | (L.MASK_DEPTH if depth_eps is not None else 0)
+        rc = self.ctx.lib.da3s_unproject_voxel_jobs(self.ctx.h, _ptr(table), n_frames, H, W, flags, float(conf_thr),
+                                                    float(conf_floor or 0.0), float(depth_eps or 0.0), float(voxel), self._st())
+        L.check(rc, "da3s_unproject_voxel_jobs")
+
     def finish(self, voxel):
         rc = self.ctx.lib.da3s_voxel_finish(self.ctx.h, float(voxel), self.max_voxels, _ptr(self.xyz), _ptr(self.rgb),
                                             _ptr(self.count), _ptr(self.key), C.c_void_p(self.nv.data_ptr()),

@@ -140,7 +140,7 @@ class SequencePlan:
     read() synchronises and returns host/trimmed results.  This is one "step" of bench.py."""
 
     def __init__(self, submaps, overlap=1, voxel=0.02, conf_percentile=65.0, unproject_mode="fast", table_slots=None,
-                 max_voxels=None, sample_idx=None, export=True, skip_overlap=True, **opt_kw):
+                 max_voxels=None, sample_idx=None, export=True, skip_overlap=True, fuse_export=True, **opt_kw):
         self.submaps = submaps
         self.n = len(submaps)
         self.dev = submaps[0].depth.device
@@ -149,6 +149,9 @@ class SequencePlan:
         self.voxel = float(voxel)
         self.mode = unproject_mode
         self.export = export
+        # fuse_export: the exported points go straight from the depth maps into the voxel grid (one kernel);
+        # False keeps the per-point arrays (self.xyz / self.mask) for callers that want the full cloud
+        self.fuse_export = bool(fuse_export) and unproject_mode == "fast"
         self.opts = L.default_opts(**opt_kw)
         self.n_pairs = self.n - 1
         self.entries = [pair_entry(submaps[k], submaps[k + 1], overlap) for k in range(self.n_pairs)]
@@ -164,29 +167,37 @@ class SequencePlan:
             segs = [dict(a=sm.conf[f0:], kind=L.SEL_POSITIVE, stat=L.SEL_PERCENTILE, percent=float(min(conf_percentile, 99.9)))
                     for sm, f0 in zip(submaps, self.first)]
             self.percentiles = ops.SelectPlan(segs, self.dev)
-            self.xyz = [torch.empty((self.F - f0, self.H, self.W, 3), dtype=torch.float32, device=self.dev) for f0 in self.first]
-            self.mask = [torch.empty((self.F - f0, self.H, self.W), dtype=torch.uint8, device=self.dev) for f0 in self.first]
-            self.n_kept = torch.zeros((1,), dtype=torch.int64, device=self.dev)
-            # one job per exported frame: static pointers into the submaps, the cumulative Sim(3) table,
-            # the percentile records and the output buffers -> the whole export is ONE unprojection launch
-            jobs = []
-            for k, (sm, f0) in enumerate(zip(submaps, self.first)):
-                for f in range(f0, self.F):
-                    jobs.append(dict(depth=sm.depth[f], conf=sm.conf[f], cam=sm.cams[f], sim3=self.cum[k],
-                                     conf_thr=self.percentiles.value_ptr_tensor(k), xyz=self.xyz[k][f - f0],
-                                     mask=self.mask[k][f - f0]))
-            self.n_jobs = len(jobs)
-            self.job_table = ops.make_frame_jobs(jobs, self.dev)
-            total = sum(x.numel() // 3 for x in self.xyz)
+            total = sum((self.F - f0) * self.H * self.W for f0 in self.first)
             if table_slots is None:
                 table_slots = 1 << max(12, int(np.ceil(np.log2(max(total // 4, 4096)))))
                 table_slots = min(table_slots, 1 << 27)
             if max_voxels is None:
                 max_voxels = table_slots
             self.grid = ops.VoxelGrid(self.dev, table_slots, max_voxels, submaps[0].images is not None)
-            # every submap's cloud goes into the grid in one launch
-            self.rgb_views = [sm.images[f0:] if sm.images is not None else None for sm, f0 in zip(submaps, self.first)]
-            self.voxel_jobs = self.grid.make_jobs(list(zip(self.xyz, self.rgb_views, self.mask)))
+            if self.fuse_export:
+                frames = []
+                for k, (sm, f0) in enumerate(zip(submaps, self.first)):
+                    for f in range(f0, self.F):
+                        frames.append(dict(depth=sm.depth[f], conf=sm.conf[f], cam=sm.cams[f], sim3=self.cum[k],
+                                           conf_thr=self.percentiles.value_ptr_tensor(k),
+                                           rgb=sm.images[f] if sm.images is not None else None))
+                self.export_jobs = self.grid.make_export_jobs(frames)
+            else:
+                self.xyz = [torch.empty((self.F - f0, self.H, self.W, 3), dtype=torch.float32, device=self.dev) for f0 in self.first]
+                self.mask = [torch.empty((self.F - f0, self.H, self.W), dtype=torch.uint8, device=self.dev) for f0 in self.first]
+                # one job per exported frame: static pointers into the submaps, the cumulative Sim(3) table,
+                # the percentile records and the output buffers -> the whole export is ONE unprojection launch
+                jobs = []
+                for k, (sm, f0) in enumerate(zip(submaps, self.first)):
+                    for f in range(f0, self.F):
+                        jobs.append(dict(depth=sm.depth[f], conf=sm.conf[f], cam=sm.cams[f], sim3=self.cum[k],
+                                         conf_thr=self.percentiles.value_ptr_tensor(k), xyz=self.xyz[k][f - f0],
+                                         mask=self.mask[k][f - f0]))
+                self.n_jobs = len(jobs)
+                self.job_table = ops.make_frame_jobs(jobs, self.dev)
+                # every submap's cloud goes into the grid in one launch
+                self.rgb_views = [sm.images[f0:] if sm.images is not None else None for sm, f0 in zip(submaps, self.first)]
+                self.voxel_jobs = self.grid.make_jobs(list(zip(self.xyz, self.rgb_views, self.mask)))
             self.points_per_step = total
         else:
             self.points_per_step = 0
@@ -204,13 +215,18 @@ class SequencePlan:
             return
         self.percentiles.run()
         mark("percentile")
-        ops.unproject_filter_jobs(self.job_table, self.n_jobs, self.H, self.W, mode=self.mode, world=True, conf_cmp=">=",
-                                  conf_floor=0.0, depth_eps=1e-6)
-        mark("unproject")
         self.grid.begin()
         mark("voxel_clear")
-        self.grid.insert_jobs(self.voxel_jobs, self.voxel, width=self.W)
-        mark("voxel_insert")
+        if self.fuse_export:
+            self.grid.insert_frames(self.export_jobs, self.H, self.W, self.voxel, world=True, conf_cmp=">=", conf_floor=0.0,
+                                    depth_eps=1e-6)
+            mark("export_fused")
+        else:
+            ops.unproject_filter_jobs(self.job_table, self.n_jobs, self.H, self.W, mode=self.mode, world=True, conf_cmp=">=",
+                                      conf_floor=0.0, depth_eps=1e-6)
+            mark("unproject")
+            self.grid.insert_jobs(self.voxel_jobs, self.voxel, width=self.W)
+            mark("voxel_insert")
         self.grid.finish(self.voxel)
         mark("voxel_compact")
 

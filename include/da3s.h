@@ -299,6 +299,20 @@ typedef struct da3s_voxel_job {
 } da3s_voxel_job;
 int da3s_voxel_insert_jobs(da3s_ctx* ctx, const da3s_voxel_job* jobs_dev, int n_jobs, long long max_n,
                            int width, float voxel, void* stream);
+/* Fused export of image frames straight into the grid: what da3s_unproject_filter_jobs (fast float32
+ * mode, same flags) followed by da3s_voxel_insert_jobs would insert — bit for bit — without writing
+ * the points (utils/da3_streaming.py:639-644 + the map export that follows it).  Only
+ * DA3S_UNPROJ_FAST (+ DA3S_UNPROJ_WORLD, DA3S_MASK_CONF_*, DA3S_MASK_DEPTH) is accepted. */
+typedef struct da3s_export_job {
+    const float*    depth;      /* [H,W], 16-byte aligned          */
+    const float*    conf;       /* [H,W] or null                   */
+    const da3s_cam* cam;
+    const double*   sim3;       /* [13] or null                    */
+    const float*    conf_thr;   /* device scalar or null           */
+    const uint8_t*  rgb;        /* [H,W,3] or null (all jobs alike) */
+} da3s_export_job;
+int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* jobs_dev, int n_frames, int H, int W, int flags,
+                              float conf_thr, float conf_floor, float depth_eps, float voxel, void* stream);
 int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxels, float* xyz_out, uint8_t* rgb_out,
                       int32_t* count_out, long long* key_out, unsigned long long* n_voxels,
                       unsigned long long* n_dropped /* nullable: points lost to a full table */, void* stream);

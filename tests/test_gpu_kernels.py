@@ -456,10 +456,15 @@ def test_sequence_plan_end_to_end(cuda):
     H, W, F, n = 48, 64, 3, 4
     subs, gt = synth.make_sequence(n, F, H, W, overlap=1, seed=77, with_images=True)
     dsubs = [DeviceSubmap.from_prediction(s, cuda) for s in subs]
-    plan = SequencePlan(dsubs, overlap=1, voxel=0.05, conf_percentile=65.0, table_slots=1 << 16, world=1)
+    # two-kernel export (keeps the per-point arrays, checked below) and the fused export (depth -> grid)
+    plan = SequencePlan(dsubs, overlap=1, voxel=0.05, conf_percentile=65.0, table_slots=1 << 16, world=1, fuse_export=False)
+    fused = SequencePlan(dsubs, overlap=1, voxel=0.05, conf_percentile=65.0, table_slots=1 << 16, world=1, fuse_export=True)
+    assert fused.fuse_export and not plan.fuse_export
     for _ in range(2):                                        # twice: the grid must come back clean
         plan.run()
         out = plan.read(sort=True)
+        fused.run()
+        out_f = fused.read(sort=True)
     rows = out["rows"]
     chain = []
     for k in range(n - 1):
@@ -488,6 +493,10 @@ def test_sequence_plan_end_to_end(cuda):
     xyz, col, cnt, key = sp.voxel_downsample(np.concatenate(all_xyz), 0.05, np.concatenate(all_rgb), np.concatenate(all_mask))
     assert np.array_equal(out["voxel_key"].cpu().numpy(), key) and np.array_equal(out["voxel_count"].cpu().numpy(), cnt)
     assert np.array_equal(out["voxel_xyz"].cpu().numpy(), xyz) and np.array_equal(out["voxel_rgb"].cpu().numpy(), col)
+    # the fused kernel never writes the points, yet fills the grid with exactly the same integers
+    assert np.array_equal(out_f["rows"], out["rows"]) and np.array_equal(out_f["cum"], out["cum"])
+    assert np.array_equal(out_f["voxel_key"].cpu().numpy(), key) and np.array_equal(out_f["voxel_count"].cpu().numpy(), cnt)
+    assert np.array_equal(out_f["voxel_xyz"].cpu().numpy(), xyz) and np.array_equal(out_f["voxel_rgb"].cpu().numpy(), col)
 
 
 def test_unproject_jobs_equals_flat_launch(cuda):
