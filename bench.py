@@ -7,7 +7,7 @@
 One STEP = one pass of the whole hot path over one synthetic submap sequence already
 resident in HBM (da3slam_b200.pipeline.SequencePlan.run): exact-median thresholds -> [RANSAC]
 -> IRLS Umeyama per consecutive submap pair -> Sim(3) chain -> per-submap confidence
-percentile -> unproject + Sim(3) + filter -> voxel-grid downsample.  Metric: submap pairs
+percentile -> unproject + Sim(3) + filter + voxel-grid insert (one fused kernel) -> compaction.  Metric: submap pairs
 aligned per second (whole job, all ranks); points/s is reported next to it.
 
 N > 1 (torchrun): every rank owns its own sequence (weak scaling, no data-path collective);
@@ -36,7 +36,7 @@ WORKLOADS = {
                     table_slots=1 << 24, voxel=0.02, desc="300 frames, 19 submaps x 16 x 518x518, 18 pairs"),
     # configs[2]: 2000 frames, 32-frame submaps, RANSAC 1024 hypotheses (make_image_chunks -> 65 submaps / 64 pairs)
     "seq2000": dict(n_submaps=65, frames=32, H=518, W=518, overlap=1, n_hyp=1024, outlier=0.3, export=True,
-                    table_slots=1 << 27, voxel=0.02, desc="2000 frames, 65 submaps x 32 x 518x518, 64 pairs, RANSAC 1024"),
+                    table_slots=1 << 28, voxel=0.02, desc="2000 frames, 65 submaps x 32 x 518x518, 64 pairs, RANSAC 1024"),
     # configs[3]: 512 independent loop-candidate pairs (2-frame submaps, so every pair reads distinct frames)
     "loop512": dict(n_submaps=513, frames=2, H=518, W=518, overlap=1, n_hyp=0, outlier=0.0, export=False,
                     table_slots=0, voxel=0.02, desc="512 submap pairs, 518x518, 1 overlap frame, alignment only"),
@@ -375,13 +375,21 @@ def gpu_arm(args, w, rank, world):
     kname, bytes_per_step, n_launch, note = single[dom]
     dur_ms = stages.get(dom, 0.0)
     achieved = bytes_per_step / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as fh:
+            ent = json.load(fh).get(args.workload, {}).get(dom)
+        if ent:
+            traffic, traffic_src = float(ent["bytes"]), f"{ent['kernel']}: {ent['source']}"
+    except (OSError, ValueError):
+        pass
     roofline = {"bound": "hbm", "kernel": kname, "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_step / n_launch, "launches_per_step": n_launch,
                 "avg_launch_ms": dur_ms / n_launch, "stage_share_of_step": dur_ms / ms_per_step, "note": note}
     per_stage = {}
     for k, (kn, b, nl, _) in single.items():
-        if stages.get(k, 0) > 0:
+        if stages.get(k, 0) > 0.02:                      # skip stages that did not run a kernel (re-used clean table)
             per_stage[k] = {"ms": stages[k], "GB/s": b / (stages[k] * 1e-3) / 1e9, "frac_of_peak": b / (stages[k] * 1e-3) / 1e9 / peak}
 
     out = {

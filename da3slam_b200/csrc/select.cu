@@ -551,7 +551,8 @@ select_pass_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, unsi
 // C: resolve — one block per segment selects the live ranks among the candidates (a few
 // per cent of the segment, L2 resident) or, on fallback, in the whole segment.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEL_THREADS)
+#define SEL_RESOLVE_THREADS 1024             // one block per segment: all the parallelism a segment gets
+__global__ void __launch_bounds__(SEL_RESOLVE_THREADS)
 select_resolve_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, da3s_select_out* out) {
     __shared__ SelScratch sc;
     const int seg_id = blockIdx.x;
@@ -609,7 +610,7 @@ int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, lon
         select_count_kernel<<<dim3((unsigned int)bx, n_segs), SEL_THREADS, 0, st>>>(segs, work, cand, cand_cap, tickets);
         DA3S_LAUNCH_CHECK(ctx);
         if (!big) {
-            select_resolve_kernel<<<n_segs, SEL_THREADS, 0, st>>>(segs, work, out);
+            select_resolve_kernel<<<n_segs, SEL_RESOLVE_THREADS, 0, st>>>(segs, work, out);
             DA3S_LAUNCH_CHECK(ctx);
         } else {
             dim3 grid((unsigned int)(cand_cap / per_block), n_segs);
