@@ -226,8 +226,13 @@ def gpu_arm(args, w, rank, world):
         rng = np.random.default_rng(99 + rank)
         sample_idx = torch.from_numpy(rng.integers(0, M, size=(n_pairs, w["n_hyp"], 3)).astype(np.int32))
         opt.update(n_hyp=w["n_hyp"], ransac_thr=RANSAC_THR)
+    exchange = None
+    if args.global_map and world > 1 and w["export"]:
+        # one global map over all ranks: records routed to the rank owning their key through peer memory (NVLink)
+        from da3slam_b200.sharding import VoxelExchange
+        exchange = VoxelExchange(dev, world, rank, cap=w["table_slots"] // world)
     plan = SequencePlan(dsubs, overlap=w["overlap"], voxel=w["voxel"], conf_percentile=CONF_PERCENTILE,
-                        table_slots=w["table_slots"] or None, sample_idx=sample_idx, export=w["export"], **opt)
+                        table_slots=w["table_slots"] or None, sample_idx=sample_idx, export=w["export"], exchange=exchange, **opt)
     ctx = ops.context(dev)
     gathered = [torch.empty((n_pairs, 16), dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
 
@@ -400,7 +405,8 @@ def gpu_arm(args, w, rank, world):
                    "overlap": w["overlap"], "pairs_per_gpu": n_pairs, "n_hyp": w["n_hyp"], "voxel": w["voxel"],
                    "conf_percentile": CONF_PERCENTILE, "irls": "huber delta=1.0, <=20 it, tol 1e-6 (utils/align.py defaults)",
                    "l2": f"inputs {sum(s['depth'].numel() * 8 for s in subs) / 1e6:.0f} MB per GPU vs 126 MB L2; no explicit flush",
-                   "parallelism": f"pairs sharded, {world} rank(s), Sim(3) rows all_gather only"},
+                   "parallelism": f"pairs sharded, {world} rank(s), Sim(3) rows all_gather"
+                                  + (" + global voxel map merged over NVLink peer memory" if exchange is not None else " only")},
         "points_per_sec": world * px_export / (ms_per_step * 1e-3) if w["export"] else None,
         "pixels_per_step_per_gpu": px_export, "voxels_out": n_vox,
         "stages_ms": stages, "stage_bandwidth": per_stage,
@@ -419,6 +425,8 @@ def main():
     ap.add_argument("--workload", default="c3vd300", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--global-map", action="store_true",
+                    help="N > 1: merge the rank-local voxel grids into one global map (da3s_voxel_send over NVLink peer memory)")
     ap.add_argument("--cpu-workers", type=int, default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -80,6 +80,7 @@ SIGNATURES = {
     "da3s_version": (_I, []),
     "da3s_last_cuda_error": (_I, [_P]),
     "da3s_launch_count": (_ULL, [_P]),
+    "da3s_enable_peer_access": (_I, [_P, _I]),
     "da3s_build_cams": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "da3s_unproject_filter": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _F, _F, _P, _P, _P, _P, _P]),
     "da3s_unproject_filter_jobs": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
@@ -97,6 +98,8 @@ SIGNATURES = {
     "da3s_voxel_begin": (_I, [_P, _L, _P]),
     "da3s_voxel_insert": (_I, [_P, _P, _P, _P, _L, _F, _P]),
     "da3s_voxel_insert_jobs": (_I, [_P, _P, _I, _L, _I, _F, _P]),
+    "da3s_voxel_send": (_I, [_P, _I, _I, _P, _P, _L, _P]),
+    "da3s_voxel_merge_inbox": (_I, [_P, _P, _P, _I, _L, _P]),
     "da3s_unproject_voxel_jobs": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P]),
     "da3s_voxel_finish": (_I, [_P, _F, _L, _P, _P, _P, _P, _P, _P, _P]),
     "da3s_align_pairs_host": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(AlignOpts), _P, _P, _P]),

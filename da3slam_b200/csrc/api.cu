@@ -51,6 +51,24 @@ extern "C" int da3s_destroy(da3s_ctx* ctx) {
 extern "C" int da3s_last_cuda_error(const da3s_ctx* ctx) { return ctx ? ctx->last_cuda_error : 0; }
 extern "C" unsigned long long da3s_launch_count(const da3s_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
 
+extern "C" int da3s_enable_peer_access(da3s_ctx* ctx, int peer_device) {
+    if (!ctx || peer_device < 0) return DA3S_EINVAL;
+    if (peer_device == ctx->device) return DA3S_OK;
+    int prev = 0, can = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaDeviceCanAccessPeer(&can, ctx->device, peer_device);
+    if (e == cudaSuccess && can) {
+        e = cudaDeviceEnablePeerAccess(peer_device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    } else if (e == cudaSuccess) {
+        e = cudaErrorPeerAccessUnsupported;
+    }
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) { ctx->last_cuda_error = (int)e; cudaGetLastError(); return DA3S_ECUDA; }
+    return DA3S_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // host-buffer path: H2D copies, the device pipeline, D2H of the rows, one synchronise.
 // ---------------------------------------------------------------------------------

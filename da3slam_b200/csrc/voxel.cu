@@ -509,6 +509,189 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Multi-GPU merge of voxel grids (map export): every rank fills its own grid, then ONE
+// kernel compacts it and writes every record straight into the inbox of the rank that owns its
+// key — peer memory over NVLink, no staging buffer and no collective in the data path — and the
+// owner folds its inbox into its (clean) table.  The sums are integers, so the merged grid is
+// bit-identical to inserting all points on one GPU.
+//   count  per warp and destination: occupied slots whose owner is d
+//   scan   one block per destination: exclusive offsets in slot order (deterministic inbox content)
+//   send   re-read keys, read + reset records, store 48-byte records at inbox[owner][rank*cap + offset]
+// ---------------------------------------------------------------------------------
+#define VOX_MAX_WORLD 16
+struct VoxPeers { unsigned long long* inbox[VOX_MAX_WORLD]; unsigned long long* counts[VOX_MAX_WORLD]; };
+
+__device__ __forceinline__ int vox_owner(unsigned long long key, int world) {
+    return (int)((vox_hash(key) >> 40) % (unsigned long long)world);      // high bits: independent of the slot index
+}
+
+__global__ void __launch_bounds__(VC_THREADS)
+voxel_count_dest_kernel(const unsigned long long* __restrict__ acc, long long slots, int world,
+                        unsigned int* __restrict__ warp_counts /* [n_warps][world] */) {
+    const unsigned int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
+    const long long base = wid * VC_PER_WARP;
+    if (base >= slots) return;
+    unsigned int mine = 0;                                       // lane d counts destination d
+#pragma unroll 4
+    for (int j = 0; j < VC_ROUNDS; ++j) {
+        const long long s = base + (long long)j * 32 + lane;
+        const unsigned long long k = s < slots ? __ldcs(acc + (size_t)slots * VOX_REC + s) : VOX_EMPTY;
+        const int owner = k != VOX_EMPTY ? vox_owner(k, world) : -1;
+        for (int d = 0; d < world; ++d) {
+            const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
+            if ((int)lane == d) mine += __popc(m);
+        }
+    }
+    if ((int)lane < world) warp_counts[wid * world + lane] = mine;
+}
+
+__global__ void __launch_bounds__(1024)
+voxel_scan_dest_kernel(const unsigned int* __restrict__ counts, int n, int world, int rank, long long cap,
+                       unsigned long long* __restrict__ offsets /* [n][world] */, VoxPeers peers,
+                       unsigned long long* __restrict__ counters /* [1] += records that did not fit */) {
+    __shared__ unsigned long long carry;
+    __shared__ unsigned long long wsum[32];
+    const int d = blockIdx.x;                                    // one block per destination column
+    if (threadIdx.x == 0) carry = 0ull;
+    __syncthreads();
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < n ? (unsigned long long)counts[(size_t)i * world + d] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long before = carry;
+        for (unsigned int w = 0; w < warp; ++w) before += wsum[w];
+        if (i < n) offsets[(size_t)i * world + d] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long total = carry;
+        if ((long long)total > cap) { atomicAdd(&counters[1], total - (unsigned long long)cap); total = (unsigned long long)cap; }
+        peers.counts[d][rank] = total;                           // peer store: the owner learns how many records we sent
+    }
+}
+
+__global__ void __launch_bounds__(VC_THREADS)
+voxel_send_kernel(unsigned long long* __restrict__ acc, long long slots, const unsigned long long* __restrict__ offsets,
+                  int world, int rank, long long cap, VoxPeers peers) {
+    const unsigned int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
+    const long long base = wid * VC_PER_WARP;
+    if (base >= slots) return;
+    unsigned long long out = (int)lane < world ? offsets[wid * world + lane] : 0ull;    // lane d: next index for destination d
+#pragma unroll 2
+    for (int j = 0; j < VC_ROUNDS; ++j) {
+        const long long s = base + (long long)j * 32 + lane;
+        const unsigned long long k = s < slots ? acc[(size_t)slots * VOX_REC + s] : VOX_EMPTY;
+        const bool occ = k != VOX_EMPTY;
+        const int owner = occ ? vox_owner(k, world) : -1;
+        unsigned long long my_idx = 0;
+        for (int d = 0; d < world; ++d) {
+            const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
+            const unsigned long long start = __shfl_sync(0xffffffffu, out, d);
+            if (owner == d) my_idx = start + __popc(m & ((1u << lane) - 1u));
+            if ((int)lane == d) out += __popc(m);
+        }
+        if (occ) {
+            unsigned long long* rec = acc + (size_t)s * VOX_REC;
+            const unsigned long long sx = rec[1];
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rec + 2);
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(rec + 4);
+            *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2(VOX_EMPTY, 0ull);
+            *reinterpret_cast<ulonglong2*>(rec + 2) = make_ulonglong2(0ull, 0ull);
+            *reinterpret_cast<ulonglong2*>(rec + 4) = make_ulonglong2(0ull, 0ull);
+            acc[(size_t)slots * VOX_REC + s] = VOX_EMPTY;
+            if ((long long)my_idx < cap) {
+                unsigned long long* dst = peers.inbox[owner] + ((size_t)rank * (size_t)cap + my_idx) * 6;   // NVLink stores
+                *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(k, sx);
+                *reinterpret_cast<ulonglong2*>(dst + 2) = a;
+                *reinterpret_cast<ulonglong2*>(dst + 4) = b;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+voxel_merge_kernel(const unsigned long long* __restrict__ inbox, const unsigned long long* __restrict__ counts, int world, long long cap,
+                   unsigned long long* __restrict__ acc, long long slots, unsigned long long* __restrict__ counters) {
+    const int src = blockIdx.y;
+    const long long n = (long long)counts[src];
+    const unsigned long long* seg = inbox + (size_t)src * (size_t)cap * 6;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(seg + i * 6);
+        const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(seg + i * 6 + 2);
+        const ulonglong2 r2 = *reinterpret_cast<const ulonglong2*>(seg + i * 6 + 4);
+        const unsigned long long key = r0.x;
+        unsigned long long slot = vox_hash(key) & (unsigned long long)(slots - 1);
+        bool placed = false;
+        for (int probe = 0; probe < VOX_MAX_PROBE && !placed; ++probe) {
+            unsigned long long* rec = acc + slot * VOX_REC;
+            unsigned long long* kp = acc + (size_t)slots * VOX_REC + slot;
+            unsigned long long cur = *((volatile unsigned long long*)kp);
+            if (cur == VOX_EMPTY) {
+                cur = atomicCAS(kp, VOX_EMPTY, key);
+                if (cur == VOX_EMPTY) cur = key;
+            }
+            if (cur == key) {
+                atomicAdd(rec + 1, r0.y); atomicAdd(rec + 2, r1.x); atomicAdd(rec + 3, r1.y);
+                atomicAdd(rec + 4, r2.x); atomicAdd(rec + 5, r2.y);
+                placed = true;
+            }
+            slot = (slot + 1) & (unsigned long long)(slots - 1);
+        }
+        if (!placed) atomicAdd(&counters[1], r2.x >> 32);
+    }
+}
+
+extern "C" int da3s_voxel_send(da3s_ctx* ctx, int world, int rank, void* const* inbox_ptrs, void* const* count_ptrs,
+                               long long cap, void* stream) {
+    if (!ctx || world < 1 || world > VOX_MAX_WORLD || rank < 0 || rank >= world || !inbox_ptrs || !count_ptrs || cap < 1) return DA3S_EINVAL;
+    if (!ctx->vox_active) return DA3S_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    VoxPeers peers;
+    for (int d = 0; d < VOX_MAX_WORLD; ++d) {
+        peers.inbox[d] = d < world ? (unsigned long long*)inbox_ptrs[d] : nullptr;
+        peers.counts[d] = d < world ? (unsigned long long*)count_ptrs[d] : nullptr;
+        if (d < world && (!peers.inbox[d] || !peers.counts[d])) return DA3S_EINVAL;
+    }
+    const int n_warps = (int)((ctx->vox_slots + VC_PER_WARP - 1) / VC_PER_WARP);
+    const int n_cblocks = (n_warps + VC_THREADS / 32 - 1) / (VC_THREADS / 32);
+    size_t save_top = ctx->ws_top;
+    WS_ALLOC(ctx, unsigned int, warp_counts, (size_t)n_warps * world);
+    WS_ALLOC(ctx, unsigned long long, warp_offsets, (size_t)n_warps * world);
+    voxel_count_dest_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, world, warp_counts);
+    DA3S_LAUNCH_CHECK(ctx);
+    voxel_scan_dest_kernel<<<world, 1024, 0, st>>>(warp_counts, n_warps, world, rank, cap, warp_offsets, peers, ctx->vox_dropped);
+    DA3S_LAUNCH_CHECK(ctx);
+    voxel_send_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_offsets, world, rank, cap, peers);
+    DA3S_LAUNCH_CHECK(ctx);
+    ctx->ws_top = save_top;
+    ctx->vox_clean = false;         // clean again, but the table stays active: the merge inserts into it
+    return DA3S_OK;
+}
+
+extern "C" int da3s_voxel_merge_inbox(da3s_ctx* ctx, const void* inbox, const void* counts, int world, long long cap, void* stream) {
+    if (!ctx || !inbox || !counts || world < 1 || world > VOX_MAX_WORLD || cap < 1) return DA3S_EINVAL;
+    if (!ctx->vox_active) return DA3S_EINVAL;
+    long long want = (cap + 255) / 256, lim = (long long)ctx->sm_count * 8;
+    dim3 grid((unsigned int)(want > lim ? lim : want), (unsigned int)world);
+    voxel_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)inbox, (const unsigned long long*)counts, world, cap,
+                                                               ctx->vox_acc, ctx->vox_slots, ctx->vox_dropped);
+    DA3S_LAUNCH_CHECK(ctx);
+    return DA3S_OK;
+}
+
 extern "C" int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots, void* stream) {
     if (!ctx || table_slots < 1024 || (table_slots & (table_slots - 1)) || table_slots > (1ll << 31)) return DA3S_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;

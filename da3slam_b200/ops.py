@@ -439,12 +439,18 @@ class VoxelGrid:
     """Stage-level handle on the context's hash grid: begin() / insert() / finish() only enqueue
     kernels; read() synchronises and trims the outputs."""
 
-    def __init__(self, device, table_slots: int, max_voxels: int, with_rgb: bool):
+    def __init__(self, device, table_slots: int, max_voxels: int, with_rgb: bool, private_ctx: bool = False):
         assert table_slots & (table_slots - 1) == 0
+        device = torch.device(device)
         self.device = device
         self.table_slots = table_slots
         self.max_voxels = max_voxels
-        self.ctx = context(device, table_slots * 73 + (256 << 20))
+        need = table_slots * 73 + (256 << 20)
+        if private_ctx:                  # its own da3s_ctx (= its own table): several grids on one device
+            with torch.cuda.device(device):
+                self.ctx = Context(device, need)
+        else:
+            self.ctx = context(device, need)
         self.xyz = torch.empty((max_voxels, 3), dtype=torch.float32, device=device)
         self.rgb = torch.empty((max_voxels, 3), dtype=torch.uint8, device=device) if with_rgb else None
         self.count = torch.empty((max_voxels,), dtype=torch.int32, device=device)
@@ -510,6 +516,20 @@ class VoxelGrid:
         rc = self.ctx.lib.da3s_unproject_voxel_jobs(self.ctx.h, _ptr(table), n_frames, H, W, flags, float(conf_thr),
                                                     float(conf_floor or 0.0), float(depth_eps or 0.0), float(voxel), self._st())
         L.check(rc, "da3s_unproject_voxel_jobs")
+
+    def send(self, world, rank, inboxes, counts, cap):
+        """Multi-GPU merge, step 1: compact this rank's table and write every record into the inbox of the rank
+        that owns its key.  inboxes[d] / counts[d]: rank d's [world, cap, 6] int64 inbox and [world] int64 counters
+        as tensors mapped in THIS process (own tensors for d == rank, CUDA-IPC mappings for the peers)."""
+        ip = (C.c_void_p * world)(*[t.data_ptr() for t in inboxes])
+        cp = (C.c_void_p * world)(*[t.data_ptr() for t in counts])
+        rc = self.ctx.lib.da3s_voxel_send(self.ctx.h, world, rank, ip, cp, cap, self._st())
+        L.check(rc, "da3s_voxel_send")
+
+    def merge_inbox(self, inbox, counts, world, cap):
+        """Multi-GPU merge, step 2 (after every rank's send has completed): fold the own inbox into the table."""
+        rc = self.ctx.lib.da3s_voxel_merge_inbox(self.ctx.h, _ptr(inbox), _ptr(counts), world, cap, self._st())
+        L.check(rc, "da3s_voxel_merge_inbox")
 
     def finish(self, voxel):
         rc = self.ctx.lib.da3s_voxel_finish(self.ctx.h, float(voxel), self.max_voxels, _ptr(self.xyz), _ptr(self.rgb),

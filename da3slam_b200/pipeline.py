@@ -140,7 +140,7 @@ class SequencePlan:
     read() synchronises and returns host/trimmed results.  This is one "step" of bench.py."""
 
     def __init__(self, submaps, overlap=1, voxel=0.02, conf_percentile=65.0, unproject_mode="fast", table_slots=None,
-                 max_voxels=None, sample_idx=None, export=True, skip_overlap=True, fuse_export=True, **opt_kw):
+                 max_voxels=None, sample_idx=None, export=True, skip_overlap=True, fuse_export=True, exchange=None, **opt_kw):
         self.submaps = submaps
         self.n = len(submaps)
         self.dev = submaps[0].depth.device
@@ -149,6 +149,9 @@ class SequencePlan:
         self.voxel = float(voxel)
         self.mode = unproject_mode
         self.export = export
+        # exchange: a sharding.VoxelExchange -> the step ends with the multi-GPU merge of the rank-local grids
+        # (each rank keeps the voxels whose key it owns) instead of a local compaction
+        self.exchange = exchange
         # fuse_export: the exported points go straight from the depth maps into the voxel grid (one kernel);
         # False keeps the per-point arrays (self.xyz / self.mask) for callers that want the full cloud
         self.fuse_export = bool(fuse_export) and unproject_mode == "fast"
@@ -227,8 +230,12 @@ class SequencePlan:
             mark("unproject")
             self.grid.insert_jobs(self.voxel_jobs, self.voxel, width=self.W)
             mark("voxel_insert")
-        self.grid.finish(self.voxel)
-        mark("voxel_compact")
+        if self.exchange is not None:
+            self.exchange.merge(self.grid, self.voxel)
+            mark("voxel_merge")
+        else:
+            self.grid.finish(self.voxel)
+            mark("voxel_compact")
 
     def read(self, sort=False):
         out = {"rows": self.rows.cpu().numpy(), "cum": self.cum.cpu().numpy()}

@@ -5,6 +5,11 @@ alike — are independent units, so each rank aligns a contiguous block of the p
 ONLY exchange is one all_gather of the [n_local, 16] float64 Sim(3) rows (128 B per pair,
 latency bound; NCCL over NVLink on GPUs, gloo on CPU for the tests).  The chain accumulation
 (utils/geometry.py:73-119) then runs on every rank on the gathered table.
+
+Global map export: every rank voxel-hashes its own submaps, then
+`VoxelExchange.merge` routes each voxel record to the rank that owns its key.  The transfer is done
+by the compaction kernel itself (da3s_voxel_send: peer stores into CUDA-IPC-mapped inboxes over
+NVLink); torch.distributed only carries the IPC handles once and a barrier per merge.
 """
 from __future__ import annotations
 
@@ -39,3 +44,68 @@ def gather_rows(rows_local: torch.Tensor, n_total: int, group=None) -> torch.Ten
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf, group=group)
     return torch.cat([o[:n] for o, n in zip(out, sizes)], dim=0)
+
+
+class VoxelExchange:
+    """Inboxes for the multi-GPU voxel merge.  One per rank; built once (collective call).
+
+    cap = records any one rank may send to any other one (>= voxels_of_a_rank / world, with slack).
+    local=True: every rank lives in THIS process (several grids on one device — the single-GPU test);
+    call attach_local() with all of them, no process group is used.  Otherwise the inbox storages are
+    shared through CUDA IPC and mapped into every rank of `group`."""
+
+    def __init__(self, device, world: int, rank: int, cap: int, group=None, local: bool = False):
+        self.device, self.world, self.rank, self.cap, self.group = torch.device(device), world, rank, int(cap), group
+        self.inbox = torch.zeros((world, self.cap, 6), dtype=torch.int64, device=self.device)
+        self.counts = torch.zeros((world,), dtype=torch.int64, device=self.device)
+        self.peer_inbox, self.peer_counts = [None] * world, [None] * world
+        self._keep = []
+        self._peer_devices, self._enabled_for = set(), None
+        self.local = bool(local)
+        if world == 1:
+            self.peer_inbox, self.peer_counts = [self.inbox], [self.counts]
+        elif not self.local:
+            self._map_ipc()
+
+    def attach_local(self, peers):
+        """peers: the VoxelExchange of every rank, all in this process."""
+        self.peer_inbox = [p.inbox for p in peers]
+        self.peer_counts = [p.counts for p in peers]
+
+    def _map_ipc(self):
+        mine = (self.inbox.untyped_storage()._share_cuda_(), self.counts.untyped_storage()._share_cuda_())
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        for r, (hi, hc) in enumerate(everyone):
+            if r == self.rank:
+                self.peer_inbox[r], self.peer_counts[r] = self.inbox, self.counts
+                continue
+            # open the handles with OUR device current (first field of the tuple): the mapping is then made for the
+            # device whose kernels will store through it (cudaIpcOpenMemHandle + lazy peer access over NVLink)
+            si = torch.UntypedStorage._new_shared_cuda(self.device.index, *hi[1:])
+            sc = torch.UntypedStorage._new_shared_cuda(self.device.index, *hc[1:])
+            self._keep += [si, sc]
+            self._peer_devices.add(hi[0])
+            # the mapping belongs to the peer's device; only its address is used (by kernels running on OUR device)
+            self.peer_inbox[r] = torch.empty(0, dtype=torch.int64, device=si.device).set_(si).view(self.world, self.cap, 6)
+            self.peer_counts[r] = torch.empty(0, dtype=torch.int64, device=sc.device).set_(sc).view(self.world)
+        dist.barrier(group=self.group)                               # nobody frees a storage before it is mapped
+
+    def send(self, grid):
+        if self._peer_devices and self._enabled_for is not grid.ctx:
+            from . import _lib
+            for d in sorted(self._peer_devices):
+                _lib.check(grid.ctx.lib.da3s_enable_peer_access(grid.ctx.h, d), "da3s_enable_peer_access")
+            self._enabled_for = grid.ctx
+        grid.send(self.world, self.rank, self.peer_inbox, self.peer_counts, self.cap)
+
+    def merge(self, grid, voxel: float):
+        """Collective: after it, `grid.read()` returns this rank's share of the global map (voxels whose key it owns)."""
+        self.send(grid)
+        if self.local and self.world > 1:
+            raise RuntimeError("local exchanges are driven rank by rank: send() all, then merge_inbox() + finish() each")
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)                      # my peer stores have landed
+            dist.barrier(group=self.group)                           # ... and so have everybody else's
+        grid.merge_inbox(self.inbox, self.counts, self.world, self.cap)
+        grid.finish(voxel)

@@ -49,6 +49,9 @@ int da3s_version(void);
 int da3s_last_cuda_error(const da3s_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 unsigned long long da3s_launch_count(const da3s_ctx* ctx);
+/* lets kernels of this context's device address memory of `peer_device` (NVLink peer access); needed once
+ * per peer before da3s_voxel_send is given pointers into that peer's memory */
+int da3s_enable_peer_access(da3s_ctx* ctx, int peer_device);
 
 /* ---- camera table ------------------------------------------------------------- */
 /* One entry per frame, device resident.  Built by da3s_build_cams from the network's
@@ -313,6 +316,20 @@ typedef struct da3s_export_job {
 } da3s_export_job;
 int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* jobs_dev, int n_frames, int H, int W, int flags,
                               float conf_thr, float conf_floor, float depth_eps, float voxel, void* stream);
+/* ---- multi-GPU merge of voxel grids (global map export) -------------------
+ * One rank per GPU fills its own grid (inserts above), then
+ *   da3s_voxel_send         compacts the local table (leaving it clean and still active) and writes every
+ *                           48-byte record {key, sum_qx, sum_qy, sum_qz, (n,sum_r), (sum_g,sum_b)} into the
+ *                           inbox of the rank that owns its key: inbox_ptrs[d] is rank d's inbox
+ *                           [world][cap][6] u64 mapped into this process (peer memory over NVLink, e.g. a
+ *                           CUDA-IPC mapping), count_ptrs[d] its [world] u64 counters; rank r writes
+ *                           segment r and counts[r].  Records beyond `cap` are dropped and reported by finish.
+ *   (the callers synchronise: every rank's send must have completed)
+ *   da3s_voxel_merge_inbox  folds this rank's own inbox into its table; da3s_voxel_finish then emits the
+ *                           rank's share of the global map.  Integer sums => bit-identical to one GPU. */
+int da3s_voxel_send(da3s_ctx* ctx, int world, int rank, void* const* inbox_ptrs /* host array [world] */,
+                    void* const* count_ptrs /* host array [world] */, long long cap, void* stream);
+int da3s_voxel_merge_inbox(da3s_ctx* ctx, const void* inbox, const void* counts, int world, long long cap, void* stream);
 int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxels, float* xyz_out, uint8_t* rgb_out,
                       int32_t* count_out, long long* key_out, unsigned long long* n_voxels,
                       unsigned long long* n_dropped /* nullable: points lost to a full table */, void* stream);

@@ -435,6 +435,61 @@ def test_voxel_insert_jobs_one_launch(cuda):
         assert np.array_equal(xyz.cpu().numpy(), e_xyz) and np.array_equal(col.cpu().numpy(), e_col)
 
 
+def test_voxel_multi_rank_merge_is_bit_exact(cuda):
+    """SURVEY 8e map export: three ranks (three private tables on this one GPU) fill their grids, send every
+    record to the rank that owns its key (da3s_voxel_send writes straight into the owner's inbox) and merge;
+    the union of their shares == the grid of all points on one rank, bit for bit."""
+    from da3slam_b200.sharding import VoxelExchange
+    rng = np.random.default_rng(21)
+    world, voxel = 3, 0.04
+    pts = [rng.normal(0, 0.5, (n, 3)).astype(np.float32) for n in (9000, 14000, 1)]      # the same region: shared voxels
+    rgb = [rng.integers(0, 256, (len(p_), 3), dtype=np.uint8) for p_ in pts]
+    grids = [ops.VoxelGrid(cuda, 1 << 15, 1 << 15, True, private_ctx=True) for _ in range(world)]
+    cap = 1 << 14
+    ex = [VoxelExchange(cuda, world, r, cap, local=True) for r in range(world)]
+    for e in ex:
+        e.attach_local(ex)
+    for r in range(world):
+        grids[r].begin()
+        grids[r].insert(dev_t(pts[r], cuda), dev_t(rgb[r], cuda), None, voxel)
+    for r in range(world):
+        ex[r].send(grids[r])
+    torch.cuda.synchronize()
+    shares = []
+    for r in range(world):
+        grids[r].merge_inbox(ex[r].inbox, ex[r].counts, world, cap)
+        grids[r].finish(voxel)
+        shares.append([t.cpu().numpy() for t in grids[r].read(sort=True)])
+    assert int(sum(int(e.counts.sum()) for e in ex)) >= sum(len(s_[3]) for s_ in shares)
+    key = np.concatenate([s_[3] for s_ in shares])
+    assert len(np.unique(key)) == len(key)                                   # every voxel has exactly one owner
+    order = np.argsort(key)
+    e_xyz, e_col, e_cnt, e_key = sp.voxel_downsample(np.concatenate(pts), voxel, np.concatenate(rgb), None)
+    assert np.array_equal(key[order], e_key)
+    assert np.array_equal(np.concatenate([s_[2] for s_ in shares])[order], e_cnt)
+    assert np.array_equal(np.concatenate([s_[0] for s_ in shares])[order], e_xyz)
+    assert np.array_equal(np.concatenate([s_[1] for s_ in shares])[order], e_col)
+    assert min(len(s_[3]) for s_ in shares) > 0.2 * len(key) / world          # the key hash spreads the voxels
+    for g in grids:
+        g.ctx.close()
+
+
+def test_voxel_merge_across_gpus():
+    """The real thing: one process per GPU, inboxes mapped through CUDA IPC, records stored over NVLink
+    (tests/multi_gpu_voxel_check.py).  Needs two GPUs; profiles/r1_multi_gpu_voxel_merge_2gpu.json is a recorded run."""
+    import json, os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, POINTS="500000")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(here, "multi_gpu_voxel_check.py")], capture_output=True, text=True,
+                       env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    assert json.loads(line)["bit_identical_to_single_gpu"] is True
+
+
 def test_errors_are_loud(cuda):
     with pytest.raises(RuntimeError):
         ops.unproject_filter(torch.zeros(1, 4, 4), None, torch.zeros(1, 200, dtype=torch.uint8))      # CPU tensor
