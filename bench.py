@@ -341,14 +341,36 @@ def gpu_arm(args, w, rank, world):
         for _ in range(k_e2e):
             e2e_step()
         barrier()
-        e2e_s = (time.perf_counter() - t0) / k_e2e
+        serial_s = (time.perf_counter() - t0) / k_e2e
+
+        # the public serving loop: upload of sequence k+1, compute of k and download of k-1 overlap (full-duplex PCIe)
+        from da3slam_b200.pipeline import SequenceStream
+        host_seq = [dict(hp, intrinsics=s_["intrinsics"].cpu().pin_memory(), extrinsics=s_["extrinsics"].cpu().pin_memory())
+                    for hp, s_ in zip(host, subs)]
+        stream = SequenceStream(host_seq, dev, slots=2, overlap=w["overlap"], voxel=w["voxel"], conf_percentile=CONF_PERCENTILE,
+                                table_slots=w["table_slots"] or None, sample_idx=sample_idx, export=w["export"], **opt)
+        k_stream = max(4, min(args.steps, 10))
+        for _ in stream.process([host_seq] * 3):                 # warm-up (also fills the pipeline once)
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        n_out = 0
+        for res in stream.process([host_seq] * k_stream):
+            n_out += 1
+            last_rows = res["rows"]
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / k_stream
+        assert n_out == k_stream and np.array_equal(last_rows, rows0)       # same inputs -> same rows as the resident run
+        h2d, d2h = stream.h2d_bytes, stream.d2h_bytes
         if world > 1:
-            tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            tt = torch.tensor([e2e_s, serial_s], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = float(tt.item())
+            e2e_s, serial_s = float(tt[0].item()), float(tt[1].item())
         e2e = {"value": world * n_pairs / e2e_s, "unit": "submap-pairs/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": k_e2e,
-               "api": "SequencePlan.run on pinned host predictions (torch H2D/D2H on the same stream)"}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": k_stream,
+               "api": "SequenceStream.process on pinned host predictions: 2 slots, upload k+1 | compute k | download k-1 on "
+                      "three streams; every step uploads its inputs and downloads rows + voxel map inside the timed region",
+               "ms_per_step_without_overlap": serial_s * 1e3}
 
     if world > 1:
         dist.destroy_process_group()

@@ -382,7 +382,8 @@ extern "C" int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* j
 //          RESETS the records, so the table is clean for the next begin() without a clearing
 //          pass.  No __syncthreads: the previous block-synchronous version was bound by exposed
 //          DRAM latency (profiles/r1_*: long_scoreboard 70, issue 8 %).
-// Output order = slot order: deterministic for a given table size.
+// Output order = slot order (which of two colliding keys gets the earlier slot depends on the insertion race;
+// the canonical order is ascending key — ops.VoxelGrid.read(sort=True)).
 #define VC_THREADS 256
 #define VC_ROUNDS 16
 #define VC_PER_WARP (32 * VC_ROUNDS)        // 512 slots per warp

@@ -77,14 +77,15 @@ def _ptr(t, name="tensor", dtype=None):
 # ------------------------------------------------------------------------------------------
 # camera table
 # ------------------------------------------------------------------------------------------
-def build_cams(intrinsics: torch.Tensor, extrinsics: torch.Tensor, general_inverse: bool = False) -> torch.Tensor:
-    """[n,3,3] f32, [n,3,4] f32 -> opaque uint8 tensor [n, 200] holding da3s_cam records."""
+def build_cams(intrinsics: torch.Tensor, extrinsics: torch.Tensor, general_inverse: bool = False, out=None) -> torch.Tensor:
+    """[n,3,3] f32, [n,3,4] f32 -> opaque uint8 tensor [n, 200] holding da3s_cam records (`out`: refresh in place)."""
     K = intrinsics.to(torch.float32).contiguous()
     E = extrinsics.to(torch.float32).contiguous()
     n = K.shape[0]
     assert K.shape == (n, 3, 3) and E.shape == (n, 3, 4)
     ctx = context(K.device)
-    cams = torch.empty((n, L.CAM_BYTES), dtype=torch.uint8, device=K.device)
+    cams = out if out is not None else torch.empty((n, L.CAM_BYTES), dtype=torch.uint8, device=K.device)
+    assert cams.shape == (n, L.CAM_BYTES) and cams.dtype == torch.uint8 and cams.is_contiguous()
     rc = ctx.lib.da3s_build_cams(ctx.h, _ptr(K), _ptr(E), n, L.CAM_GENERAL_INV if general_inverse else L.CAM_CLOSED_FORM,
                                  _ptr(cams), _stream(K))
     L.check(rc, "da3s_build_cams")

@@ -243,3 +243,129 @@ class SequencePlan:
             xyz, rgb, cnt, key = self.grid.read(sort=sort)
             out.update(voxel_xyz=xyz, voxel_rgb=rgb, voxel_count=cnt, voxel_key=key)
         return out
+
+
+class SequenceStream:
+    """Serving loop for sequences whose predictions arrive in (pinned) host memory: a few slots, each with its
+    own device buffers and SequencePlan, three streams.  While sequence k is aligned and exported, sequence
+    k+1 is uploaded (host->device) and the results of sequence k-1 are read back (device->host): the PCIe
+    link is full duplex, so a step costs max(upload, compute, download) instead of their sum.
+
+        stream = SequenceStream(example_host_submaps, device, overlap=1, voxel=0.02, ...)
+        for result in stream.process(iterable_of_host_submap_lists):
+            result["rows"], result["voxel_xyz"], ...        # pinned views, valid until the slot is reused
+
+    Host submaps: dicts with depth, conf, intrinsics, extrinsics (+ processed_images), shapes as in the example."""
+
+    class _Slot:
+        pass
+
+    def __init__(self, example, device="cuda", slots=2, general_inverse=False, with_keys=False, **plan_kw):
+        self.dev = torch.device(device)
+        self.with_keys = with_keys                                  # also download the voxel keys (canonical order = ascending key)
+        self.general_inverse = general_inverse
+        self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.slots = []
+        for _ in range(slots):
+            sl = SequenceStream._Slot()
+            sl.subs = [DeviceSubmap.from_prediction(p, self.dev, general_inverse) for p in example]
+            sl.plan = SequencePlan(sl.subs, **plan_kw)
+            n_pairs = sl.plan.n_pairs
+            sl.rows = torch.empty((n_pairs, 16), dtype=torch.float64, pin_memory=True)
+            sl.cum = torch.empty((sl.plan.n, 13), dtype=torch.float64, pin_memory=True)
+            sl.nv = torch.zeros((2,), dtype=torch.int64, pin_memory=True)
+            sl.vox = None
+            if sl.plan.export:
+                g = sl.plan.grid
+                sl.vox = dict(xyz=torch.empty((g.max_voxels, 3), dtype=torch.float32, pin_memory=True),
+                              rgb=torch.empty((g.max_voxels, 3), dtype=torch.uint8, pin_memory=True) if g.rgb is not None else None,
+                              count=torch.empty((g.max_voxels,), dtype=torch.int32, pin_memory=True),
+                              key=torch.empty((g.max_voxels,), dtype=torch.int64, pin_memory=True) if with_keys else None)
+            sl.h2d_done = sl.compute_done = sl.d2h_done = None
+            self.slots.append(sl)
+        torch.cuda.synchronize(self.dev)
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _upload(self, sl, host_subs):
+        with torch.cuda.stream(self.s_in):
+            if sl.compute_done is not None:
+                self.s_in.wait_event(sl.compute_done)               # the previous sequence in this slot has been consumed
+            n = 0
+            for sm, hp in zip(sl.subs, host_subs):
+                for name, dst in (("depth", sm.depth), ("conf", sm.conf), ("intrinsics", sm.intrinsics), ("extrinsics", sm.extrinsics),
+                                  ("processed_images", sm.images)):
+                    if dst is None:
+                        continue
+                    src = hp[name] if isinstance(hp[name], torch.Tensor) else torch.from_numpy(hp[name])
+                    dst.copy_(src, non_blocking=True)
+                    n += dst.numel() * dst.element_size()
+                ops.build_cams(sm.intrinsics, sm.extrinsics, self.general_inverse, out=sm.cams)
+            sl.h2d_done = torch.cuda.Event()
+            sl.h2d_done.record(self.s_in)
+        self.h2d_bytes = n
+
+    def _compute(self, sl):
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(sl.h2d_done)
+        if sl.d2h_done is not None:
+            cur.wait_event(sl.d2h_done)                             # the slot's previous results have left the device
+        sl.plan.run()
+        sl.rows.copy_(sl.plan.rows, non_blocking=True)
+        sl.cum.copy_(sl.plan.cum, non_blocking=True)
+        if sl.plan.export:
+            sl.nv.copy_(sl.plan.grid.nv, non_blocking=True)
+        sl.compute_done = torch.cuda.Event()
+        sl.compute_done.record(cur)
+
+    def _download(self, sl):
+        sl.compute_done.synchronize()                               # host: the result size is known
+        out = {"rows": sl.rows.numpy(), "cum": sl.cum.numpy()}
+        moved = sl.rows.numel() * 8 + sl.cum.numel() * 8
+        if sl.plan.export:
+            nv, dropped = int(sl.nv[0]), int(sl.nv[1])
+            if dropped:
+                raise L.Da3sError(L.ENOMEM, "SequenceStream", f"voxel table full: {dropped} points dropped")
+            g = sl.plan.grid
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(sl.compute_done)
+                sl.vox["xyz"][:nv].copy_(g.xyz[:nv], non_blocking=True)
+                if g.rgb is not None:
+                    sl.vox["rgb"][:nv].copy_(g.rgb[:nv], non_blocking=True)
+                sl.vox["count"][:nv].copy_(g.count[:nv], non_blocking=True)
+                if self.with_keys:
+                    sl.vox["key"][:nv].copy_(g.key[:nv], non_blocking=True)
+                sl.d2h_done = torch.cuda.Event()
+                sl.d2h_done.record(self.s_out)
+            out.update(voxel_xyz=sl.vox["xyz"][:nv], voxel_rgb=sl.vox["rgb"][:nv] if g.rgb is not None else None,
+                       voxel_count=sl.vox["count"][:nv], voxel_key=sl.vox["key"][:nv] if self.with_keys else None, n_voxels=nv)
+            moved += nv * (12 + 4 + (3 if g.rgb is not None else 0) + (8 if self.with_keys else 0)) + 16
+        self.d2h_bytes = moved
+        return out, sl
+
+    def process(self, sequences):
+        """Generator: yields one result dict per input sequence, in order.  A result's pinned arrays are complete
+        when it is yielded and stay valid until `slots` more sequences have been submitted."""
+        it = iter(sequences)
+        pending = []                                                # slots whose compute has been enqueued
+        k = 0
+        nxt = next(it, None)
+        if nxt is not None:
+            self._upload(self.slots[0], nxt)
+        while nxt is not None:
+            sl = self.slots[k % len(self.slots)]
+            following = next(it, None)
+            if following is not None:
+                self._upload(self.slots[(k + 1) % len(self.slots)], following)   # overlaps with the compute below
+            self._compute(sl)
+            pending.append(sl)
+            if len(pending) >= len(self.slots):                     # read back the oldest one while the newest computes
+                out, done = self._download(pending.pop(0))
+                if done.d2h_done is not None:
+                    done.d2h_done.synchronize()
+                yield out
+            nxt, k = following, k + 1
+        while pending:
+            out, done = self._download(pending.pop(0))
+            if done.d2h_done is not None:
+                done.d2h_done.synchronize()
+            yield out

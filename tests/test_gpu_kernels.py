@@ -554,6 +554,31 @@ def test_sequence_plan_end_to_end(cuda):
     assert np.array_equal(out_f["voxel_xyz"].cpu().numpy(), xyz) and np.array_equal(out_f["voxel_rgb"].cpu().numpy(), col)
 
 
+def test_sequence_stream_matches_resident_plan(cuda):
+    """SequenceStream (upload k+1 | compute k | download k-1 on three streams, two slots) returns, for every
+    sequence and in order, exactly what a SequencePlan on resident data returns."""
+    from da3slam_b200.pipeline import SequencePlan, SequenceStream
+    H, W, F, n = 40, 48, 3, 3
+    seqs = [synth.make_sequence(n, F, H, W, overlap=1, seed=500 + i, with_images=True)[0] for i in range(5)]
+    kw = dict(overlap=1, voxel=0.05, conf_percentile=65.0, table_slots=1 << 15, world=1)
+    stream = SequenceStream(seqs[0], cuda, slots=2, with_keys=True, **kw)
+    got = []
+    for res in stream.process(seqs):
+        got.append({k: (np.array(v) if v is not None and not isinstance(v, int) else v) for k, v in res.items()})   # copy: slots are reused
+    assert len(got) == len(seqs)
+    for subs, res in zip(seqs, got):
+        plan = SequencePlan([DeviceSubmap.from_prediction(s_, cuda) for s_ in subs], **kw)
+        plan.run()
+        ref = plan.read(sort=True)                               # canonical order: ascending key (slot order depends on probing races)
+        assert np.array_equal(res["rows"], ref["rows"]) and np.array_equal(res["cum"], ref["cum"])
+        assert res["n_voxels"] == ref["voxel_key"].shape[0]
+        order = np.argsort(res["voxel_key"])
+        assert np.array_equal(res["voxel_key"][order], ref["voxel_key"].cpu().numpy())
+        assert np.array_equal(res["voxel_xyz"][order], ref["voxel_xyz"].cpu().numpy())
+        assert np.array_equal(res["voxel_rgb"][order], ref["voxel_rgb"].cpu().numpy())
+        assert np.array_equal(res["voxel_count"][order], ref["voxel_count"].cpu().numpy())
+
+
 def test_unproject_jobs_equals_flat_launch(cuda):
     rng = np.random.default_rng(12)
     n, H, W = 5, 30, 44
