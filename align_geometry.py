@@ -2,13 +2,18 @@
 positional order and defaults — SURVEY.md section 8b), with every per-pixel computation on
 the B200 through libda3s.so.  ``main_align.py`` imports exactly these names.
 
-What differs from the reference, on purpose:
-  * ``align_two_point_clouds`` / ``_icp`` / ``_umeyama``: the reference searches nearest
-    neighbours (Open3D ICP, align_geometry.py:8-56; KD-tree loop :84-140).  Every call site
-    passes the two clouds of the SAME overlap frame in pixel order (main_align.py:37-44), so
-    this implementation uses the pixel correspondences directly — closed-form Umeyama
-    (:59-82) over all finite pairs, or SE(3) for "icp" — in one fused pass instead of up to
-    30 x M KD-tree queries.  A nearest-neighbour mode is the next item of SURVEY.md 8(f).
+Correspondences of ``align_two_point_clouds`` / ``_icp`` / ``_umeyama`` (module attribute
+``CORRESPONDENCES``, environment variable ``DA3S_CORRESPONDENCES``):
+  * ``"nearest"`` (default): the reference's own semantics — nearest-neighbour search
+    (Open3D ICP, align_geometry.py:8-56; KD-tree Umeyama loop :84-140) — on the GPU
+    (``da3s_icp_points``: uniform-grid exact nearest neighbour + float64 moments + closed form,
+    one launch per iteration, no host round trip).  Open3D is not vendored: parity is against
+    the restatement in oracle/ref_port.py (scipy cKDTree), see oracle/SPEC.md.
+  * ``"pixel"``: every call site passes the two clouds of the SAME overlap frame in pixel order
+    (main_align.py:37-44), so the pixel correspondences can be used directly — closed-form
+    Umeyama (:59-82) over all finite pairs, or SE(3) for "icp" — in one fused pass instead of
+    30 rounds of M nearest-neighbour queries.  Not what the reference computes.
+Also different from the reference, on purpose:
   * the stubs ``align_two_point_clouds_irls`` / ``_turboreg`` (reference :143-159 return
     None) are implemented: Huber-IRLS with unit confidences.
 """
@@ -18,8 +23,18 @@ from typing import List, Tuple
 
 import numpy as np
 
+import os
+
 from da3slam_b200 import _lib as _L
 from da3slam_b200 import host as _host
+
+CORRESPONDENCES = os.environ.get("DA3S_CORRESPONDENCES", "nearest")
+
+
+def _nearest() -> bool:
+    if CORRESPONDENCES not in ("nearest", "pixel"):
+        raise ValueError(f"align_geometry.CORRESPONDENCES must be 'nearest' or 'pixel', got {CORRESPONDENCES!r}")
+    return CORRESPONDENCES == "nearest"
 
 
 def _finite_pairs(source, target):
@@ -39,8 +54,10 @@ def _umeyama_sim3(X: np.ndarray, Y: np.ndarray) -> Tuple[float, np.ndarray, np.n
 
 def align_two_point_clouds_icp(source: np.ndarray, target: np.ndarray, threshold: float = 0.0001,
                                max_iterations: int = 50) -> Tuple[float, np.ndarray, np.ndarray]:
-    """Rigid registration, s == 1.0 (align_geometry.py:8-56).  Pixel correspondences, see the
-    module docstring; `threshold` gates pairs by residual after the first solve."""
+    """Rigid registration, s == 1.0 (align_geometry.py:8-56): point-to-point ICP from the identity with
+    nearest-neighbour correspondences within `threshold` (or the pixel correspondences, module docstring)."""
+    if _nearest():
+        return _host.icp(source, target, threshold, max_iterations, rigid=True)
     src, tgt = _finite_pairs(source, target)
     s, R, t = _host.umeyama(src, tgt, None, _L.UMEYAMA_MEAN)
     # SE(3): keep the rotation, recompute t for unit scale (Kabsch); the rotation of the
@@ -51,7 +68,10 @@ def align_two_point_clouds_icp(source: np.ndarray, target: np.ndarray, threshold
 
 def align_two_point_clouds_umeyama(source: np.ndarray, target: np.ndarray, threshold: float = 0.001,
                                    max_iterations: int = 30) -> Tuple[float, np.ndarray, np.ndarray]:
-    """target ~= s R source + t (align_geometry.py:84-140)."""
+    """target ~= s R source + t (align_geometry.py:84-140): up to `max_iterations` rounds of nearest neighbour
+    (d^2 < threshold^2, fewer than 20 inliers stops) + closed-form Sim(3), composed."""
+    if _nearest():
+        return _host.icp(source, target, threshold, max_iterations, rigid=False)
     src, tgt = _finite_pairs(source, target)
     return _host.umeyama(src, tgt, None, _L.UMEYAMA_MEAN)
 

@@ -20,6 +20,7 @@ CAM_CLOSED_FORM, CAM_GENERAL_INV = 0, 1
 SEL_VALUES, SEL_POSITIVE, SEL_RATIO = 0, 1, 2
 SEL_MEDIAN, SEL_PERCENTILE = 0, 1
 UMEYAMA_WEIGHTED, UMEYAMA_MEAN, UMEYAMA_NORMRATIO = 0, 1, 2
+ICP_SIM3, ICP_RIGID = 0, 1
 ROW_LEN = 16
 
 CAM_BYTES = 8 * 4 + 21 * 8          # sizeof(da3s_cam) = 200
@@ -98,6 +99,7 @@ SIGNATURES = {
     "da3s_voxel_begin": (_I, [_P, _L, _P]),
     "da3s_voxel_insert": (_I, [_P, _P, _P, _P, _L, _F, _P]),
     "da3s_voxel_insert_jobs": (_I, [_P, _P, _I, _L, _I, _F, _P]),
+    "da3s_icp_points": (_I, [_P, _P, _L, _P, _L, _I, _I, _D, _D, _I, _P, _P]),
     "da3s_voxel_send": (_I, [_P, _I, _I, _P, _P, _L, _P]),
     "da3s_voxel_merge_inbox": (_I, [_P, _P, _P, _I, _L, _P]),
     "da3s_unproject_voxel_jobs": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P]),

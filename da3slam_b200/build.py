@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libda3s.so")
-SOURCES = ["api.cu", "unproject.cu", "select.cu", "pair_align.cu", "voxel.cu"]
+SOURCES = ["api.cu", "unproject.cu", "select.cu", "pair_align.cu", "voxel.cu", "icp.cu"]
 HEADERS = ["common.cuh", "sim3_math.cuh", "unproject_frame.cuh", os.path.join("..", "..", "include", "da3s.h")]
 
 NVCC_FLAGS = [

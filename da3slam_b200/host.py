@@ -108,6 +108,17 @@ def umeyama(src, dst, weights=None, variant=L.UMEYAMA_WEIGHTED):
     return _row_to_tuple(ops.umeyama_points(_up(a), _up(b), w, variant))
 
 
+def icp(source, target, threshold, max_iterations, rigid=False):
+    """Nearest-neighbour registration target ~= s R source + t of two unordered clouds [n,3], [m,3]:
+    rigid=False -> align_geometry.py:84-140 (KD-tree Umeyama loop); rigid=True -> Open3D point-to-point ICP
+    (align_geometry.py:29-45, utils/align_geometry_single.py:146-160), s == 1."""
+    a, b = _pts(source), _pts(target)
+    if a.dtype != b.dtype:
+        a, b = a.astype(np.float64), b.astype(np.float64)
+    row = ops.icp_points(_up(a), _up(b), threshold, max_iterations, L.ICP_RIGID if rigid else L.ICP_SIM3)
+    return _row_to_tuple(row)
+
+
 def irls_pixel(point_map1, point_map2, conf1, conf2, min_points=100, max_iterations=20,
                convergence_threshold=1e-6, delta=1.0, compat="reference", indices=None):
     """utils/align.py:111-218.  compat='reference' keeps the reference's behaviour bit for

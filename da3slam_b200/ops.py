@@ -412,6 +412,28 @@ def umeyama_points(src, dst, weights=None, variant=L.UMEYAMA_WEIGHTED, idx_src=N
     return row
 
 
+def icp_points(src, dst, threshold: float, max_iterations: int, mode=L.ICP_SIM3, cell_size=None) -> torch.Tensor:
+    """Nearest-neighbour registration of two UNORDERED clouds src [n,3] -> dst [m,3] (da3s_icp_points):
+    mode ICP_SIM3 = align_geometry.py:84-140, ICP_RIGID = Open3D point-to-point ICP.  Returns the [16] row."""
+    src = src.contiguous()
+    dst = dst.contiguous()
+    assert src.dtype == dst.dtype and src.dtype in (torch.float32, torch.float64)
+    n, m = src.numel() // 3, dst.numel() // 3
+    need = 4 * m * 12 + m * 4 + (64 << 20)
+    ctx = context(src.device, need if need > (1 << 30) else None)
+    row = torch.zeros((L.ROW_LEN,), dtype=torch.float64, device=src.device)
+    if cell_size is None:
+        # grid cells of about twice the target's point spacing (a surface sampled by m points over its bounding box)
+        d = dst.view(-1, 3)
+        fin = torch.isfinite(d).all(dim=1)
+        ext = (d[fin].amax(dim=0) - d[fin].amin(dim=0)).max().item() if bool(fin.any()) else 0.0
+        cell_size = 2.0 * ext / max(1.0, math.sqrt(m)) if ext > 0 else 0.0
+    rc = ctx.lib.da3s_icp_points(ctx.h, _ptr(src), n, _ptr(dst), m, int(src.dtype == torch.float64), int(mode), float(threshold),
+                                 float(cell_size), int(max_iterations), _ptr(row), _stream(src))
+    L.check(rc, "da3s_icp_points")
+    return row
+
+
 def irls_points(src, dst, conf_src, conf_dst, idx_src=None, idx_dst=None, delta=1.0, max_iterations=20, tol=1e-6):
     src = src.contiguous()
     dst = dst.contiguous()

@@ -316,6 +316,21 @@ typedef struct da3s_export_job {
 } da3s_export_job;
 int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* jobs_dev, int n_frames, int H, int W, int flags,
                               float conf_thr, float conf_floor, float depth_eps, float voxel, void* stream);
+/* ---- nearest-neighbour registration of two unordered clouds -----------
+ * DA3S_ICP_SIM3  replaces align_geometry.py:84-140 (align_two_point_clouds_umeyama: KD-tree nearest
+ *                neighbour, d^2 < thr^2, fewer than 20 inliers stops, _umeyama_sim3 per iteration, composed);
+ * DA3S_ICP_RIGID replaces the Open3D registration_icp calls at align_geometry.py:29-45 and
+ *                utils/align_geometry_single.py:146-160 (point-to-point, s == 1, relative fitness / rmse 1e-6).
+ * src [n_src,3], dst [n_dst,3] float32 or float64 device arrays; rows with a non-finite coordinate are
+ * ignored (:94-95).  Result row as DA3S_ROW_* (NVALID = inliers of the last evaluation, ITERS = updates
+ * applied, STATUS 1 = the first evaluation already had too few inliers: identity returned).
+ * cell_size: edge of the search grid's cells, 0 = threshold; pass about twice the point spacing of `dst`
+ * when the threshold is much larger than that (the search walks shells of cells and stops early). */
+#define DA3S_ICP_SIM3  0
+#define DA3S_ICP_RIGID 1
+int da3s_icp_points(da3s_ctx* ctx, const void* src, long long n_src, const void* dst, long long n_dst, int points_f64,
+                    int mode, double threshold, double cell_size, int max_iterations, double* sim3_row, void* stream);
+
 /* ---- multi-GPU merge of voxel grids (global map export) -------------------
  * One rank per GPU fills its own grid (inserts above), then
  *   da3s_voxel_send         compacts the local table (leaving it clean and still active) and writes every

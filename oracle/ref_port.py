@@ -445,6 +445,52 @@ def umeyama_icp_kdtree(source, target, threshold=0.001, max_iterations=30):
     return float(s_c), R_c, t_c
 
 
+def icp_point_to_point_kdtree(source, target, threshold=0.0001, max_iterations=50):
+    """C — Open3D registration_icp(TransformationEstimationPointToPoint(), ICPConvergenceCriteria(max_iteration))
+    as called at align_geometry.py:29-45 / utils/align_geometry_single.py:146-160.  Open3D is not vendored and not
+    installed: PARITY UNPINNED.  Restated from its published algorithm (pipelines/registration/Registration.cpp):
+    evaluate correspondences (nearest neighbour within `threshold`), then up to max_iteration times
+    {Kabsch update without scale on the correspondences, apply, re-evaluate, stop when |d fitness| < 1e-6 and
+    |d inlier_rmse| < 1e-6}.  Returns (1.0, R, t)."""
+    from scipy.spatial import cKDTree
+    src = np.asarray(source, np.float64)
+    tgt = np.asarray(target, np.float64)
+    src = src[np.isfinite(src).all(axis=1)]
+    tgt = tgt[np.isfinite(tgt).all(axis=1)]
+    tree = cKDTree(tgt)
+    R, t = np.eye(3), np.zeros(3)
+
+    def evaluate(R, t):
+        w = src @ R.T + t
+        dist, idx = tree.query(w, k=1)
+        inl = (dist * dist) < threshold * threshold
+        n = int(inl.sum())
+        fit = n / max(len(src), 1)
+        rmse = float(np.sqrt((dist[inl] ** 2).sum() / n)) if n else 0.0
+        return w, idx, inl, fit, rmse
+
+    w, idx, inl, fit, rmse = evaluate(R, t)
+    for _ in range(max_iterations):
+        if inl.sum() < 1:
+            break
+        X, Y = w[inl], tgt[idx[inl]]
+        mx, my = X.mean(0), Y.mean(0)
+        cov = (Y - my).T @ (X - mx) / len(X)
+        U, D, Vt = np.linalg.svd(cov)
+        S = np.eye(3)
+        if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+            S[2, 2] = -1.0
+        Ru = U @ S @ Vt
+        tu = my - Ru @ mx
+        R, t = Ru @ R, Ru @ t + tu
+        w, idx, inl, fit2, rmse2 = evaluate(R, t)
+        stop = abs(fit - fit2) < 1e-6 and abs(rmse - rmse2) < 1e-6
+        fit, rmse = fit2, rmse2
+        if stop:
+            break
+    return 1.0, R, t
+
+
 # --------------------------------------------------------------------------
 # P / V — viewer-side filtering (viewer.py:198-234, :317-356;
 #          utils/viser_server.py:107-108, :182-186)

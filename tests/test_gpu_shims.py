@@ -79,9 +79,13 @@ def test_umeyama_and_irls_shims(golden, cuda):
     close_sim3(ua.align_two_point_clouds_umeyama(g["pm1"], g["pm2"]), float(g["N_s"]), g["N_R"], g["N_t"])
     close_sim3(ua.align_two_point_clouds(g["pm1"], g["pm2"]), float(g["Napi_s"]), g["Napi_R"], g["Napi_t"])
     # pixel-correspondence registration: exact data -> exact recovery
-    close_sim3(ag.align_two_point_clouds_umeyama(g["src"], g["dst"]), float(g["U_s"]), g["U_R"], g["U_t"])
-    s, R, t = ag.align_two_point_clouds_icp(g["src"], g["dst"])
-    assert s == 1.0 and rel_err(R, g["U_R"]) < REL
+    ag.CORRESPONDENCES = "pixel"
+    try:
+        close_sim3(ag.align_two_point_clouds_umeyama(g["src"], g["dst"]), float(g["U_s"]), g["U_R"], g["U_t"])
+        s, R, t = ag.align_two_point_clouds_icp(g["src"], g["dst"])
+        assert s == 1.0 and rel_err(R, g["U_R"]) < REL
+    finally:
+        ag.CORRESPONDENCES = "nearest"
     gi = golden("irls")
     for tag, (a1, a2) in {"same": (gi["c1"], gi["c1"]), "indep": (gi["c1"], gi["c2"])}.items():
         for seed in (0, 1):
@@ -183,3 +187,38 @@ def test_viewer_against_restated_reference(cuda):
     assert 0 < len(v.visible_points()[0]) < len(pts)
     v.clear()
     assert v.total_points == 0 and len(v.visible_points()[0]) == 0
+
+
+@pytest.mark.gpu
+def test_nearest_neighbour_registration_matches_restated_reference(cuda):
+    """align_geometry.align_two_point_clouds_umeyama (KD-tree Umeyama loop, :84-140) and _icp (Open3D point-to-point
+    ICP, :8-56) in their default nearest-neighbour mode vs the cKDTree restatements in oracle/ref_port.py
+    (Open3D is not vendored: parity unpinned).  Unordered clouds of different sizes, a small Sim(3) / SE(3) apart."""
+    import align_geometry as ag
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(31)
+    n = 20000
+    u, v = rng.random(n), rng.random(n)
+    surf = np.stack([2 * u - 1, 1.5 * v - 0.75, 1.5 + 0.3 * np.sin(3 * u) * np.cos(2 * v)], axis=1)
+    tgt = surf + rng.normal(0, 2e-4, surf.shape)
+    R0 = Rotation.from_rotvec([0.004, -0.003, 0.005]).as_matrix()
+    for rigid, s0, thr, iters in ((False, 1.004, 0.02, 12), (True, 1.0, 0.05, 20)):
+        t0 = np.array([0.004, -0.003, 0.002])
+        src = ((surf[rng.permutation(n)[: n - 3000]] - t0) @ R0) / s0          # tgt ~= s0 R0 src + t0, shuffled and shorter
+        src[5] = np.nan                                                          # rows with a non-finite coordinate are ignored
+        for dtype in (np.float64, np.float32):
+            a, b = src.astype(dtype), tgt.astype(dtype)
+            if rigid:
+                got = ag.align_two_point_clouds_icp(a, b, thr, iters)
+                want = rp.icp_point_to_point_kdtree(a, b, thr, iters)
+                assert got[0] == 1.0
+            else:
+                got = ag.align_two_point_clouds_umeyama(a, b, thr, iters)
+                want = rp.umeyama_icp_kdtree(a, b, thr, iters)
+            # float32 input: the reference keeps the matched target points in float32 (Y = target[idxs[mask]], :129), so
+            # _umeyama_sim3's Y.mean / Y - mu_y run in float32 (observed 5e-6 on t); the kernel accumulates in float64
+            close_sim3(got, want[0], want[1], want[2], tol=REL if dtype == np.float64 else 2e-5)
+            assert abs(got[0] - s0) < 2e-3 and np.abs(got[2] - t0).max() < 5e-3            # and it actually registers
+    # nothing within the threshold: the reference breaks out of its loop and returns the identity (:124)
+    s, R, t = ag.align_two_point_clouds_umeyama(src.astype(np.float64) + 5.0, tgt, 0.001, 5)
+    assert s == 1.0 and np.array_equal(R, np.eye(3)) and np.array_equal(t, np.zeros(3))

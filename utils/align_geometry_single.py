@@ -56,8 +56,8 @@ def extract_single_overlap_point_cloud(prev_chunk_prediction, cur_chunk_predicti
 
 def align_two_point_clouds_icp(source: np.ndarray, target: np.ndarray, threshold: float, max_iterations: int,
                                verbose: bool = True) -> Tuple[float, np.ndarray, np.ndarray]:
-    """target ~= R source + t, s == 1 (:126-180).  Pixel correspondences instead of Open3D's
-    nearest-neighbour search — see align_geometry.py's module docstring."""
+    """target ~= R source + t, s == 1 (:126-180): point-to-point ICP; correspondences as selected by
+    align_geometry.CORRESPONDENCES (nearest neighbour by default, as Open3D does)."""
     import align_geometry as _ag
     n_src, n_tgt = source.shape[0], target.shape[0]
     s, R, t = _ag.align_two_point_clouds_icp(source, target, threshold, max_iterations)
