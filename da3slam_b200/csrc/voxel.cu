@@ -405,6 +405,7 @@ voxel_count_kernel(const unsigned long long* __restrict__ acc, long long slots, 
     if (lane == 0) warp_counts[wid] = c;
 }
 
+#define VS_ITEMS 8                          // counts per thread and round: 8192 per round of the single scan block
 __global__ void __launch_bounds__(1024)
 voxel_scan_kernel(const unsigned int* __restrict__ counts, int n, unsigned long long* __restrict__ offsets,
                   unsigned long long* __restrict__ counters) {
@@ -413,9 +414,12 @@ voxel_scan_kernel(const unsigned int* __restrict__ counts, int n, unsigned long 
     if (threadIdx.x == 0) carry = 0ull;
     __syncthreads();
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
-        const unsigned long long v = i < n ? (unsigned long long)counts[i] : 0ull;
+    for (int base = 0; base < n; base += 1024 * VS_ITEMS) {
+        const int i0 = base + threadIdx.x * VS_ITEMS;
+        unsigned int c[VS_ITEMS];
+        unsigned long long v = 0ull;
+#pragma unroll
+        for (int k = 0; k < VS_ITEMS; ++k) { c[k] = (i0 + k < n) ? counts[i0 + k] : 0u; v += c[k]; }
         unsigned long long incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -426,7 +430,9 @@ voxel_scan_kernel(const unsigned int* __restrict__ counts, int n, unsigned long 
         __syncthreads();
         unsigned long long before = carry;
         for (unsigned int w = 0; w < warp; ++w) before += wsum[w];
-        if (i < n) offsets[i] = before + incl - v;
+        unsigned long long run = before + incl - v;
+#pragma unroll
+        for (int k = 0; k < VS_ITEMS; ++k) { if (i0 + k < n) offsets[i0 + k] = run; run += c[k]; }
         __syncthreads();
         if (threadIdx.x == 1023) carry = before + incl;
         __syncthreads();
