@@ -18,6 +18,10 @@ from utils.align_geometry_single import (estimate_depth_scale, get_aligned_chunk
                                          image_to_chw01)
 
 
+def _say(msg: str) -> None:
+    print(f"[solver] {msg}")
+
+
 class SLAMSolver:
     def __init__(self, image_dir, config):
         self.config = config
@@ -35,53 +39,46 @@ class SLAMSolver:
 
     def load_model(self):
         """solver.py:49-67: cuda | mps | cpu, DepthAnything3.from_pretrained(Weights.DA3)."""
-        self.device = "cuda" if torch.cuda.is_available() else "mps" if torch.backends.mps.is_available() else "cpu"
-        print(f"Using device: {self.device}")
-        try:
-            from depth_anything_3.api import DepthAnything3
-            model_path = self.config["Weights"]["DA3"]
-            print(f"Loading DA3 model from {model_path}...")
-            self.model = DepthAnything3.from_pretrained(model_path).to(self.device)
-            self.model.eval()
-            print("Model loaded successfully")
-        except ImportError as e:
-            print(f"Failed to load DA3 model: {e}")
-            raise
-        except Exception as e:
-            print(f"Error loading model: {e}")
-            raise
+        if torch.cuda.is_available():
+            self.device = "cuda"
+        else:
+            self.device = "mps" if torch.backends.mps.is_available() else "cpu"
+        _say(f"network device: {self.device}")
+        from depth_anything_3.api import DepthAnything3        # the reference's network, not part of this path
+        weights = self.config["Weights"]["DA3"]
+        self.model = DepthAnything3.from_pretrained(weights).to(self.device).eval()
+        _say(f"DA3 weights loaded from {weights}")
 
     def init_viewer(self):
         """solver.py:69-78."""
-        port = self.config["Model"]["port"]
         try:
             from viewer import SLAMViewer
-            self.viewer = SLAMViewer(port=port)
-            print(f"Viewer initialized on port {port}")
-        except ImportError as e:
-            print(f"Failed to initialize viewer: {e}")
+        except ImportError as err:                              # viser missing: run headless
+            _say(f"no viewer ({err})")
             self.viewer = None
+            return
+        self.viewer = SLAMViewer(port=self.config["Model"]["port"])
 
     def update_buffer_after_chunk_processed(self):
         """Drop chunk - overlap frames so the next chunk starts on the overlap frame (solver.py:80-85)."""
-        if len(self.frame_buffer) > self.overlap_size:
-            for _ in range(self.chunk_size - self.overlap_size):
-                if self.frame_buffer:
-                    self.frame_buffer.popleft()
+        if len(self.frame_buffer) <= self.overlap_size:
+            return
+        drop = min(self.chunk_size - self.overlap_size, len(self.frame_buffer))
+        for _ in range(drop):
+            self.frame_buffer.popleft()
 
     def update_viewer(self, chunk_prediction: Dict):
         """Every frame of the chunk (overlap frame included, as the reference does) with its global
         extrinsic (solver.py:87-114)."""
         if self.viewer is None:
             return
-        extrinsics_global = chunk_prediction.get("extrinsics_global", None)
-        if extrinsics_global is None:
-            print("warn: no extrinsics_global; if is not the first chunk then error")
-            extrinsics_global = chunk_prediction["extrinsics"]
-        for i in range(len(chunk_prediction["image_paths"])):
-            self.viewer.add_frame(image=image_to_chw01(chunk_prediction, i), depth=chunk_prediction["depth"][i],
-                                  conf=chunk_prediction["conf"][i], extrinsic=extrinsics_global[i],
-                                  intrinsic=chunk_prediction["intrinsics"][i])
+        poses = chunk_prediction.get("extrinsics_global")
+        if poses is None:                                       # only legitimate for the first chunk
+            _say("chunk has no global extrinsics yet: showing it in its local frame")
+            poses = chunk_prediction["extrinsics"]
+        for i, _path in enumerate(chunk_prediction["image_paths"]):
+            self.viewer.add_frame(image_to_chw01(chunk_prediction, i), chunk_prediction["depth"][i], chunk_prediction["conf"][i],
+                                  poses[i], chunk_prediction["intrinsics"][i])
 
     def process_chunk_alignment(self, prev_chunk_prediction: Dict, cur_chunk_prediction: Dict) -> Tuple[float, np.ndarray, np.ndarray]:
         """solver.py:116-153: depth scale (mutates cur depth), overlap registration, extrinsics chain."""
@@ -97,14 +94,14 @@ class SLAMSolver:
 
     def run_single_chunk_prediction(self, chunk_image_paths: List[str]) -> Dict:
         """One network call; the Prediction fields the hot path consumes (solver.py:155-177)."""
-        print(f"  Predict single chunk with {len(chunk_image_paths)} images through da3...")
+        _say(f"chunk {self.chunk_count}: network inference on {len(chunk_image_paths)} frames")
         if torch.cuda.is_available():
             torch.cuda.empty_cache()
         with torch.no_grad():
-            prediction = self.model.inference(image=chunk_image_paths, process_res_method="upper_bound_resize")
-        return {"chunk_idx": self.chunk_count, "image_paths": chunk_image_paths,
-                "processed_images": prediction.processed_images, "depth": prediction.depth, "conf": prediction.conf,
-                "extrinsics": prediction.extrinsics, "intrinsics": prediction.intrinsics}
+            pred = self.model.inference(image=chunk_image_paths, process_res_method="upper_bound_resize")
+        out = {name: getattr(pred, name) for name in ("processed_images", "depth", "conf", "extrinsics", "intrinsics")}
+        out.update(chunk_idx=self.chunk_count, image_paths=chunk_image_paths)
+        return out
 
     def load_chunk_image_paths(self) -> List[str]:
         return list(self.frame_buffer)[:self.chunk_size]
@@ -117,8 +114,6 @@ class SLAMSolver:
         self.frame_buffer.append(image_path)
         if not self.should_run_chunk_prediction():
             return
-        print("=" * 50)
-        print(f"\n  Processing chunk {self.chunk_count}...")
         cur = self.run_single_chunk_prediction(self.load_chunk_image_paths())
         self.chunk_prediction_list.append(cur)
         if self.chunk_count == 0:
@@ -129,20 +124,14 @@ class SLAMSolver:
         self.update_viewer(cur)
         self.update_buffer_after_chunk_processed()
         self.chunk_count += 1
-        time.sleep(self.config["Model"]["sleep_between_chunk"])
-        print("  Sleep for observation")
-        print("=" * 50)
+        time.sleep(self.config["Model"]["sleep_between_chunk"])   # the reference pauses so the viewer can be watched
 
     def run(self):
         """solver.py:230-246."""
-        print("=" * 50)
-        print("Starting DA3-SLAM ...")
-        print("=" * 50)
-        image_paths = load_image(self.image_dir)
-        if not image_paths:
-            print(f"Warning: No images found in {self.image_dir}")
+        frames = load_image(self.image_dir)
+        if not frames:
+            _say(f"nothing to do: {self.image_dir} holds no images")
             return
-        for img_path in extract_keyframe(image_paths, self.config["Model"]["keyframe_interval"]):
-            self.process_frame(img_path)
-        print("=" * 50)
-        print("SLAM process completed!")
+        for path in extract_keyframe(frames, self.config["Model"]["keyframe_interval"]):
+            self.process_frame(path)
+        _say(f"done: {self.chunk_count} chunks")
