@@ -828,16 +828,19 @@ __global__ void ransac_hyp_kernel(RansacArgs a) {
 }
 
 #define RS_THREADS 256
-#define RS_SUB 1024                         // correspondences staged per shared-memory sub-tile
+#define RS_SUB 512                          // correspondences staged per shared-memory sub-tile
 #define RS_HPT 4                            // hypotheses per thread -> 1024 per launch slice
 
 // Threads own hypotheses (coefficients in registers), points are broadcast from shared
-// memory: the inner loop is 15 FFMA/FADD/FMUL + compare + add per (point, hypothesis), with
-// two LDS.128 per point amortised over RS_HPT hypotheses.
-__global__ void __launch_bounds__(RS_THREADS)
+// memory.  Two hypotheses share every arithmetic instruction: sm_100's packed float32 pipe
+// (FFMA2 / FADD2 / FMUL2 on register pairs, each half an ordinary IEEE operation, so SPEC 4's
+// fma chain is reproduced bit for bit) evaluates the residual of a point under a PAIR of
+// hypotheses in 15 instructions; the point is stored duplicated (v, v) so that one LDS.128
+// delivers two broadcast operands.  Per (point, hypothesis): 7.5 FP + compare + add + 0.75 LDS.
+__global__ void __launch_bounds__(RS_THREADS, 2)
 ransac_score_kernel(RansacArgs a) {
     __shared__ FrameConst fc;
-    __shared__ float4 pts[RS_SUB][2];       // (x0,x1,x2,y0) (y1,y2,-,-)
+    __shared__ float4 pts[RS_SUB][3];       // (x0,x0,x1,x1) (x2,x2,-y0,-y0) (-y1,-y1,-y2,-y2)
     const int pair = blockIdx.y;
     const da3s_pair pr = a.pairs[pair];
     const int frame = blockIdx.x / a.tiles_per_frame;
@@ -845,7 +848,7 @@ ransac_score_kernel(RansacArgs a) {
     if (threadIdx.x == 0) frame_const_basic(fc, pr, frame, a.thr, a.dscale, pair);
     __syncthreads();
 
-    float A[RS_HPT][12];
+    float2 A[RS_HPT / 2][12];               // .x: hypothesis 2q, .y: hypothesis 2q + 1
     int cnt[RS_HPT];
     bool hok[RS_HPT];
 #pragma unroll
@@ -856,9 +859,10 @@ ransac_score_kernel(RansacArgs a) {
         const float* hA = a.hyp_A + ((size_t)pair * a.n_hyp + (hok[m] ? h : 0)) * 9;
         const float* ht = a.hyp_t + ((size_t)pair * a.n_hyp + (hok[m] ? h : 0)) * 3;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) A[m][k] = hA[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) A[m][9 + k] = ht[k];
+        for (int k = 0; k < 12; ++k) {
+            const float c = k < 9 ? hA[k] : ht[k - 9];
+            if (m & 1) A[m >> 1][k].y = c; else A[m >> 1][k].x = c;
+        }
     }
 
     const size_t foff = (size_t)frame * (size_t)a.P;
@@ -881,18 +885,28 @@ ransac_score_kernel(RansacArgs a) {
                                         ldg_stream1(pr.depth_b + foff + pix), ldg_stream1(pr.conf_b + foff + pix), x, y, dbs);
                 if (keep) ransac_points(fc, a.world, x, y, xs, ys);
             }
-            pts[slot][0] = make_float4(xs[0], xs[1], xs[2], ys[0]);
-            pts[slot][1] = make_float4(ys[1], ys[2], 0.0f, 0.0f);
+            pts[slot][0] = make_float4(xs[0], xs[0], xs[1], xs[1]);
+            pts[slot][1] = make_float4(xs[2], xs[2], -ys[0], -ys[0]);      // d = p - y  ==  p + (-y), exactly
+            pts[slot][2] = make_float4(-ys[1], -ys[1], -ys[2], -ys[2]);
         }
         __syncthreads();
         long long rem = p_end - sb;
         const int n_here = rem < RS_SUB ? (int)rem : RS_SUB;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < n_here; ++i) {
-            const float4 p0 = pts[i][0], p1 = pts[i][1];
-            const float x[3] = {p0.x, p0.y, p0.z}, y[3] = {p0.w, p1.x, p1.y};
+            const float4 p0 = pts[i][0], p1 = pts[i][1], p2 = pts[i][2];
+            const float2 X0 = make_float2(p0.x, p0.y), X1 = make_float2(p0.z, p0.w), X2 = make_float2(p1.x, p1.y);
+            const float2 N0 = make_float2(p1.z, p1.w), N1 = make_float2(p2.x, p2.y), N2 = make_float2(p2.z, p2.w);
 #pragma unroll
-            for (int m = 0; m < RS_HPT; ++m) cnt[m] += (residual2_f32(A[m], x, y) < a.thr2) ? 1 : 0;
+            for (int q = 0; q < RS_HPT / 2; ++q) {
+                // residual2_f32 (SPEC 4) for two hypotheses at once
+                const float2 d0 = __fadd2_rn(__ffma2_rn(A[q][0], X0, __ffma2_rn(A[q][1], X1, __ffma2_rn(A[q][2], X2, A[q][9]))), N0);
+                const float2 d1 = __fadd2_rn(__ffma2_rn(A[q][3], X0, __ffma2_rn(A[q][4], X1, __ffma2_rn(A[q][5], X2, A[q][10]))), N1);
+                const float2 d2 = __fadd2_rn(__ffma2_rn(A[q][6], X0, __ffma2_rn(A[q][7], X1, __ffma2_rn(A[q][8], X2, A[q][11]))), N2);
+                const float2 r2 = __ffma2_rn(d0, d0, __ffma2_rn(d1, d1, __fmul2_rn(d2, d2)));
+                cnt[2 * q] += (r2.x < a.thr2) ? 1 : 0;
+                cnt[2 * q + 1] += (r2.y < a.thr2) ? 1 : 0;
+            }
         }
         __syncthreads();
     }
