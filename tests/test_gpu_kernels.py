@@ -579,6 +579,60 @@ def test_sequence_stream_matches_resident_plan(cuda):
         assert np.array_equal(res["voxel_count"][order], ref["voxel_count"].cpu().numpy())
 
 
+def test_full_size_properties(cuda):
+    """BASELINE-size frames (518 x 518, 268 324 correspondences per pair), where the oracle would take minutes:
+    size-independent properties instead — ground-truth recovery, bit-identical rows under re-sharding, Sim(3)
+    equivariance under an exact power-of-two depth scaling, exact order statistics against a full sort, and
+    conservation of points through the voxel grid (fused and two-kernel export)."""
+    from da3slam_b200.pipeline import SequencePlan, pair_entry
+    H = W = 518
+    subs, gt = synth.make_sequence_device(4, 3, H, W, overlap=1, seed=4321, with_images=True, device=cuda)
+    dsubs = [DeviceSubmap.from_prediction(s_, cuda) for s_ in subs]
+    entries = [pair_entry(dsubs[k], dsubs[k + 1], 1) for k in range(3)]
+    opts = L.default_opts(world=1)
+    rows, aux, _ = ops.align_pairs(ops.make_pairs(entries, cuda), 3, 1, H, W, opts, want_aux=True)
+    r = rows.cpu().numpy()
+    for k in range(3):                                           # (1) the estimate recovers the generating Sim(3)
+        assert r[k, 15] == 0 and abs(r[k, 0] - gt[k][0]) < 1e-3 * gt[k][0]
+        assert np.abs(r[k, 1:10].reshape(3, 3) - gt[k][1]).max() < 1e-3
+    for k in range(3):                                           # (2) one pair alone == the same pair inside the batch
+        alone, _, _ = ops.align_pairs(ops.make_pairs(entries[k:k + 1], cuda), 1, 1, H, W, opts)
+        assert np.array_equal(alone.cpu().numpy()[0], r[k])
+    # (3) camera-frame alignment, source depths x 2 (exact in float32): every source point doubles exactly, so s
+    #     halves, R and t stay (up to the rounding of the float32 micro-batches, far inside the 1e-6 contract)
+    cam = L.default_opts(world=0)
+    scaled = DeviceSubmap(dsubs[1].depth * 2.0, dsubs[1].conf, dsubs[1].cams, dsubs[1].intrinsics, dsubs[1].extrinsics, dsubs[1].images)
+    r1, _, _ = ops.align_pairs(ops.make_pairs(entries[:1], cuda), 1, 1, H, W, cam)
+    r2, _, _ = ops.align_pairs(ops.make_pairs([pair_entry(dsubs[0], scaled, 1)], cuda), 1, 1, H, W, cam)
+    r1, r2 = r1.cpu().numpy()[0], r2.cpu().numpy()[0]
+    assert abs(2.0 * r2[0] - r1[0]) <= REL * r1[0] and np.abs(r2[1:13] - r1[1:13]).max() <= REL
+    assert r2[13] == r1[13] == r[0, 13]                         # the same correspondences were kept
+    # (4) exact median threshold of a full frame against a full sort (numpy >= 2 float32 arithmetic, utils/align.py:140-142)
+    cA, cB = dsubs[0].conf[-1].flatten(), dsubs[1].conf[0].flatten()
+    med = []
+    for c in (cA, cB):
+        srt = torch.sort(c).values
+        n = srt.numel()
+        med.append(((srt[n // 2 - 1] + srt[n // 2]) / 2.0) if n % 2 == 0 else srt[n // 2])
+    want_thr = (torch.minimum(med[0], med[1]) * torch.tensor(0.1, dtype=torch.float32, device=cuda)).item()
+    assert np.float32(aux.cpu().numpy()[0, 0]) == np.float32(want_thr)
+    assert r[0, 13] == int(((cA > want_thr) & (cB > want_thr) & (dsubs[0].depth[-1].flatten() > 1e-6)
+                            & (dsubs[1].depth[0].flatten() > 1e-6)).sum().item())
+    # (5) every kept point lands in exactly one voxel: counts sum to the kept points; fused == two-kernel export
+    kw = dict(overlap=1, voxel=0.02, conf_percentile=65.0, table_slots=1 << 22, world=1)
+    two = SequencePlan(dsubs, fuse_export=False, **kw)
+    two.run()
+    out2 = two.read(sort=True)
+    kept = sum(int(m_.sum().item()) for m_ in two.mask)
+    assert int(out2["voxel_count"].sum().item()) == kept and kept > 0
+    fused = SequencePlan(dsubs, fuse_export=True, **kw)
+    fused.run()
+    outf = fused.read(sort=True)
+    for name in ("voxel_key", "voxel_count", "voxel_xyz", "voxel_rgb"):
+        assert torch.equal(outf[name], out2[name]), name
+    assert np.array_equal(outf["rows"], out2["rows"]) and np.array_equal(out2["rows"], r)
+
+
 def test_unproject_jobs_equals_flat_launch(cuda):
     rng = np.random.default_rng(12)
     n, H, W = 5, 30, 44
