@@ -100,8 +100,8 @@ __device__ __forceinline__ void stg_stream(float4* p, float4 v) {
 
 // order-preserving float32 <-> uint32 key (total order: -inf < ... < -0 < +0 < ... < +inf < NaN+)
 __device__ __forceinline__ unsigned int f32_to_key(float f) {
-    unsigned int u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    const unsigned int u = __float_as_uint(f);
+    return u ^ ((unsigned int)((int)u >> 31) | 0x80000000u);        // negative: ~u, else u | sign bit (two instructions)
 }
 __device__ __forceinline__ float key_to_f32(unsigned int k) {
     unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;

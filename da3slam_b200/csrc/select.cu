@@ -258,27 +258,34 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
     SelWork* w = work + seg_id;
     if (w->done) return;                                             // block-uniform
     const unsigned int lo = w->lo_key, hi = w->hi_key;
-    const bool lo_ne_hi = hi != lo;
-    const unsigned int span = lo_ne_hi ? hi - lo - 1u : 0u;          // lo < k < hi  <=>  (k - lo - 1) < span  (unsigned)
     if (threadIdx.x < 4) blk[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) n_stage = 0;
     __syncthreads();
     const unsigned int lane = threadIdx.x & 31;
     unsigned int n_valid = 0, n_less = 0, n_eqlo = 0, n_eqhi = 0;
-    // 16 keys of one thread: count, then stage the candidates with ONE warp scan + one shared atomic per
-    // warp (a warp almost always holds a candidate, so per-element voting would cost more than the counting)
+    // 16 keys of one thread.  Pass 1 touches every key but only classifies it as below / inside the closed
+    // bracket [lo, hi] (bit masks, counted with popc once per 16); the few keys inside (~8 %) are then split
+    // into == lo, == hi and strict candidates, and the candidates are staged with ONE warp scan + one shared
+    // atomic per warp (a warp almost always holds a candidate, so per-element voting would cost more than
+    // the counting).
+    const unsigned int width = hi - lo;                              // lo <= hi
     auto visit16 = [&](const unsigned int (&keys)[SEL_ITEMS], unsigned int okmask) {
-        unsigned int cmask = 0;
+        unsigned int lessmask = 0, inmask = 0, lomask = 0, himask = 0;
 #pragma unroll
-        for (int e = 0; e < SEL_ITEMS; ++e) {
+        for (int e = 0; e < SEL_ITEMS; ++e) {                       // branch-free: bit e of each mask
             const unsigned int k = keys[e];
-            const bool ok = (okmask >> e) & 1u;
-            n_valid += ok;
-            n_less += ok && (k < lo);
-            n_eqlo += ok && (k == lo);
-            n_eqhi += ok && (k == hi);
-            if (ok && ((k - lo - 1u) < span)) cmask |= 1u << e;
+            lessmask |= (k < lo ? 1u : 0u) << e;
+            inmask |= ((k - lo) <= width ? 1u : 0u) << e;           // unsigned: k < lo wraps above width
+            lomask |= (k == lo ? 1u : 0u) << e;
+            himask |= (k == hi ? 1u : 0u) << e;
         }
+        lomask &= okmask;
+        himask &= okmask & ~lomask;                                  // lo == hi: counted once, as == lo
+        n_valid += __popc(okmask);
+        n_less += __popc(lessmask & okmask);
+        n_eqlo += __popc(lomask);
+        n_eqhi += __popc(himask);
+        const unsigned int cmask = inmask & okmask & ~lomask & ~himask;
         const unsigned int cnt = __popc(cmask);
         unsigned int incl = cnt;
 #pragma unroll
@@ -326,16 +333,16 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
 #pragma unroll
             for (int it = 0; it < SEL_ITEMS / 4; ++it)
                 v[it] = ldg_stream(reinterpret_cast<const float4*>(seg.a + base + ((long long)it * SEL_THREADS + threadIdx.x) * 4));
-            const bool all_ok = seg.kind == DA3S_SEL_VALUES;
 #pragma unroll
             for (int it = 0; it < SEL_ITEMS / 4; ++it) {
                 const float f[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     keys[it * 4 + j] = f32_to_key(f[j]);
-                    if (all_ok || f[j] > 0.0f) okmask |= 1u << (it * 4 + j);
+                    okmask |= (f[j] > 0.0f ? 1u : 0u) << (it * 4 + j);
                 }
             }
+            if (seg.kind == DA3S_SEL_VALUES) okmask = 0xFFFFu;       // block-uniform: every element takes part
         } else {
 #pragma unroll
             for (int e = 0; e < SEL_ITEMS; ++e) {
@@ -351,7 +358,6 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
         if (staged + (unsigned int)chunk > SEL_STAGE) flush();       // block-uniform
     }
     flush();
-    if (!lo_ne_hi) n_eqhi = 0;
     unsigned int r0 = __reduce_add_sync(0xffffffffu, n_valid), r1 = __reduce_add_sync(0xffffffffu, n_less);
     unsigned int r2 = __reduce_add_sync(0xffffffffu, n_eqlo), r3 = __reduce_add_sync(0xffffffffu, n_eqhi);
     if (lane == 0) {
