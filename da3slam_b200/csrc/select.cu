@@ -298,9 +298,15 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
             unsigned int pos = 0;
             if (lane == 31) pos = atomicAdd(&n_stage, total);
             pos = __shfl_sync(0xffffffffu, pos, 31) + incl - cnt;
+            // one shared-window address, then a predicated store + add per key (the generic form re-derives the
+            // window base for every store)
+            unsigned int saddr = (unsigned int)__cvta_generic_to_shared(stage) + 4u * pos;
 #pragma unroll
             for (int e = 0; e < SEL_ITEMS; ++e)
-                if ((cmask >> e) & 1u) stage[pos++] = keys[e];
+                if ((cmask >> e) & 1u) {
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(keys[e]) : "memory");
+                    saddr += 4u;
+                }
         }
     };
     auto flush = [&]() {                                             // every thread of the block calls it
@@ -333,16 +339,24 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
 #pragma unroll
             for (int it = 0; it < SEL_ITEMS / 4; ++it)
                 v[it] = ldg_stream(reinterpret_cast<const float4*>(seg.a + base + ((long long)it * SEL_THREADS + threadIdx.x) * 4));
+            if (seg.kind == DA3S_SEL_VALUES) {                       // block-uniform: every element takes part
 #pragma unroll
-            for (int it = 0; it < SEL_ITEMS / 4; ++it) {
-                const float f[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+                for (int it = 0; it < SEL_ITEMS / 4; ++it) {
+                    keys[it * 4 + 0] = f32_to_key(v[it].x); keys[it * 4 + 1] = f32_to_key(v[it].y);
+                    keys[it * 4 + 2] = f32_to_key(v[it].z); keys[it * 4 + 3] = f32_to_key(v[it].w);
+                }
+                okmask = 0xFFFFu;
+            } else {                                                 // DA3S_SEL_POSITIVE
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    keys[it * 4 + j] = f32_to_key(f[j]);
-                    okmask |= (f[j] > 0.0f ? 1u : 0u) << (it * 4 + j);
+                for (int it = 0; it < SEL_ITEMS / 4; ++it) {
+                    const float f[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        keys[it * 4 + j] = f32_to_key(f[j]);
+                        okmask |= (f[j] > 0.0f ? 1u : 0u) << (it * 4 + j);
+                    }
                 }
             }
-            if (seg.kind == DA3S_SEL_VALUES) okmask = 0xFFFFu;       // block-uniform: every element takes part
         } else {
 #pragma unroll
             for (int e = 0; e < SEL_ITEMS; ++e) {
