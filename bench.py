@@ -422,7 +422,7 @@ def gpu_arm(args, w, rank, world):
     out = {
         "metric": "submap_pairs_aligned_per_sec", "value": world * n_pairs / (ms_per_step * 1e-3), "unit": "submap-pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "frames_per_submap": w["frames"], "H": w["H"], "W": w["W"],
                    "overlap": w["overlap"], "pairs_per_gpu": n_pairs, "n_hyp": w["n_hyp"], "voxel": w["voxel"],
                    "conf_percentile": CONF_PERCENTILE, "irls": "huber delta=1.0, <=20 it, tol 1e-6 (utils/align.py defaults)",
@@ -468,7 +468,7 @@ def main():
         v = float(np.mean(vals))
         line = {"impl": "reference", "metric": "submap_pairs_aligned_per_sec", "value": v, "unit": "submap-pairs/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["step_s"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
                 "config": {"workload": args.workload, "desc": w["desc"]},
                 "cpu_baseline": {"value": v, "unit": "submap-pairs/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
                                  "per_pair_latency_s": info["lat_pair_s"], "per_submap_export_latency_s": info["lat_submap_s"]},
