@@ -183,6 +183,12 @@ def test_viewer_against_restated_reference(cuda):
     assert v._threshold() == thr                                                            # exact percentile: bit-exact
     pts, cols = v.visible_points()
     assert len(pts) == int(mask.sum()) and rel_err(pts, ref_pts[mask]) < 2e-6
+    # voxel-limited subset: exactly the voxel downsample of what would have been shown
+    v.vis_voxel = 0.1
+    vp, vc = v.visible_points()
+    e_xyz, e_col, _, _ = sp.voxel_downsample(pts, 0.1, cols, None)
+    assert 0 < len(vp) < len(pts) and np.array_equal(vp, e_xyz) and np.array_equal(vc, e_col)
+    v.vis_voxel = None
     v.frame_selector = "1"
     assert 0 < len(v.visible_points()[0]) < len(pts)
     v.clear()

@@ -9,8 +9,11 @@ Reference behaviour kept (viewer.py:156-247, :317-356):
     ``conf >= threshold``; optional single-frame filter.
 Changed on purpose: the reference re-stacks every stored array on every ``add_frame``
 (O(frames^2), viewer.py:323-330); here a frame is appended once to device buffers and the
-threshold is one exact selection over the resident confidences.  viser is optional — without
-it the viewer runs headless and ``visible_points()`` returns what would have been pushed.
+threshold is one exact selection over the resident confidences.  Setting ``vis_voxel`` (scene units,
+an attribute — the constructor keeps the reference's signature) makes ``visible_points()`` hand over the
+voxel-downsampled subset of the filtered map instead of every point (oracle/SPEC.md section 5).
+viser is optional — without it the viewer runs headless and ``visible_points()`` returns what would
+have been pushed.
 """
 from __future__ import annotations
 
@@ -37,6 +40,7 @@ class SLAMViewer:
         self.vis_point_size = vis_point_size
         self.conf_percent = 65.0                 # viewer.py:86-88 slider default
         self.frame_selector = "All"              # viewer.py:90-92 dropdown default
+        self.vis_voxel = None                    # > 0: push one averaged point per occupied voxel of this size
         self._lock = threading.Lock()            # the reference mutates its lists from GUI threads unguarded
         self.server = None
         self.point_cloud = None
@@ -126,7 +130,11 @@ class SLAMViewer:
                 cols.append(col[m])
             if not pts:
                 return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint8)
-            return torch.cat(pts).cpu().numpy(), torch.cat(cols).cpu().numpy()
+            all_pts, all_cols = torch.cat(pts), torch.cat(cols)
+            if self.vis_voxel and all_pts.shape[0] > 0:
+                vx, vc, _, _ = _ops.voxel_downsample([(all_pts.contiguous(), all_cols.contiguous(), None)], float(self.vis_voxel))
+                return vx.cpu().numpy(), vc.cpu().numpy()
+            return all_pts.cpu().numpy(), all_cols.cpu().numpy()
 
     def _update_point_cloud(self):
         if self.server is None:
