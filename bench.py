@@ -215,7 +215,11 @@ def gpu_arm(args, w, rank, world):
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic sequence of this rank, resident in HBM ----
-    subs, gt = synth.make_sequence_device(w["n_submaps"], w["frames"], w["H"], w["W"], w["overlap"], seed=1234 + 1000 * rank,
+    # weak scaling: every rank works on a sequence of the SAME content (same seed), so that per-rank work is identical
+    # and the step is not paced by whichever rank drew the scene with the most voxels; with --global-map the ranks'
+    # scenes differ (their maps are merged)
+    seed = 1234 + (1000 * rank if args.global_map else 0)
+    subs, gt = synth.make_sequence_device(w["n_submaps"], w["frames"], w["H"], w["W"], w["overlap"], seed=seed,
                                           outlier_ratio=w["outlier"], with_images=w["export"], device=dev)
     dsubs = [DeviceSubmap.from_prediction(s, dev) for s in subs]
     n_pairs = w["n_submaps"] - 1
@@ -223,7 +227,7 @@ def gpu_arm(args, w, rank, world):
     sample_idx = None
     opt = dict(world=1)
     if w["n_hyp"] > 0:
-        rng = np.random.default_rng(99 + rank)
+        rng = np.random.default_rng(99 + (rank if args.global_map else 0))
         sample_idx = torch.from_numpy(rng.integers(0, M, size=(n_pairs, w["n_hyp"], 3)).astype(np.int32))
         opt.update(n_hyp=w["n_hyp"], ransac_thr=RANSAC_THR)
     exchange = None
@@ -234,7 +238,7 @@ def gpu_arm(args, w, rank, world):
     plan = SequencePlan(dsubs, overlap=w["overlap"], voxel=w["voxel"], conf_percentile=CONF_PERCENTILE,
                         table_slots=w["table_slots"] or None, sample_idx=sample_idx, export=w["export"], exchange=exchange, **opt)
     ctx = ops.context(dev)
-    gathered = [torch.empty((n_pairs, 16), dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    gathered = torch.empty((world * n_pairs, 16), dtype=torch.float64, device=dev) if world > 1 else None
 
     stage_names = []
 
@@ -246,8 +250,8 @@ def gpu_arm(args, w, rank, world):
                 events.append((name, e))
         mark("start")
         plan.run(mark)
-        if world > 1:                                   # the only exchange: Sim(3) rows over NCCL/NVLink
-            dist.all_gather(gathered, plan.rows)
+        if world > 1:                                   # the only exchange: Sim(3) rows, one NCCL all_gather over NVLink
+            dist.all_gather_into_tensor(gathered, plan.rows)
             mark("allgather")
 
     def barrier():
@@ -290,6 +294,10 @@ def gpu_arm(args, w, rank, world):
     for ev in all_events:
         for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
             stages[n1] = stages.get(n1, 0.0) + e0.elapsed_time(e1) / args.steps
+    per_rank = None
+    if world > 1:                                   # every rank's own stage times (the step waits for the slowest one)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {k: round(v, 4) for k, v in stages.items()})
 
     # ---- end-to-end: host buffers in, results out, copies inside the timed region ----
     e2e = None
@@ -431,7 +439,7 @@ def gpu_arm(args, w, rank, world):
                                   + (" + global voxel map merged over NVLink peer memory" if exchange is not None else " only")},
         "points_per_sec": world * px_export / (ms_per_step * 1e-3) if w["export"] else None,
         "pixels_per_step_per_gpu": px_export, "voxels_out": n_vox,
-        "stages_ms": stages, "stage_bandwidth": per_stage,
+        "stages_ms": stages, "stages_ms_per_rank": per_rank, "stage_bandwidth": per_stage,
         "accuracy": {"max_rel_scale_error_vs_ground_truth": err_s, "irls_iterations_mean": float(np.mean(iters))},
         "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }

@@ -206,12 +206,16 @@ class SequencePlan:
             self.points_per_step = 0
         ops.context(self.dev)            # make sure the context (and its workspace) exists before the first timed run
 
-    def run(self, mark=None):
-        """Enqueue one step.  `mark(name)` is called between stages (bench.py records CUDA events)."""
+    def run(self, mark=None, after_align=None):
+        """Enqueue one step.  `mark(name)` is called between stages (bench.py records CUDA events);
+        `after_align()` right after the Sim(3) rows have been enqueued — the place to start their exchange
+        between ranks so that it overlaps with the export of this rank's own submaps."""
         mark = mark or (lambda name: None)
         self.rows, _, _ = ops.align_pairs(self.pair_table, self.n_pairs, self.overlap, self.H, self.W, self.opts,
                                           self.sample_idx)
         mark("align")
+        if after_align is not None:
+            after_align()
         ops.accumulate_sim3(self.rows, out=self.cum)
         if not self.export:
             mark("chain")
