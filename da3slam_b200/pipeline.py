@@ -90,6 +90,38 @@ def align_sequence(submaps, overlap=1, **kw):
     return align_submap_pairs([(submaps[k], submaps[k + 1]) for k in range(len(submaps) - 1)], overlap, **kw)
 
 
+def loop_constraints(items, overlap=None, **opt_kw):
+    """Loop-closure constraints from jointly predicted loop chunks (utils/da3_streaming.py:366-481).
+
+    items: list of (a, b, frames_a, loop_a, frames_b, loop_b): chunk indices a, b and four DeviceSubmaps —
+    `frames_a` / `frames_b` the chunks' own predictions of the frames that also went through the network together
+    as ONE loop chunk, `loop_a` / `loop_b` the loop chunk's predictions of the same frames.  Both halves of every
+    item are aligned on the GPU in one batch (loop -> a and loop -> b, every frame an overlap frame), and
+    T_ab = T_a o T_b^-1 maps chunk b into chunk a (compute_sim3_ab upstream).  Returns [(a, b, (s, R, t))] for
+    posegraph.optimize."""
+    from . import posegraph
+    if not items:
+        return []
+    overlap = overlap or items[0][2].depth.shape[0]        # every shared frame is an overlap frame
+    pairs = []
+    for a, b, fa, la, fb, lb in items:                      # target = the chunk's own frames, source = the loop chunk's
+        pairs += [(fa, la), (fb, lb)]
+    rows, _, _ = align_submap_pairs(pairs, overlap=overlap, **opt_kw)
+    sims = rows_to_sim3(rows.cpu().numpy())
+    out = []
+    for i, (a, b, *_rest) in enumerate(items):
+        T_a, T_b = sims[2 * i], sims[2 * i + 1]
+        out.append((a, b, posegraph._compose(posegraph._as_sim3(T_a), posegraph._inverse(posegraph._as_sim3(T_b)))))
+    return out
+
+
+def close_loops(sequential, loops, max_iterations=30, lambda_init=1e-6):
+    """Sim(3) pose graph over the chunk chain with the loop constraints (posegraph.optimize): returns the corrected
+    sequential list, ready for accumulate_sim3 (upstream: Sim3LoopOptimizer.optimize, utils/da3_streaming.py:617)."""
+    from . import posegraph
+    return posegraph.optimize(sequential, loops, max_iterations=max_iterations, lambda_init=lambda_init)
+
+
 def accumulate_sim3(chain):
     """utils/geometry.py:73-119: identity first, then left-to-right composition
     (output length = len(chain) + 1).  Host float64: it is len(chain) 3x3 products."""

@@ -633,6 +633,48 @@ def test_full_size_properties(cuda):
     assert np.array_equal(outf["rows"], out2["rows"]) and np.array_equal(out2["rows"], r)
 
 
+def _reexpress(sub, frames, sim):
+    """The same frames predicted in another frame L with p_old = s R p_L + t: depth / s, w2c [R_e R | (t_e + R_e t) / s]."""
+    s_, R_, t_ = sim
+    E = np.asarray(sub["extrinsics"], np.float64)[frames]
+    out = {k: np.ascontiguousarray(np.asarray(sub[k])[frames]) for k in ("depth", "conf", "intrinsics")}
+    out["depth"] = (out["depth"] / np.float32(s_)).astype(np.float32)
+    Rn = E[:, :, :3] @ R_
+    tn = (E[:, :, 3] + E[:, :, :3] @ t_) / s_
+    out["extrinsics"] = np.concatenate([Rn, tn[:, :, None]], axis=2).astype(np.float32)
+    return out
+
+
+def test_loop_constraints_and_pose_graph(cuda):
+    """Loop closure end to end: a jointly predicted loop chunk holding the last frame of chunk 0 and the
+    first frame of chunk 3 gives, through two batched GPU alignments, the constraint 'chunk 3 in chunk 0'; the pose graph
+    then pulls a drifting chain back."""
+    from da3slam_b200 import pipeline, posegraph
+    rng = np.random.default_rng(8)
+    n, F, H, W = 4, 2, 60, 80
+    subs, gt = synth.make_sequence(n, F, H, W, overlap=1, seed=91)
+    A = posegraph.sequential_to_absolute(gt)                                   # chunk k in chunk 0's frame
+    S_L = synth.random_sim3(rng)                                               # loop frame: p_0 = S_L p_L
+    own_a = _reexpress(subs[0], [F - 1], (1.0, np.eye(3), np.zeros(3)))
+    own_b = _reexpress(subs[3], [0], (1.0, np.eye(3), np.zeros(3)))
+    loop_a = _reexpress(subs[0], [F - 1], S_L)                                 # p_0 = S_L p_L
+    loop_b = _reexpress(subs[3], [0], posegraph._compose(posegraph._inverse(A[3]), posegraph._as_sim3(S_L)))   # p_3 = A_3^-1 S_L p_L
+    dev = [DeviceSubmap.from_prediction(x, cuda) for x in (own_a, loop_a, own_b, loop_b)]
+    loops = pipeline.loop_constraints([(0, 3, dev[0], dev[1], dev[2], dev[3])], world=1)
+    (a, b, T), = loops
+    assert (a, b) == (0, 3)
+    assert abs(T[0] - A[3][0]) < 2e-3 * A[3][0] and np.abs(T[1] - A[3][1]).max() < 2e-3 and np.abs(T[2] - A[3][2]).max() < 2e-2
+    # drifting odometry + the measured loop: the end of the chain comes back
+    noisy = [posegraph._compose(posegraph._as_sim3(g), posegraph._unchart(np.concatenate([rng.normal(0, 0.02, 3), [rng.normal(0, 0.02)],
+                                                                                               rng.normal(0, 0.05, 3)]))) for g in gt]
+    fixed = pipeline.close_loops(noisy, loops)
+
+    def end_err(seq):
+        E_ = posegraph.sequential_to_absolute(seq)[-1]
+        return np.linalg.norm(posegraph._chart(posegraph._compose(posegraph._inverse(A[3]), E_)))
+    assert end_err(fixed) < 0.5 * end_err(noisy)
+
+
 def test_unproject_jobs_equals_flat_launch(cuda):
     rng = np.random.default_rng(12)
     n, H, W = 5, 30, 44
