@@ -26,6 +26,33 @@
 #define VOX_REC 8                           // u64 words per record
 #define VOX_MAX_PROBE 4096
 
+// Locality-preserving slot: the 4 x 4 x 4 block of voxels a key belongs to is hashed to a REGION of 64 consecutive
+// slots, the position inside the region is the voxel's position inside its block; on a collision the probe moves
+// to the next region (same position).  Neighbouring voxels — what a warp's batch of neighbouring pixels hits — then
+// share key sectors and DRAM rows instead of being scattered over the whole table.
+#ifndef VOX_LOCAL
+#define VOX_LOCAL 1
+#endif
+#ifndef VOX_LOCAL_BITS
+#define VOX_LOCAL_BITS 2                    // 4 x 4 x 4 voxels per region
+#endif
+__device__ __forceinline__ unsigned long long vox_hash(unsigned long long k);
+__device__ __forceinline__ unsigned long long vox_slot0(unsigned long long key, long long slots) {
+#if VOX_LOCAL
+    const unsigned long long m = (1ull << VOX_LOCAL_BITS) - 1ull;
+    const unsigned long long coarse = key & ~((m << 42) | (m << 21) | m);
+    const unsigned long long local = (((key >> 42) & m) << (2 * VOX_LOCAL_BITS)) | (((key >> 21) & m) << VOX_LOCAL_BITS) | (key & m);
+    return ((vox_hash(coarse) << (3 * VOX_LOCAL_BITS)) | local) & (unsigned long long)(slots - 1);
+#else
+    return vox_hash(key) & (unsigned long long)(slots - 1);
+#endif
+}
+#if VOX_LOCAL
+#define VOX_STEP (1ull << (3 * VOX_LOCAL_BITS))
+#else
+#define VOX_STEP 1ull
+#endif
+
 __device__ __forceinline__ unsigned long long vox_hash(unsigned long long k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
     return k;
@@ -88,7 +115,7 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
         }
         if (lane != leader) return;
     }
-    unsigned long long slot = vox_hash(key) & (unsigned long long)(slots - 1);
+    unsigned long long slot = vox_slot0(key, slots);
     for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
         unsigned long long* rec = acc + slot * VOX_REC;
         unsigned long long* kp = acc + (size_t)slots * VOX_REC + slot;
@@ -103,7 +130,7 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
             if (has_rgb) atomicAdd(rec + 5, gb);
             return;
         }
-        slot = (slot + 1) & (unsigned long long)(slots - 1);
+        slot = (slot + VOX_STEP) & (unsigned long long)(slots - 1);
     }
     atomicAdd(&counters[1], cr >> 32);                              // table full: reported by finish
 }
@@ -390,18 +417,22 @@ extern "C" int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* j
 #define VC_PER_BLOCK (VC_PER_WARP * VC_THREADS / 32)
 
 __global__ void __launch_bounds__(VC_THREADS)
-voxel_count_kernel(const unsigned long long* __restrict__ acc, long long slots, unsigned int* __restrict__ warp_counts) {
+voxel_count_kernel(const unsigned long long* __restrict__ acc, long long slots, unsigned int* __restrict__ warp_counts,
+                   unsigned int* __restrict__ occ_bits /* [n_warps][VC_ROUNDS] */) {
     const unsigned int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
     const long long base = wid * VC_PER_WARP;
     if (base >= slots) return;
-    unsigned int c = 0;
+    unsigned int c = 0, mine = 0;
 #pragma unroll
     for (int j = 0; j < VC_ROUNDS; ++j) {                       // 16 independent loads per lane, one key per record
         const long long s = base + (long long)j * 32 + lane;
-        if (s < slots) c += __ldcs(acc + (size_t)slots * VOX_REC + s) != VOX_EMPTY;
+        const bool occ = s < slots && __ldcs(acc + (size_t)slots * VOX_REC + s) != VOX_EMPTY;
+        const unsigned int word = __ballot_sync(0xffffffffu, occ);       // occupancy of round j: the emit pass reads
+        if ((int)lane == j) mine = word;                                 // 64 bytes per warp instead of 4 KB of keys
+        c += __popc(word);
     }
-    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane < VC_ROUNDS) occ_bits[wid * VC_ROUNDS + lane] = mine;
     if (lane == 0) warp_counts[wid] = c;
 }
 
@@ -442,7 +473,8 @@ voxel_scan_kernel(const unsigned int* __restrict__ counts, int n, unsigned long 
 
 __global__ void __launch_bounds__(VC_THREADS)
 voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
-                  const unsigned long long* __restrict__ warp_offsets, float voxel, long long max_voxels,
+                  const unsigned long long* __restrict__ warp_offsets, const unsigned int* __restrict__ occ_bits,
+                  float voxel, long long max_voxels,
                   float* __restrict__ xyz_out, uint8_t* __restrict__ rgb_out, int32_t* __restrict__ count_out,
                   long long* __restrict__ key_out) {
     const double vd = (double)voxel;
@@ -450,11 +482,14 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
     const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
     const long long base = wid * VC_PER_WARP;
     if (base >= slots) return;
+    const unsigned int my_word = lane < VC_ROUNDS ? occ_bits[wid * VC_ROUNDS + lane] : 0u;
+    if (__ballot_sync(0xffffffffu, my_word != 0u) == 0u) return;  // nothing in these 512 slots (warp-uniform)
     unsigned long long key[VC_ROUNDS];
 #pragma unroll
-    for (int j = 0; j < VC_ROUNDS; ++j) {                       // 16 independent coalesced loads per lane
+    for (int j = 0; j < VC_ROUNDS; ++j) {                       // keys of occupied slots only
         const long long s = base + (long long)j * 32 + lane;
-        key[j] = s < slots ? acc[(size_t)slots * VOX_REC + s] : VOX_EMPTY;
+        const unsigned int word = __shfl_sync(0xffffffffu, my_word, j);
+        key[j] = ((word >> lane) & 1u) ? acc[(size_t)slots * VOX_REC + s] : VOX_EMPTY;
     }
     unsigned long long out = warp_offsets[wid];
 #pragma unroll
@@ -640,7 +675,7 @@ voxel_merge_kernel(const unsigned long long* __restrict__ inbox, const unsigned 
         const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(seg + i * 6 + 2);
         const ulonglong2 r2 = *reinterpret_cast<const ulonglong2*>(seg + i * 6 + 4);
         const unsigned long long key = r0.x;
-        unsigned long long slot = vox_hash(key) & (unsigned long long)(slots - 1);
+        unsigned long long slot = vox_slot0(key, slots);
         bool placed = false;
         for (int probe = 0; probe < VOX_MAX_PROBE && !placed; ++probe) {
             unsigned long long* rec = acc + slot * VOX_REC;
@@ -655,7 +690,7 @@ voxel_merge_kernel(const unsigned long long* __restrict__ inbox, const unsigned 
                 atomicAdd(rec + 4, r2.x); atomicAdd(rec + 5, r2.y);
                 placed = true;
             }
-            slot = (slot + 1) & (unsigned long long)(slots - 1);
+            slot = (slot + VOX_STEP) & (unsigned long long)(slots - 1);
         }
         if (!placed) atomicAdd(&counters[1], r2.x >> 32);
     }
@@ -703,9 +738,9 @@ extern "C" int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots, void* stre
     if (!ctx || table_slots < 1024 || (table_slots & (table_slots - 1)) || table_slots > (1ll << 31)) return DA3S_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     // layout of the reserved tail: records [slots][8] u64 | counters [4] u64 (256 B) |
-    // warp counts [slots/512] u32 | warp offsets [slots/512] u64
+    // warp counts [slots/512] u32 | warp offsets [slots/512] u64 | occupancy bits [slots/32] u32
     const long long n_cblocks = (table_slots + VC_PER_WARP - 1) / VC_PER_WARP;
-    size_t bytes = (size_t)table_slots * (VOX_REC + 1) * 8 + 256 + (size_t)n_cblocks * 16 + 512;
+    size_t bytes = (size_t)table_slots * (VOX_REC + 1) * 8 + 256 + (size_t)n_cblocks * (16 + 4 * VC_ROUNDS) + 512;
     const bool reuse = (ctx->vox_slots == table_slots) && ctx->vox_clean && ctx->vox_bytes > 0;
     if (!reuse) {
         if (bytes > ctx->ws_bytes) return DA3S_ENOMEM;
@@ -780,11 +815,12 @@ extern "C" int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxel
     const int n_cblocks = (n_warps + VC_THREADS / 32 - 1) / (VC_THREADS / 32);
     unsigned int* warp_counts = ctx->vox_occ;
     unsigned long long* warp_offsets = (unsigned long long*)(warp_counts + ((n_warps + 1) & ~1));
-    voxel_count_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_counts);
+    unsigned int* occ_bits = (unsigned int*)(warp_offsets + n_warps);
+    voxel_count_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_counts, occ_bits);
     DA3S_LAUNCH_CHECK(ctx);
     voxel_scan_kernel<<<1, 1024, 0, st>>>(warp_counts, n_warps, warp_offsets, ctx->vox_dropped);
     DA3S_LAUNCH_CHECK(ctx);
-    voxel_emit_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_offsets, voxel, max_voxels,
+    voxel_emit_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_offsets, occ_bits, voxel, max_voxels,
                                                        xyz_out, rgb_out, count_out, key_out);
     DA3S_LAUNCH_CHECK(ctx);
     DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_voxels, ctx->vox_dropped, 8, cudaMemcpyDeviceToDevice, st));
