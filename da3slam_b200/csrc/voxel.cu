@@ -25,6 +25,19 @@
 #define VOX_BIAS (1 << 20)
 #define VOX_REC 8                           // u64 words per record
 #define VOX_MAX_PROBE 4096
+// Table addressing.  VOX_INTERLEAVE = 0 (default): one dense key array behind all records; 1: every group of 64 slots
+// keeps its 64 keys (512 B) directly in front of its 64 records (4 KB) — measured equal within noise
+// (export 1.46 vs 1.44 ms), so the simpler layout stays.
+#ifndef VOX_INTERLEAVE
+#define VOX_INTERLEAVE 0
+#endif
+#if VOX_INTERLEAVE
+#define VOX_KEY_PTR(acc, slots, s) ((acc) + ((size_t)(s) >> 6) * (64 * (VOX_REC + 1)) + ((size_t)(s) & 63))
+#define VOX_REC_PTR(acc, slots, s) ((acc) + ((size_t)(s) >> 6) * (64 * (VOX_REC + 1)) + 64 + ((size_t)(s) & 63) * VOX_REC)
+#else
+#define VOX_KEY_PTR(acc, slots, s) ((acc) + (size_t)(slots) * VOX_REC + (size_t)(s))
+#define VOX_REC_PTR(acc, slots, s) ((acc) + (size_t)(s) * VOX_REC)
+#endif
 
 // Locality-preserving slot: the 4 x 4 x 4 block of voxels a key belongs to is hashed to a REGION of 64 consecutive
 // slots, the position inside the region is the voxel's position inside its block; on a collision the probe moves
@@ -59,11 +72,12 @@ __device__ __forceinline__ unsigned long long vox_hash(unsigned long long k) {
 }
 
 __global__ void voxel_clear_kernel(unsigned long long* acc, long long slots) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one u64 word per thread
-    const long long words = slots * (VOX_REC + 1);
-    unsigned long long* keys = acc + (size_t)slots * VOX_REC;
-    for (; i < words; i += (long long)gridDim.x * blockDim.x) {
-        if (i < slots) keys[i] = VOX_EMPTY; else acc[i - slots] = 0ull;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one slot per thread
+    for (; i < slots; i += (long long)gridDim.x * blockDim.x) {
+        *VOX_KEY_PTR(acc, slots, i) = VOX_EMPTY;
+        unsigned long long* rec = VOX_REC_PTR(acc, slots, i);
+#pragma unroll
+        for (int k = 0; k < VOX_REC; k += 2) *reinterpret_cast<ulonglong2*>(rec + k) = make_ulonglong2(0ull, 0ull);
     }
 }
 
@@ -117,8 +131,8 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
     }
     unsigned long long slot = vox_slot0(key, slots);
     for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
-        unsigned long long* rec = acc + slot * VOX_REC;
-        unsigned long long* kp = acc + (size_t)slots * VOX_REC + slot;
+        unsigned long long* rec = VOX_REC_PTR(acc, slots, slot);
+        unsigned long long* kp = VOX_KEY_PTR(acc, slots, slot);
         unsigned long long cur = *((volatile unsigned long long*)kp);
         if (cur == VOX_EMPTY) {
             cur = atomicCAS(kp, VOX_EMPTY, key);
@@ -427,7 +441,7 @@ voxel_count_kernel(const unsigned long long* __restrict__ acc, long long slots, 
 #pragma unroll
     for (int j = 0; j < VC_ROUNDS; ++j) {                       // 16 independent loads per lane, one key per record
         const long long s = base + (long long)j * 32 + lane;
-        const bool occ = s < slots && __ldcs(acc + (size_t)slots * VOX_REC + s) != VOX_EMPTY;
+        const bool occ = s < slots && __ldcs(VOX_KEY_PTR(acc, slots, s)) != VOX_EMPTY;
         const unsigned int word = __ballot_sync(0xffffffffu, occ);       // occupancy of round j: the emit pass reads
         if ((int)lane == j) mine = word;                                 // 64 bytes per warp instead of 4 KB of keys
         c += __popc(word);
@@ -489,7 +503,7 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
     for (int j = 0; j < VC_ROUNDS; ++j) {                       // keys of occupied slots only
         const long long s = base + (long long)j * 32 + lane;
         const unsigned int word = __shfl_sync(0xffffffffu, my_word, j);
-        key[j] = ((word >> lane) & 1u) ? acc[(size_t)slots * VOX_REC + s] : VOX_EMPTY;
+        key[j] = ((word >> lane) & 1u) ? (*VOX_KEY_PTR(acc, slots, s)) : VOX_EMPTY;
     }
     unsigned long long out = warp_offsets[wid];
 #pragma unroll
@@ -506,7 +520,7 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
             out += __popc(m);
             if (occ[q]) {
                 const long long s = base + (long long)j * 32 + lane;
-                unsigned long long* rec = acc + (size_t)s * VOX_REC;
+                unsigned long long* rec = VOX_REC_PTR(acc, slots, s);
                 rx[q] = rec[1];
                 ra[q] = *reinterpret_cast<const ulonglong2*>(rec + 2);
                 rb[q] = *reinterpret_cast<const ulonglong2*>(rec + 4);
@@ -517,9 +531,9 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
             if (!occ[q]) continue;
             const int j = j0 + q;
             const long long s = base + (long long)j * 32 + lane;
-            unsigned long long* rec = acc + (size_t)s * VOX_REC;
+            unsigned long long* rec = VOX_REC_PTR(acc, slots, s);
             *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2(VOX_EMPTY, 0ull);
-            acc[(size_t)slots * VOX_REC + s] = VOX_EMPTY;
+            (*VOX_KEY_PTR(acc, slots, s)) = VOX_EMPTY;
             *reinterpret_cast<ulonglong2*>(rec + 2) = make_ulonglong2(0ull, 0ull);
             *reinterpret_cast<ulonglong2*>(rec + 4) = make_ulonglong2(0ull, 0ull);
             if ((long long)oo[q] >= max_voxels) continue;
@@ -579,7 +593,7 @@ voxel_count_dest_kernel(const unsigned long long* __restrict__ acc, long long sl
 #pragma unroll 4
     for (int j = 0; j < VC_ROUNDS; ++j) {
         const long long s = base + (long long)j * 32 + lane;
-        const unsigned long long k = s < slots ? __ldcs(acc + (size_t)slots * VOX_REC + s) : VOX_EMPTY;
+        const unsigned long long k = s < slots ? __ldcs(VOX_KEY_PTR(acc, slots, s)) : VOX_EMPTY;
         const int owner = k != VOX_EMPTY ? vox_owner(k, world) : -1;
         for (int d = 0; d < world; ++d) {
             const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
@@ -635,7 +649,7 @@ voxel_send_kernel(unsigned long long* __restrict__ acc, long long slots, const u
 #pragma unroll 2
     for (int j = 0; j < VC_ROUNDS; ++j) {
         const long long s = base + (long long)j * 32 + lane;
-        const unsigned long long k = s < slots ? acc[(size_t)slots * VOX_REC + s] : VOX_EMPTY;
+        const unsigned long long k = s < slots ? (*VOX_KEY_PTR(acc, slots, s)) : VOX_EMPTY;
         const bool occ = k != VOX_EMPTY;
         const int owner = occ ? vox_owner(k, world) : -1;
         unsigned long long my_idx = 0;
@@ -646,14 +660,14 @@ voxel_send_kernel(unsigned long long* __restrict__ acc, long long slots, const u
             if ((int)lane == d) out += __popc(m);
         }
         if (occ) {
-            unsigned long long* rec = acc + (size_t)s * VOX_REC;
+            unsigned long long* rec = VOX_REC_PTR(acc, slots, s);
             const unsigned long long sx = rec[1];
             const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rec + 2);
             const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(rec + 4);
             *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2(VOX_EMPTY, 0ull);
             *reinterpret_cast<ulonglong2*>(rec + 2) = make_ulonglong2(0ull, 0ull);
             *reinterpret_cast<ulonglong2*>(rec + 4) = make_ulonglong2(0ull, 0ull);
-            acc[(size_t)slots * VOX_REC + s] = VOX_EMPTY;
+            (*VOX_KEY_PTR(acc, slots, s)) = VOX_EMPTY;
             if ((long long)my_idx < cap) {
                 unsigned long long* dst = peers.inbox[owner] + ((size_t)rank * (size_t)cap + my_idx) * 6;   // NVLink stores
                 *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(k, sx);
@@ -678,8 +692,8 @@ voxel_merge_kernel(const unsigned long long* __restrict__ inbox, const unsigned 
         unsigned long long slot = vox_slot0(key, slots);
         bool placed = false;
         for (int probe = 0; probe < VOX_MAX_PROBE && !placed; ++probe) {
-            unsigned long long* rec = acc + slot * VOX_REC;
-            unsigned long long* kp = acc + (size_t)slots * VOX_REC + slot;
+            unsigned long long* rec = VOX_REC_PTR(acc, slots, slot);
+            unsigned long long* kp = VOX_KEY_PTR(acc, slots, slot);
             unsigned long long cur = *((volatile unsigned long long*)kp);
             if (cur == VOX_EMPTY) {
                 cur = atomicCAS(kp, VOX_EMPTY, key);
@@ -753,8 +767,7 @@ extern "C" int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots, void* stre
         ctx->vox_dropped = ctx->vox_acc + (size_t)table_slots * (VOX_REC + 1);       // counters[4]
         ctx->vox_occ = (unsigned int*)(ctx->vox_dropped + 32);                 // block counts, then block offsets
         ctx->vox_slots = table_slots;
-        long long words = table_slots * (VOX_REC + 1);
-        long long want = (words + 255) / 256, cap = (long long)ctx->sm_count * 32;
+        long long want = (table_slots + 255) / 256, cap = (long long)ctx->sm_count * 32;
         voxel_clear_kernel<<<(int)(want > cap ? cap : want), 256, 0, st>>>(ctx->vox_acc, table_slots);
         DA3S_LAUNCH_CHECK(ctx);
     }
