@@ -15,6 +15,7 @@ import torch
 from . import _lib as L
 
 _contexts = {}
+_retired = []        # outgrown contexts stay alive: objects created earlier (VoxelGrid, plans) keep using theirs
 
 
 class Context:
@@ -50,8 +51,7 @@ def context(device=None, workspace_bytes: int | None = None) -> Context:
     want = workspace_bytes or (1 << 30)
     if ctx is None or ctx.workspace_bytes < want:
         if ctx is not None:
-            torch.cuda.synchronize(device)
-            ctx.close()
+            _retired.append(ctx)
         with torch.cuda.device(device):
             ctx = Context(device, want)
         _contexts[device.index] = ctx
