@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
 select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, unsigned int* cand, long long cand_cap,
                     unsigned int* tickets) {
     __shared__ unsigned int stage[SEL_STAGE];
-    __shared__ unsigned int n_stage;
+    __shared__ unsigned int n_stage, stage_limit;
     __shared__ unsigned long long blk[4];
     __shared__ unsigned long long cand_base;
     __shared__ bool is_last;
@@ -259,7 +259,7 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
     if (w->done) return;                                             // block-uniform
     const unsigned int lo = w->lo_key, hi = w->hi_key;
     if (threadIdx.x < 4) blk[threadIdx.x] = 0ull;
-    if (threadIdx.x == 0) n_stage = 0;
+    if (threadIdx.x == 0) { n_stage = 0; stage_limit = SEL_STAGE; }
     __syncthreads();
     const unsigned int lane = threadIdx.x & 31;
     unsigned int n_valid = 0, n_less = 0, n_eqlo = 0, n_eqhi = 0;
@@ -297,7 +297,26 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
         if (total) {                                                 // warp-uniform
             unsigned int pos = 0;
             if (lane == 31) pos = atomicAdd(&n_stage, total);
-            pos = __shfl_sync(0xffffffffu, pos, 31) + incl - cnt;
+            const unsigned int warp_pos = __shfl_sync(0xffffffffu, pos, 31);
+            if (warp_pos + total > SEL_STAGE) {
+                // the block's staging area is full (values concentrated around the wanted rank in this part of the
+                // segment, e.g. sorted or smooth data): this warp's candidates go straight to the segment's
+                // candidate array; everything staged below `stage_limit` is still valid
+                unsigned long long gpos = 0;
+                if (lane == 31) { atomicMin(&stage_limit, warp_pos); gpos = atomicAdd(&w->c_cand, (unsigned long long)total); }
+                gpos = __shfl_sync(0xffffffffu, gpos, 31) + incl - cnt;
+                unsigned int* dst = cand + (size_t)seg_id * cand_cap;
+                bool over = false;
+#pragma unroll
+                for (int e = 0; e < SEL_ITEMS; ++e)
+                    if ((cmask >> e) & 1u) {
+                        if ((long long)gpos < cand_cap) dst[gpos] = keys[e]; else over = true;
+                        ++gpos;
+                    }
+                if (over) w->overflow = 1;
+                return;
+            }
+            pos = warp_pos + incl - cnt;
             // one shared-window address, then a predicated store + add per key (the generic form re-derives the
             // window base for every store)
             unsigned int saddr = (unsigned int)__cvta_generic_to_shared(stage) + 4u * pos;
@@ -311,7 +330,7 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
     };
     auto flush = [&]() {                                             // every thread of the block calls it
         __syncthreads();
-        const unsigned int total = n_stage;
+        const unsigned int total = n_stage < stage_limit ? n_stage : stage_limit;  // reservations from stage_limit on went to global directly
         if (threadIdx.x == 0) cand_base = total ? atomicAdd(&w->c_cand, (unsigned long long)total) : 0ull;
         __syncthreads();
         if (total) {
@@ -365,11 +384,7 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
                 if (i < seg.n && sel_key(seg, i, keys[e])) okmask |= 1u << e;
             }
         }
-        visit16(keys, okmask);
-        __syncthreads();
-        const unsigned int staged = n_stage;
-        __syncthreads();                                             // everyone has read it before the next chunk appends
-        if (staged + (unsigned int)chunk > SEL_STAGE) flush();       // block-uniform
+        visit16(keys, okmask);                                       // no block barrier between chunks: warps run ahead freely
     }
     flush();
     unsigned int r0 = __reduce_add_sync(0xffffffffu, n_valid), r1 = __reduce_add_sync(0xffffffffu, n_less);

@@ -170,6 +170,26 @@ def test_select_median_percentile_bit_exact(cuda):
     assert out["value"][0] == 0 and out["n_valid"][1] == 0 and np.isnan(out["value"][1])
 
 
+def test_select_sorted_and_smooth_segments(cuda):
+    """Values concentrated around the wanted rank in one part of the segment (sorted input, a smooth ramp, a plateau at
+    the median): the block that holds them cannot stage all its candidates in shared memory and writes them to the
+    candidate array directly — the answers stay exact."""
+    rng = np.random.default_rng(17)
+    n = 700_001
+    ramp = np.linspace(0.5, 3.0, n).astype(np.float32)
+    cases = [np.sort(rng.normal(1, 0.3, n).astype(np.float32)), ramp, ramp[::-1].copy(),
+             np.where(np.arange(n) % 3 == 0, np.float32(1.25), rng.random(n).astype(np.float32) * 2.5).astype(np.float32),
+             np.repeat(rng.random(n // 5000 + 1).astype(np.float32), 5000)[:n]]
+    segs, want = [], []
+    for a in cases:
+        for stat, pct in ((L.SEL_MEDIAN, 0.0), (L.SEL_PERCENTILE, 65.0), (L.SEL_PERCENTILE, 3.0)):
+            segs.append(dict(a=dev_t(a, cuda), kind=L.SEL_VALUES, stat=stat, percent=pct))
+            want.append(np.median(a) if stat == L.SEL_MEDIAN else np.percentile(a, pct))
+    out = ops.select(segs, cuda)
+    for i, w_ in enumerate(want):
+        assert out["n_valid"][i] == n and np.float32(out["value"][i]) == np.float32(w_), i
+
+
 def test_select_depth_ratio_median(golden, cuda):
     g = golden("depth_scale")
     segs, refs, counts = [], [], []
