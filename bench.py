@@ -382,7 +382,7 @@ def gpu_arm(args, w, rank, world):
         from da3slam_b200.pipeline import SequenceStream
         host_seq = [dict(hp, intrinsics=s_["intrinsics"].cpu().pin_memory(), extrinsics=s_["extrinsics"].cpu().pin_memory())
                     for hp, s_ in zip(host, subs)]
-        stream = SequenceStream(host_seq, dev, slots=2, overlap=w["overlap"], voxel=w["voxel"], conf_percentile=CONF_PERCENTILE,
+        stream = SequenceStream(host_seq, dev, slots=2, upload_streams=int(os.environ.get("DA3S_UPLOAD_STREAMS", "2")), overlap=w["overlap"], voxel=w["voxel"], conf_percentile=CONF_PERCENTILE,
                                 table_slots=w["table_slots"] or None, sample_idx=sample_idx, export=w["export"], **opt)
         k_stream = max(4, min(args.steps, 10))
         for _ in stream.process([host_seq] * 3):                 # warm-up (also fills the pipeline once)

@@ -296,11 +296,13 @@ class SequenceStream:
     class _Slot:
         pass
 
-    def __init__(self, example, device="cuda", slots=2, general_inverse=False, with_keys=False, **plan_kw):
+    def __init__(self, example, device="cuda", slots=2, general_inverse=False, with_keys=False, upload_streams=2, **plan_kw):
         self.dev = torch.device(device)
         self.with_keys = with_keys                                  # also download the voxel keys (canonical order = ascending key)
         self.general_inverse = general_inverse
         self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        # several upload streams: concurrent copies keep the host->device link busier than one queue of copies
+        self.s_up = [self.s_in] + [torch.cuda.Stream(self.dev) for _ in range(max(0, int(upload_streams) - 1))]
         self.slots = []
         for _ in range(slots):
             sl = SequenceStream._Slot()
@@ -323,11 +325,14 @@ class SequenceStream:
         self.h2d_bytes = self.d2h_bytes = 0
 
     def _upload(self, sl, host_subs):
-        with torch.cuda.stream(self.s_in):
+        streams = self.s_up
+        for st in streams:
             if sl.compute_done is not None:
-                self.s_in.wait_event(sl.compute_done)               # the previous sequence in this slot has been consumed
-            n = 0
-            for sm, hp in zip(sl.subs, host_subs):
+                st.wait_event(sl.compute_done)                      # the previous sequence in this slot has been consumed
+        n = 0
+        for k, (sm, hp) in enumerate(zip(sl.subs, host_subs)):
+            st = streams[k % len(streams)]
+            with torch.cuda.stream(st):
                 for name, dst in (("depth", sm.depth), ("conf", sm.conf), ("intrinsics", sm.intrinsics), ("extrinsics", sm.extrinsics),
                                   ("processed_images", sm.images)):
                     if dst is None:
@@ -336,8 +341,12 @@ class SequenceStream:
                     dst.copy_(src, non_blocking=True)
                     n += dst.numel() * dst.element_size()
                 ops.build_cams(sm.intrinsics, sm.extrinsics, self.general_inverse, out=sm.cams)
-            sl.h2d_done = torch.cuda.Event()
-            sl.h2d_done.record(self.s_in)
+        for st in streams[1:]:
+            join = torch.cuda.Event()
+            join.record(st)
+            self.s_in.wait_event(join)
+        sl.h2d_done = torch.cuda.Event()
+        sl.h2d_done.record(self.s_in)
         self.h2d_bytes = n
 
     def _compute(self, sl):
