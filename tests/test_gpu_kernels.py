@@ -415,6 +415,27 @@ def test_voxel_downsample_bit_exact(cuda, n):
             assert np.array_equal(out[1].cpu().numpy(), col)
 
 
+@pytest.mark.parametrize("centre", [0.0, -37.5, 812.25])
+def test_voxel_dense_cloud_warp_reduction(cuda, centre):
+    """Many points per voxel (the hires case): batches of 32 points with <= 4 distinct voxels merge with masked warp
+    reductions on the 16-bit limbs of the 32-bit fixed-point offsets; per-voxel counts go past 2^16."""
+    rng = np.random.default_rng(17)
+    n = 300007
+    cells = rng.integers(0, 3, (n, 3)).astype(np.float32)                      # 27 voxels, ~11 k points each
+    cells[: n // 2] = np.repeat(cells[: n // 2: 64], 64, axis=0)[: n // 2]       # runs of one voxel / mixed batches
+    pts = (np.float32(centre) + (cells + rng.random((n, 3), dtype=np.float32) * 0.98 + 0.01) * np.float32(0.05)).astype(np.float32)
+    pts[-70000:] = np.float32(centre) + np.float32(0.051)                       # one voxel with 70 000 identical points
+    rgb = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    for use_rgb in (True, False):
+        out = ops.voxel_downsample([(dev_t(pts, cuda), dev_t(rgb, cuda) if use_rgb else None, None)], 0.05)
+        xyz, col, cnt, key = sp.voxel_downsample(pts, 0.05, rgb if use_rgb else None, None)
+        assert cnt.max() >= 70000 and len(key) <= 64
+        assert np.array_equal(out[3].cpu().numpy(), key) and np.array_equal(out[2].cpu().numpy(), cnt)
+        assert np.array_equal(out[0].cpu().numpy(), xyz)
+        if use_rgb:
+            assert np.array_equal(out[1].cpu().numpy(), col)
+
+
 def test_voxel_accumulates_across_clouds(cuda):
     rng = np.random.default_rng(4)
     a = rng.normal(0, 0.5, (5000, 3)).astype(np.float32)
