@@ -247,7 +247,7 @@ select_sample_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, da
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, unsigned int* cand, long long cand_cap,
-                    unsigned int* tickets) {
+                    unsigned int* tickets, int chunks /* per block, <= SEL_CHUNKS */) {
     __shared__ unsigned int stage[SEL_STAGE];
     __shared__ unsigned int n_stage, stage_limit;
     __shared__ unsigned long long blk[4];
@@ -347,8 +347,8 @@ select_count_kernel(const da3s_select_seg* __restrict__ segs, SelWork* work, uns
         __syncthreads();
     };
     const long long chunk = (long long)SEL_THREADS * SEL_ITEMS;
-    for (int ch = 0; ch < SEL_CHUNKS; ++ch) {                        // block-uniform
-        const long long base = ((long long)blockIdx.x * SEL_CHUNKS + ch) * chunk;
+    for (int ch = 0; ch < chunks; ++ch) {                            // block-uniform
+        const long long base = ((long long)blockIdx.x * chunks + ch) * chunk;
         if (base >= seg.n) break;
         const bool vec = (seg.kind != DA3S_SEL_RATIO) && aligned16(seg.a) && base + chunk <= seg.n;
         unsigned int keys[SEL_ITEMS];
@@ -640,9 +640,14 @@ int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, lon
     select_sample_kernel<<<n_segs, SEL_THREADS, 0, st>>>(segs, work, out);
     DA3S_LAUNCH_CHECK(ctx);
     if (max_n > SEL_SAMPLE) {
-        long long bx = (max_n + per_block * SEL_CHUNKS - 1) / (per_block * SEL_CHUNKS);
+        // chunks per block: SEL_CHUNKS for big batches (amortises the block epilogue), fewer when that would leave
+        // the GPU with less than ~8 blocks per SM (a handful of overlap frames: latency, not bandwidth, is the cost)
+        int chunks = SEL_CHUNKS;
+        const long long n_chunks = (max_n + per_block - 1) / per_block;
+        while (chunks > 1 && (n_chunks + chunks - 1) / chunks * n_segs < (long long)ctx->sm_count * 8) chunks >>= 1;
+        long long bx = (n_chunks + chunks - 1) / chunks;
         if (bx > 2147483647LL) return DA3S_EINVAL;
-        select_count_kernel<<<dim3((unsigned int)bx, n_segs), SEL_THREADS, 0, st>>>(segs, work, cand, cand_cap, tickets);
+        select_count_kernel<<<dim3((unsigned int)bx, n_segs), SEL_THREADS, 0, st>>>(segs, work, cand, cand_cap, tickets, chunks);
         DA3S_LAUNCH_CHECK(ctx);
         if (!big) {
             select_resolve_kernel<<<n_segs, SEL_RESOLVE_THREADS, 0, st>>>(segs, work, out);

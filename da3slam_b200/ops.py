@@ -221,14 +221,19 @@ def select_value_view(d_out: torch.Tensor) -> torch.Tensor:
 class SelectPlan:
     """A prebuilt device segment table: run() only enqueues the three selection passes."""
 
-    def __init__(self, segments, device):
-        self.device = device
+    def __init__(self, segments, device, private_ctx: bool = False):
+        self.device = torch.device(device)
         self.n = len(segments)
         self.d_segs, self.max_n, self._keep = _build_segs(segments, device)
         self.out = torch.empty((self.n, SELECT_OUT_BYTES), dtype=torch.uint8, device=device)
+        self.ctx = None
+        if private_ctx:                  # its own da3s_ctx (= its own scratch): may run on a side stream next to other calls
+            need = (4 << 20) + self.n * ((self.max_n // 8 + (1 << 16)) * 4 + (1 << 16))
+            with torch.cuda.device(self.device):
+                self.ctx = Context(self.device, need)
 
     def run(self) -> torch.Tensor:
-        ctx = context(self.device)
+        ctx = self.ctx or context(self.device)
         rc = ctx.lib.da3s_select(ctx.h, _ptr(self.d_segs), self.n, self.max_n, _ptr(self.out), _stream(self.d_segs))
         L.check(rc, "da3s_select")
         return self.out

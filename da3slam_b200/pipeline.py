@@ -172,7 +172,8 @@ class SequencePlan:
     read() synchronises and returns host/trimmed results.  This is one "step" of bench.py."""
 
     def __init__(self, submaps, overlap=1, voxel=0.02, conf_percentile=65.0, unproject_mode="fast", table_slots=None,
-                 max_voxels=None, sample_idx=None, export=True, skip_overlap=True, fuse_export=True, exchange=None, **opt_kw):
+                 max_voxels=None, sample_idx=None, export=True, skip_overlap=True, fuse_export=True, exchange=None,
+                 overlap_percentile=True, **opt_kw):
         self.submaps = submaps
         self.n = len(submaps)
         self.dev = submaps[0].depth.device
@@ -181,6 +182,7 @@ class SequencePlan:
         self.voxel = float(voxel)
         self.mode = unproject_mode
         self.export = export
+        self.side = None
         # exchange: a sharding.VoxelExchange -> the step ends with the multi-GPU merge of the rank-local grids
         # (each rank keeps the voxels whose key it owns) instead of a local compaction
         self.exchange = exchange
@@ -201,7 +203,12 @@ class SequencePlan:
             self.first = [0] + [overlap if skip_overlap else 0] * (self.n - 1)
             segs = [dict(a=sm.conf[f0:], kind=L.SEL_POSITIVE, stat=L.SEL_PERCENTILE, percent=float(min(conf_percentile, 99.9)))
                     for sm, f0 in zip(submaps, self.first)]
-            self.percentiles = ops.SelectPlan(segs, self.dev)
+            # the export thresholds depend on the confidence maps only, not on the alignment: with overlap_percentile
+            # the pairs are aligned on a high-priority side stream (its short dependent kernels are scheduled first)
+            # while the thresholds are selected on the caller's stream with their own da3s_ctx (= own scratch)
+            self.side = torch.cuda.Stream(self.dev, priority=-1) if overlap_percentile else None
+            self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
+            self.percentiles = ops.SelectPlan(segs, self.dev, private_ctx=overlap_percentile)
             total = sum((self.F - f0) * self.H * self.W for f0 in self.first)
             if table_slots is None:
                 table_slots = 1 << max(12, int(np.ceil(np.log2(max(total // 4, 4096)))))
@@ -243,8 +250,19 @@ class SequencePlan:
         `after_align()` right after the Sim(3) rows have been enqueued — the place to start their exchange
         between ranks so that it overlaps with the export of this rank's own submaps."""
         mark = mark or (lambda name: None)
-        self.rows, _, _ = ops.align_pairs(self.pair_table, self.n_pairs, self.overlap, self.H, self.W, self.opts,
-                                          self.sample_idx)
+        main = torch.cuda.current_stream(self.dev)
+        if self.export and self.side is not None:
+            self.fork.record(main)                                   # inputs are ready where the caller's stream is now
+            self.side.wait_event(self.fork)
+            with torch.cuda.stream(self.side):
+                self.rows, _, _ = ops.align_pairs(self.pair_table, self.n_pairs, self.overlap, self.H, self.W, self.opts,
+                                                  self.sample_idx)
+            self.join.record(self.side)
+            self.percentiles.run()
+            main.wait_event(self.join)
+        else:
+            self.rows, _, _ = ops.align_pairs(self.pair_table, self.n_pairs, self.overlap, self.H, self.W, self.opts,
+                                              self.sample_idx)
         mark("align")
         if after_align is not None:
             after_align()
@@ -252,7 +270,8 @@ class SequencePlan:
         if not self.export:
             mark("chain")
             return
-        self.percentiles.run()
+        if self.side is None:
+            self.percentiles.run()
         mark("percentile")
         self.grid.begin()
         mark("voxel_clear")

@@ -553,9 +553,11 @@ def test_sequence_plan_end_to_end(cuda):
     subs, gt = synth.make_sequence(n, F, H, W, overlap=1, seed=77, with_images=True)
     dsubs = [DeviceSubmap.from_prediction(s, cuda) for s in subs]
     # two-kernel export (keeps the per-point arrays, checked below) and the fused export (depth -> grid)
-    plan = SequencePlan(dsubs, overlap=1, voxel=0.05, conf_percentile=65.0, table_slots=1 << 16, world=1, fuse_export=False)
+    # ... and: percentile thresholds selected in line vs on the side stream next to the alignment
+    plan = SequencePlan(dsubs, overlap=1, voxel=0.05, conf_percentile=65.0, table_slots=1 << 16, world=1, fuse_export=False,
+                        overlap_percentile=False)
     fused = SequencePlan(dsubs, overlap=1, voxel=0.05, conf_percentile=65.0, table_slots=1 << 16, world=1, fuse_export=True)
-    assert fused.fuse_export and not plan.fuse_export
+    assert fused.fuse_export and not plan.fuse_export and fused.side is not None and plan.side is None
     for _ in range(2):                                        # twice: the grid must come back clean
         plan.run()
         out = plan.read(sort=True)
