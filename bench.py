@@ -297,7 +297,7 @@ def gpu_arm(args, w, rank, world):
 
     # ---- timed region: device-resident inputs ----
     clocks = ClockSampler(local) if rank == 0 else None
-    launches0 = ctx.launches
+    launches0 = plan.launches
     all_events = []
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
@@ -309,7 +309,7 @@ def gpu_arm(args, w, rank, world):
         all_events.append(ev)
     t_end.record()
     barrier()
-    launches = ctx.launches - launches0
+    launches = plan.launches - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     clock_info = clocks.stop() if clocks else None
     if world > 1:

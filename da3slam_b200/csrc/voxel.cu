@@ -91,7 +91,47 @@ __global__ void voxel_clear_kernel(unsigned long long* acc, long long slots) {
 // confidence keep rate that is ~3x fewer trips through the dependent load chain
 // (mask -> xyz -> key -> record) that bounds this kernel.
 #define VI_THREADS 256
+#ifndef VI_MIN_BLOCKS
+#define VI_MIN_BLOCKS 6
+#endif
 #define VI_QUEUE 256                        // per-warp ring of point indices (>= 31 left over + 128 new)
+
+// Add one (already merged) contribution to the voxel `key`.  The thread that claims an empty slot WRITES the
+// record (all 64 bytes, so the line is never fetched from DRAM and never needs clearing between uses) while the key
+// carries VOX_BUSY, fences, then publishes the key; every later contribution is five 64-bit integer additions.
+// A thread that meets its own key with VOX_BUSY set waits for the publication (a few hundred cycles; the claimer is
+// in another warp — lanes of one warp never hold the same key here — and always makes progress).
+#define VOX_BUSY 0x8000000000000000ull      // keys use 63 bits
+__device__ __forceinline__ bool vox_commit(unsigned long long* __restrict__ acc, long long slots, unsigned long long key,
+                                           unsigned long long sx, unsigned long long sy, unsigned long long sz,
+                                           unsigned long long cr, unsigned long long gb) {
+    unsigned long long slot = vox_slot0(key, slots);
+    for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
+        unsigned long long* rec = VOX_REC_PTR(acc, slots, slot);
+        unsigned long long* kp = VOX_KEY_PTR(acc, slots, slot);
+        unsigned long long cur = *((volatile unsigned long long*)kp);
+        if (cur == VOX_EMPTY) {
+            cur = atomicCAS(kp, VOX_EMPTY, key | VOX_BUSY);
+            if (cur == VOX_EMPTY) {
+                // two 256-bit stores = two whole 32-byte sectors (sm_100): nothing to merge with, nothing fetched
+                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec), "l"(0ull), "l"(sx), "l"(sy), "l"(sz) : "memory");
+                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + 4), "l"(cr), "l"(gb), "l"(0ull), "l"(0ull) : "memory");
+                // release store: the record is visible device-wide before the key is (no L1 invalidation, unlike __threadfence)
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(kp), "l"(key) : "memory");
+                return true;
+            }
+        }
+        if ((cur & ~VOX_BUSY) == key) {
+            while (cur & VOX_BUSY) cur = *((volatile unsigned long long*)kp);
+            atomicAdd(rec + 1, sx); atomicAdd(rec + 2, sy); atomicAdd(rec + 3, sz);
+            atomicAdd(rec + 4, cr);
+            if (gb) atomicAdd(rec + 5, gb);
+            return true;
+        }
+        slot = (slot + VOX_STEP) & (unsigned long long)(slots - 1);
+    }
+    return false;
+}
 
 // one batch of up to 32 points held in registers: float64 quantisation, in-warp merge of the lanes that fall
 // in the same voxel, then probe / claim / five additions by the merged lanes.  Every lane of the warp calls it.
@@ -155,23 +195,7 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
         }
         if (lane != leader) return;
     }
-    unsigned long long slot = vox_slot0(key, slots);
-    for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
-        unsigned long long* rec = VOX_REC_PTR(acc, slots, slot);
-        unsigned long long* kp = VOX_KEY_PTR(acc, slots, slot);
-        unsigned long long cur = *((volatile unsigned long long*)kp);
-        if (cur == VOX_EMPTY) {
-            cur = atomicCAS(kp, VOX_EMPTY, key);
-            if (cur == VOX_EMPTY) cur = key;
-        }
-        if (cur == key) {
-            atomicAdd(rec + 1, sx); atomicAdd(rec + 2, sy); atomicAdd(rec + 3, sz);
-            atomicAdd(rec + 4, cr);
-            if (has_rgb) atomicAdd(rec + 5, gb);
-            return;
-        }
-        slot = (slot + VOX_STEP) & (unsigned long long)(slots - 1);
-    }
+    if (vox_commit(acc, slots, key, sx, sy, sz, cr, gb)) return;
     atomicAdd(&counters[1], cr >> 32);                              // table full: reported by finish
 }
 
@@ -197,7 +221,7 @@ __device__ __forceinline__ void voxel_insert_point(bool active, long long i, con
 #define VI_TILES_PER_WARP 2
 #define VI_TILES_PER_BLOCK (VI_TILES_PER_WARP * VI_THREADS / 32)
 
-__global__ void __launch_bounds__(VI_THREADS)
+__global__ void __launch_bounds__(VI_THREADS, VI_MIN_BLOCKS)
 voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job single, int n_jobs, long long chunks_per_job,
                     int width, float voxel, unsigned long long* __restrict__ acc,
                     long long slots, unsigned long long* __restrict__ counters /* [0]=voxels (set by finish) [1]=dropped */) {
@@ -301,7 +325,7 @@ struct ExportArgs {
     unsigned long long* acc; long long slots; unsigned long long* counters;
 };
 
-__global__ void __launch_bounds__(VI_THREADS)
+__global__ void __launch_bounds__(VI_THREADS, VI_MIN_BLOCKS)
 export_voxel_kernel(ExportArgs a) {
     __shared__ unsigned long long queue[VI_THREADS / 32][VI_QUEUE];     // (depth bits << 32) | (v << 16) | u
     __shared__ float fc_sh[VI_THREADS / 32][EX_CONST];
@@ -557,11 +581,7 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
             if (!occ[q]) continue;
             const int j = j0 + q;
             const long long s = base + (long long)j * 32 + lane;
-            unsigned long long* rec = VOX_REC_PTR(acc, slots, s);
-            *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2(VOX_EMPTY, 0ull);
-            (*VOX_KEY_PTR(acc, slots, s)) = VOX_EMPTY;
-            *reinterpret_cast<ulonglong2*>(rec + 2) = make_ulonglong2(0ull, 0ull);
-            *reinterpret_cast<ulonglong2*>(rec + 4) = make_ulonglong2(0ull, 0ull);
+            (*VOX_KEY_PTR(acc, slots, s)) = VOX_EMPTY;      // the record itself is rewritten by the next claimer (vox_commit)
             if ((long long)oo[q] >= max_voxels) continue;
             const unsigned long long k64 = key[j], cr = rb[q].x, gb = rb[q].y, cnt = cr >> 32, o = oo[q];
             const double inv = 1.0 / 4294967296.0;
@@ -690,9 +710,6 @@ voxel_send_kernel(unsigned long long* __restrict__ acc, long long slots, const u
             const unsigned long long sx = rec[1];
             const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rec + 2);
             const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(rec + 4);
-            *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2(VOX_EMPTY, 0ull);
-            *reinterpret_cast<ulonglong2*>(rec + 2) = make_ulonglong2(0ull, 0ull);
-            *reinterpret_cast<ulonglong2*>(rec + 4) = make_ulonglong2(0ull, 0ull);
             (*VOX_KEY_PTR(acc, slots, s)) = VOX_EMPTY;
             if ((long long)my_idx < cap) {
                 unsigned long long* dst = peers.inbox[owner] + ((size_t)rank * (size_t)cap + my_idx) * 6;   // NVLink stores
@@ -715,23 +732,7 @@ voxel_merge_kernel(const unsigned long long* __restrict__ inbox, const unsigned 
         const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(seg + i * 6 + 2);
         const ulonglong2 r2 = *reinterpret_cast<const ulonglong2*>(seg + i * 6 + 4);
         const unsigned long long key = r0.x;
-        unsigned long long slot = vox_slot0(key, slots);
-        bool placed = false;
-        for (int probe = 0; probe < VOX_MAX_PROBE && !placed; ++probe) {
-            unsigned long long* rec = VOX_REC_PTR(acc, slots, slot);
-            unsigned long long* kp = VOX_KEY_PTR(acc, slots, slot);
-            unsigned long long cur = *((volatile unsigned long long*)kp);
-            if (cur == VOX_EMPTY) {
-                cur = atomicCAS(kp, VOX_EMPTY, key);
-                if (cur == VOX_EMPTY) cur = key;
-            }
-            if (cur == key) {
-                atomicAdd(rec + 1, r0.y); atomicAdd(rec + 2, r1.x); atomicAdd(rec + 3, r1.y);
-                atomicAdd(rec + 4, r2.x); atomicAdd(rec + 5, r2.y);
-                placed = true;
-            }
-            slot = (slot + VOX_STEP) & (unsigned long long)(slots - 1);
-        }
+        const bool placed = vox_commit(acc, slots, key, r0.y, r1.x, r1.y, r2.x, r2.y);
         if (!placed) atomicAdd(&counters[1], r2.x >> 32);
     }
 }
