@@ -42,7 +42,7 @@ WORKLOADS = {
                     table_slots=0, voxel=0.02, desc="512 submap pairs, 518x518, 1 overlap frame, alignment only"),
     # configs[4]: 1036x1036, 64-frame submaps + global voxel map
     "hires": dict(n_submaps=8, frames=64, H=1036, W=1036, overlap=1, n_hyp=0, outlier=0.0, export=True,
-                  table_slots=1 << 27, voxel=0.02, desc="8 submaps x 64 x 1036x1036, 7 pairs, voxel map"),
+                  table_slots=1 << 24, voxel=0.02, desc="8 submaps x 64 x 1036x1036, 7 pairs, voxel map"),
     # tiny case for CI / smoke runs of this script
     "tiny": dict(n_submaps=4, frames=4, H=64, W=80, overlap=1, n_hyp=0, outlier=0.0, export=True,
                  table_slots=1 << 16, voxel=0.05, desc="4 submaps x 4 x 64x80"),
@@ -486,9 +486,12 @@ def main():
     ap.add_argument("--global-map", action="store_true",
                     help="N > 1: merge the rank-local voxel grids into one global map (da3s_voxel_send over NVLink peer memory)")
     ap.add_argument("--cpu-workers", type=int, default=None)
+    ap.add_argument("--table-slots-log2", type=int, default=None, help="override the workload's voxel table size (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
+    if args.table_slots_log2 is not None and w["table_slots"]:
+        w = dict(w, table_slots=1 << args.table_slots_log2)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
 
