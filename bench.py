@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # BASELINE.json configs[1]: 300 frames, 16-frame submaps (solver.py deque semantics -> 19 submaps / 18 pairs)
     "c3vd300": dict(n_submaps=19, frames=16, H=518, W=518, overlap=1, n_hyp=0, outlier=0.0, export=True,
-                    table_slots=1 << 24, voxel=0.02, desc="300 frames, 19 submaps x 16 x 518x518, 18 pairs"),
+                    table_slots=1 << 25, voxel=0.02, desc="300 frames, 19 submaps x 16 x 518x518, 18 pairs"),
     # configs[2]: 2000 frames, 32-frame submaps, RANSAC 1024 hypotheses (make_image_chunks -> 65 submaps / 64 pairs)
     "seq2000": dict(n_submaps=65, frames=32, H=518, W=518, overlap=1, n_hyp=1024, outlier=0.3, export=True,
                     table_slots=1 << 28, voxel=0.02, desc="2000 frames, 65 submaps x 32 x 518x518, 64 pairs, RANSAC 1024"),

@@ -541,36 +541,52 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
                   float voxel, long long max_voxels,
                   float* __restrict__ xyz_out, uint8_t* __restrict__ rgb_out, int32_t* __restrict__ count_out,
                   long long* __restrict__ key_out) {
+    __shared__ unsigned int s_word[VC_THREADS / 32][VC_ROUNDS], s_excl[VC_THREADS / 32][VC_ROUNDS];
     const double vd = (double)voxel;
-    const unsigned int lane = threadIdx.x & 31;
-    const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + warp;
     const long long base = wid * VC_PER_WARP;
     if (base >= slots) return;
+    // The warp's 512 slots as 16 occupancy words.  The occupied slots are handled DENSELY: lane l of dense round r
+    // takes the (32 r + l)-th occupied slot, so the number of rounds — and of record loads in flight per warp —
+    // follows the voxels, not the table size (a sparser table costs the bitmap and the key scan of the count pass only).
     const unsigned int my_word = lane < VC_ROUNDS ? occ_bits[wid * VC_ROUNDS + lane] : 0u;
-    if (__ballot_sync(0xffffffffu, my_word != 0u) == 0u) return;  // nothing in these 512 slots (warp-uniform)
-    unsigned long long key[VC_ROUNDS];
+    const unsigned int my_cnt = __popc(my_word);
+    unsigned int incl = my_cnt;
 #pragma unroll
-    for (int j = 0; j < VC_ROUNDS; ++j) {                       // keys of occupied slots only
-        const long long s = base + (long long)j * 32 + lane;
-        const unsigned int word = __shfl_sync(0xffffffffu, my_word, j);
-        key[j] = ((word >> lane) & 1u) ? (*VOX_KEY_PTR(acc, slots, s)) : VOX_EMPTY;
+    for (int o = 1; o < VC_ROUNDS; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
     }
-    unsigned long long out = warp_offsets[wid];
-#pragma unroll
-    for (int j0 = 0; j0 < VC_ROUNDS; j0 += 4) {                 // 4 rounds at a time: their record loads overlap
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, VC_ROUNDS - 1);
+    if (total == 0u) return;                                      // nothing in these 512 slots (warp-uniform)
+    if (lane < VC_ROUNDS) { s_word[warp][lane] = my_word; s_excl[warp][lane] = incl - my_cnt; }
+    __syncwarp();
+    const unsigned long long out0 = warp_offsets[wid];
+    for (unsigned int r0 = 0; r0 < total; r0 += 128u) {          // 4 dense rounds at a time: their record loads overlap
         ulonglong2 ra[4], rb[4];                                // (sum_y, sum_z), ((n, sum_r), (sum_g, sum_b))
-        unsigned long long rx[4], oo[4];
+        unsigned long long rx[4], key[4];
+        long long sidx[4];
         bool occ[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int j = j0 + q;
-            occ[q] = key[j] != VOX_EMPTY;
-            const unsigned int m = __ballot_sync(0xffffffffu, occ[q]);
-            oo[q] = out + __popc(m & ((1u << lane) - 1u));
-            out += __popc(m);
+            const unsigned int rank = r0 + 32u * q + lane;
+            occ[q] = rank < total;
             if (occ[q]) {
-                const long long s = base + (long long)j * 32 + lane;
-                unsigned long long* rec = VOX_REC_PTR(acc, slots, s);
+                int w = 0;                                       // word holding the rank-th occupied slot: last excl <= rank
+#pragma unroll
+                for (int step = VC_ROUNDS / 2; step >= 1; step >>= 1)
+                    if (s_excl[warp][w + step] <= rank) w += step;
+                const unsigned int word = s_word[warp][w];
+                unsigned int n = rank - s_excl[warp][w], pos = 0;
+#pragma unroll
+                for (int sh = 16; sh >= 1; sh >>= 1) {           // position of the n-th set bit of `word`
+                    const unsigned int c = __popc((word >> pos) & ((1u << sh) - 1u));
+                    if (n >= c) { n -= c; pos += sh; }
+                }
+                sidx[q] = base + (long long)w * 32 + pos;
+                key[q] = *VOX_KEY_PTR(acc, slots, sidx[q]);
+                const unsigned long long* rec = VOX_REC_PTR(acc, slots, sidx[q]);
                 rx[q] = rec[1];
                 ra[q] = *reinterpret_cast<const ulonglong2*>(rec + 2);
                 rb[q] = *reinterpret_cast<const ulonglong2*>(rec + 4);
@@ -579,11 +595,10 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (!occ[q]) continue;
-            const int j = j0 + q;
-            const long long s = base + (long long)j * 32 + lane;
-            (*VOX_KEY_PTR(acc, slots, s)) = VOX_EMPTY;      // the record itself is rewritten by the next claimer (vox_commit)
-            if ((long long)oo[q] >= max_voxels) continue;
-            const unsigned long long k64 = key[j], cr = rb[q].x, gb = rb[q].y, cnt = cr >> 32, o = oo[q];
+            (*VOX_KEY_PTR(acc, slots, sidx[q])) = VOX_EMPTY; // the record itself is rewritten by the next claimer (vox_commit)
+            const unsigned long long o = out0 + r0 + 32u * q + lane;
+            if ((long long)o >= max_voxels) continue;
+            const unsigned long long k64 = key[q], cr = rb[q].x, gb = rb[q].y, cnt = cr >> 32;
             const double inv = 1.0 / 4294967296.0;
             const unsigned long long sq[3] = {rx[q], ra[q].x, ra[q].y};
             const double k[3] = {(double)((long long)((k64 >> 42) & 0x1FFFFF) - VOX_BIAS),
