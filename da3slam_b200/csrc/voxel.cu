@@ -12,8 +12,9 @@
 //
 // Contention is cut before it reaches L2: points of one warp that fall in the same voxel
 // (neighbouring pixels of a frame usually do) are combined (match.any + shuffles) and issue
-// one set of atomics per distinct voxel.  Compaction (count / scan / emit over the dense key
-// array) resets what it emits, so no separate clearing pass is needed between uses.
+// one commit per distinct voxel (vox_commit: the claimer of a slot writes the record, later
+// contributions add to it).  Compaction (count / scan / emit over the dense key array) resets the
+// keys it emits, so no separate clearing pass is needed between uses.
 //
 // Algorithmic bytes: 12 (+3 rgb, +1 mask) per input point read; 12 (+3) + 4 (+8 key) per
 // occupied voxel written.  Hash-table traffic (random 64 B records in L2/HBM) is what
@@ -468,10 +469,10 @@ extern "C" int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* j
 // Compaction without atomics or barriers, two streaming passes over the DENSE key array:
 //   count  every WARP counts the occupied slots of its fixed range of 512 slots
 //   scan   one block turns the per-warp counts into output offsets (and the total)
-//   emit   every warp re-reads its 16 x 32 keys (all loads in flight together), derives each
-//          occupied slot's output index from warp ballots + its offset, then reads, emits and
-//          RESETS the records, so the table is clean for the next begin() without a clearing
-//          pass.  No __syncthreads: the previous block-synchronous version was bound by exposed
+//   emit   every warp walks the occupied slots of its range densely (occupancy bitmap of the count
+//          pass), reads key + record, emits, and resets the KEY: records are rewritten by the next
+//          claimer, so the table is ready for the next begin() without a clearing pass.
+//          No __syncthreads: the previous block-synchronous version was bound by exposed
 //          DRAM latency (profiles/r1_*: long_scoreboard 70, issue 8 %).
 // Output order = slot order (which of two colliding keys gets the earlier slot depends on the insertion race;
 // the canonical order is ascending key — ops.VoxelGrid.read(sort=True)).
@@ -634,7 +635,7 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
 // bit-identical to inserting all points on one GPU.
 //   count  per warp and destination: occupied slots whose owner is d
 //   scan   one block per destination: exclusive offsets in slot order (deterministic inbox content)
-//   send   re-read keys, read + reset records, store 48-byte records at inbox[owner][rank*cap + offset]
+//   send   re-read keys, read records, reset keys, store 48-byte records at inbox[owner][rank*cap + offset]
 // ---------------------------------------------------------------------------------
 #define VOX_MAX_WORLD 16
 struct VoxPeers { unsigned long long* inbox[VOX_MAX_WORLD]; unsigned long long* counts[VOX_MAX_WORLD]; };
@@ -882,6 +883,6 @@ extern "C" int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxel
     if (n_dropped)
         DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_dropped, ctx->vox_dropped + 1, 8, cudaMemcpyDeviceToDevice, st));
     ctx->vox_active = false;
-    ctx->vox_clean = true;          // every occupied record was reset in place by the compaction pass
+    ctx->vox_clean = true;          // every occupied key was reset in place by the compaction pass
     return DA3S_OK;
 }
