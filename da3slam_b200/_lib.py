@@ -19,7 +19,7 @@ SIM3_PER_FRAME = 0x200
 CAM_CLOSED_FORM, CAM_GENERAL_INV = 0, 1
 SEL_VALUES, SEL_POSITIVE, SEL_RATIO = 0, 1, 2
 SEL_MEDIAN, SEL_PERCENTILE = 0, 1
-UMEYAMA_WEIGHTED, UMEYAMA_MEAN, UMEYAMA_NORMRATIO = 0, 1, 2
+UMEYAMA_WEIGHTED, UMEYAMA_MEAN, UMEYAMA_NORMRATIO, UMEYAMA_LEGACY_TRACE = 0, 1, 2, 3
 ICP_SIM3, ICP_RIGID = 0, 1
 ROW_LEN = 16
 
@@ -82,6 +82,7 @@ SIGNATURES = {
     "da3s_last_cuda_error": (_I, [_P]),
     "da3s_launch_count": (_ULL, [_P]),
     "da3s_enable_peer_access": (_I, [_P, _I]),
+    "da3s_measure_fp32_peak": (_I, [_P, _I, C.POINTER(_D), _P]),
     "da3s_build_cams": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "da3s_unproject_filter": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _F, _F, _P, _P, _P, _P, _P]),
     "da3s_unproject_filter_jobs": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P]),

@@ -34,7 +34,7 @@ extern "C" int da3s_create(int device, size_t workspace_bytes, da3s_ctx** out) {
     c->ws = nullptr;
     cudaError_t e = cudaMalloc((void**)&c->ws, workspace_bytes);
     if (e != cudaSuccess) { int rc = (e == cudaErrorMemoryAllocation) ? DA3S_ENOMEM : DA3S_ECUDA; cudaGetLastError(); delete c; return rc; }
-    c->ws_top = 0; c->last_cuda_error = 0; c->launches = 0;
+    c->ws_top = 0; c->ws_floor = 0; c->last_cuda_error = 0; c->launches = 0;
     c->vox_keys = nullptr; c->vox_acc = nullptr; c->vox_rgbn = nullptr; c->vox_slots = 0; c->vox_dropped = nullptr; c->vox_bytes = 0; c->vox_occ = nullptr; c->vox_clean = false; c->vox_active = false;
     *out = c;
     return DA3S_OK;
@@ -70,6 +70,57 @@ extern "C" int da3s_enable_peer_access(da3s_ctx* ctx, int peer_device) {
 }
 
 // ---------------------------------------------------------------------------------
+// float32 FMA peak of this device, measured (the roofline denominator of the ALU-bound RANSAC scoring kernel)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fp32_peak_kernel(int iters, float seed, float* sink) {
+    // 16 independent chains per thread hide the 4-cycle FFMA latency; 8 resident blocks of 256 threads per SM
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = seed + (float)(threadIdx.x + k);
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 256; ++r) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = fmaf(a[k], m, c);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == 123.456f) sink[0] = s;             // never true: keeps the chains alive
+}
+
+extern "C" int da3s_measure_fp32_peak(da3s_ctx* ctx, int iters, double* tflops_out, void* stream) {
+    if (!ctx || !tflops_out || iters <= 0) return DA3S_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    ws_reset(ctx);
+    WS_ALLOC(ctx, float, sink, 1);
+    cudaEvent_t e0, e1;
+    DA3S_CHECK_CUDA(ctx, cudaEventCreate(&e0));
+    DA3S_CHECK_CUDA(ctx, cudaEventCreate(&e1));
+    const int blocks = ctx->sm_count * 8;
+    fp32_peak_kernel<<<blocks, 256, 0, st>>>(2, 1.0f, sink);            // warm-up
+    DA3S_LAUNCH_CHECK(ctx);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, st);
+        fp32_peak_kernel<<<blocks, 256, 0, st>>>(iters, 1.0f, sink);
+        DA3S_LAUNCH_CHECK(ctx);
+        cudaEventRecord(e1, st);
+        DA3S_CHECK_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * 4096.0 * (double)iters * 256.0 * (double)blocks;
+        if (ms > 0.0f && flop / (ms * 1e-3) / 1e12 > best) best = flop / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops_out = best;
+    return DA3S_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // host-buffer path: H2D copies, the device pipeline, D2H of the rows, one synchronise.
 // ---------------------------------------------------------------------------------
 __global__ void fill_pairs_kernel(da3s_pair* pairs, int n_pairs, long long M, int overlap,
@@ -97,8 +148,9 @@ extern "C" int da3s_align_pairs_host(da3s_ctx* ctx, int n_pairs, int overlap, in
     if ((M * 4) % 16 != 0) return DA3S_EALIGN;             // packed pairs must keep 16-byte alignment
     const size_t map_bytes = sizeof(float) * (size_t)n_pairs * M;
     const size_t nf = (size_t)n_pairs * overlap;
-    // input staging lives at the start of the workspace; da3s_align_pairs resets the bump
-    // pointer, so reserve the staging area by sub-allocating from a temporary context view
+    // input staging lives at the start of the workspace; da3s_align_pairs resets the bump pointer to
+    // ctx->ws_floor, which is raised above the staging area for the duration of the nested call
+    ctx->ws_floor = 0;
     ws_reset(ctx);
     WS_ALLOC(ctx, float, d_dA, (size_t)n_pairs * M);
     WS_ALLOC(ctx, float, d_cA, (size_t)n_pairs * M);
@@ -131,12 +183,10 @@ extern "C" int da3s_align_pairs_host(da3s_ctx* ctx, int n_pairs, int overlap, in
     fill_pairs_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(d_pairs, n_pairs, M, overlap, d_dA, d_cA, d_dB, d_cB,
                                                              d_cam, d_cam + nf);
     DA3S_LAUNCH_CHECK(ctx);
-    // run the device pipeline on the remainder of the workspace
-    unsigned char* ws_save = ctx->ws; size_t bytes_save = ctx->ws_bytes;
-    size_t used = (ctx->ws_top + 255) & ~(size_t)255;
-    ctx->ws += used; ctx->ws_bytes -= used;
+    // run the device pipeline on the remainder of the workspace (an active voxel table keeps its tail)
+    ctx->ws_floor = ctx->ws_top;
     rc = da3s_align_pairs(ctx, d_pairs, n_pairs, overlap, H, W, opts, d_idx, d_rows, nullptr, nullptr, stream);
-    ctx->ws = ws_save; ctx->ws_bytes = bytes_save;
+    ctx->ws_floor = 0;
     if (rc != DA3S_OK) return rc;
     DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(sim3_rows, d_rows, sizeof(double) * (size_t)n_pairs * DA3S_ROW_LEN,
                                          cudaMemcpyDeviceToHost, st));

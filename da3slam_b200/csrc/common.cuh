@@ -17,6 +17,7 @@ struct da3s_ctx {
     unsigned char* ws;          // workspace base (cudaMalloc, 256-byte aligned)
     size_t ws_bytes;
     size_t ws_top;              // bump pointer for the current call
+    size_t ws_floor;            // ws_reset() returns here: a caller's staging area below it survives nested entry points
     int last_cuda_error;
     unsigned long long launches;
     // voxel hash-table state (lives at the END of the workspace between begin/finish)
@@ -50,7 +51,7 @@ struct da3s_ctx {
     } while (0)
 
 // ---- workspace bump allocator (per call; nothing is allocated after create) -------
-static inline void ws_reset(da3s_ctx* c) { c->ws_top = 0; }
+static inline void ws_reset(da3s_ctx* c) { c->ws_top = c->ws_floor; }
 static inline void* ws_alloc(da3s_ctx* c, size_t bytes) {
     size_t start = (c->ws_top + 255) & ~(size_t)255;
     size_t limit = c->ws_bytes - c->vox_bytes;      // the voxel table owns the tail while active

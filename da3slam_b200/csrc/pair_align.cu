@@ -1380,16 +1380,17 @@ extern "C" int da3s_umeyama_points(da3s_ctx* ctx, const void* src, const void* d
                                    int variant, double* sim3_row, void* stream) {
     if (!ctx || !src || !dst || !sim3_row || n <= 0) return DA3S_EINVAL;
     if ((idx_src == nullptr) != (idx_dst == nullptr)) return DA3S_EINVAL;
-    if (variant < 0 || variant > 2) return DA3S_EINVAL;
+    if (variant < 0 || variant > 3) return DA3S_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     ws_reset(ctx);
     PointsArgs a;
-    a.src = src; a.dst = dst; a.weights = (variant == DA3S_UMEYAMA_WEIGHTED) ? weights : nullptr; a.weights_f64 = weights_f64;
+    a.src = src; a.dst = dst; a.weights = (variant == DA3S_UMEYAMA_WEIGHTED || variant == DA3S_UMEYAMA_LEGACY_TRACE) ? weights : nullptr; a.weights_f64 = weights_f64;
     a.conf_src = nullptr; a.conf_dst = nullptr; a.n = n; a.idx_src = idx_src; a.idx_dst = idx_dst; a.irls = 0;
     a.norm_state = nullptr;
     long long count = idx_src ? n_idx : n;
     if (count <= 0) return DA3S_EINVAL;
-    int nb = points_common(ctx, a, count, 0, variant == DA3S_UMEYAMA_WEIGHTED ? SOLVE_WEIGHTED : SOLVE_MEAN, 1.0, 1, 0.0, 0, sim3_row);
+    const int solve = variant == DA3S_UMEYAMA_WEIGHTED ? SOLVE_WEIGHTED : (variant == DA3S_UMEYAMA_LEGACY_TRACE ? SOLVE_LEGACY_TRACE : SOLVE_MEAN);
+    int nb = points_common(ctx, a, count, 0, solve, 1.0, 1, 0.0, 0, sim3_row);
     if (nb < 0) return nb;
     pair_state_init_kernel<<<1, 32, 0, st>>>(a.pa);
     DA3S_LAUNCH_CHECK(ctx);

@@ -145,8 +145,11 @@ HD void svd3(const double* A, double* U, double* S, double* V) {
 // Variants of the closed form (which epsilons, which determinant test):
 //   0  utils/align.py:14-40   weights normalised by (sum w + 1e-8); var + 1e-8; det(U Vt)
 //   1  align_geometry.py:59-82  unweighted means; cov, var divided by N; var + 1e-12; det(U) det(Vt)
+//   2  utils/align.py:42-92   as 0, but the scale is trace(Sigma) / (var + 1e-8) — the reference's legacy solver,
+//      wrong for rotated data yet part of its API (weighted_umeyama_alignment0); reproduced, not corrected
 #define SOLVE_WEIGHTED 0
 #define SOLVE_MEAN 1
+#define SOLVE_LEGACY_TRACE 2
 
 // mom: raw moments (world or camera frame).  wscale: every weight is divided by this first
 // (utils/align.py:194: max(w) + 1e-8; 1.0 when not in IRLS).  Writes s, R[9], t[3].
@@ -154,8 +157,8 @@ HD void svd3(const double* A, double* U, double* S, double* V) {
 HD bool umeyama_from_moments(const double* mom, double wscale, int variant, double* s_out, double* R, double* t) {
     double S0 = mom[MOM_S0] / wscale;
     double den, eps_var;
-    if (variant == SOLVE_WEIGHTED) { den = S0 + 1e-8; eps_var = 1e-8; }
-    else                           { den = mom[MOM_N]; eps_var = 1e-12; }
+    if (variant == SOLVE_MEAN) { den = mom[MOM_N]; eps_var = 1e-12; }
+    else                       { den = S0 + 1e-8; eps_var = 1e-8; }
     bool ok = den > 0 && S0 > 0;
     double mx[3], my[3], Sx[3], Sy[3];
     for (int i = 0; i < 3; ++i) {
@@ -173,7 +176,7 @@ HD bool umeyama_from_moments(const double* mom, double wscale, int variant, doub
     double U[9], Sg[3], V[9];
     svd3(cov, U, Sg, V);
     double dsign = 1.0;
-    if (variant == SOLVE_WEIGHTED) {
+    if (variant != SOLVE_MEAN) {
         double UVt[9];
         mat3_mul_bt(U, V, UVt);
         if (det3(UVt) < 0) dsign = -1.0;
@@ -184,6 +187,7 @@ HD bool umeyama_from_moments(const double* mom, double wscale, int variant, doub
     for (int i = 0; i < 3; ++i) { Ud[3 * i] = U[3 * i]; Ud[3 * i + 1] = U[3 * i + 1]; Ud[3 * i + 2] = U[3 * i + 2] * dsign; }
     mat3_mul_bt(Ud, V, R);
     double s = (Sg[0] + Sg[1] + dsign * Sg[2]) / (var + eps_var);
+    if (variant == SOLVE_LEGACY_TRACE) s = (cov[0] + cov[4] + cov[8]) / (var + eps_var);      // utils/align.py:83-87
     double Rm[3];
     mat3_vec(R, mx, Rm);
     for (int i = 0; i < 3; ++i) t[i] = my[i] - s * Rm[i];

@@ -114,8 +114,11 @@ unproject_filter_kernel(K1Args a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // block-uniform switches, evaluated once; the per-pixel test below is branch-free
-    const bool f_gt = conf && (a.flags & DA3S_MASK_CONF_GT), f_ge = conf && (a.flags & DA3S_MASK_CONF_GE);
-    const bool f_floor = conf && (a.flags & DA3S_MASK_CONF_FLOOR), f_depth = a.flags & DA3S_MASK_DEPTH;
+    // a NaN threshold is what da3s_select returns for a segment without usable confidences: the reference then keeps
+    // every point (viewer.py:333-338: `else: conf_mask = np.ones(...)`), so the confidence tests are switched off
+    const bool use_conf = conf && !(thr != thr);
+    const bool f_gt = use_conf && (a.flags & DA3S_MASK_CONF_GT), f_ge = use_conf && (a.flags & DA3S_MASK_CONF_GE);
+    const bool f_floor = use_conf && (a.flags & DA3S_MASK_CONF_FLOOR), f_depth = a.flags & DA3S_MASK_DEPTH;
     const bool f_wz = a.flags & DA3S_MASK_WORLD_Z;
     const float cfloor = a.conf_floor, deps = a.depth_eps;
     typedef typename K1Val<MODE>::type CT;

@@ -160,20 +160,17 @@ def irls_pixel(point_map1, point_map2, conf1, conf2, min_points=100, max_iterati
 # ------------------------------------------------------------------------------------------
 # submap pairs from host predictions (the end-to-end path bench.py times)
 # ------------------------------------------------------------------------------------------
-def align_prediction_pairs(pairs, overlap=1, sample_idx=None, **opt_kw):
-    """pairs: list of (prev_prediction, cur_prediction) with HOST numpy fields.  Goes through
-    da3s_align_pairs_host: host->device copies, the batched device pipeline, rows back.
-    Returns [n,16] float64 rows (include/da3s.h DA3S_ROW_*)."""
+def align_pairs_host_arrays(dA, cA, KA, EA, dB, cB, KB, EB, sample_idx=None, **opt_kw):
+    """da3s_align_pairs_host on prepared HOST arrays (pageable numpy, or numpy views of pinned torch tensors):
+    depth/conf [n,overlap,H,W] float32 per side, K [n,overlap,3,3], E [n,overlap,3,4] float32.  The library copies
+    them in, runs the batched device pipeline, copies the [n,16] float64 rows out and synchronises."""
     import ctypes as C
-    n = len(pairs)
-    o = overlap
-
-    def stack(which, key, sl):
-        return np.ascontiguousarray(np.stack([np.asarray(_get(p[which], key))[sl] for p in pairs]), dtype=np.float32)
-    tail, head = slice(-o, None), slice(0, o)
-    dA, cA, KA, EA = (stack(0, k, tail) for k in ("depth", "conf", "intrinsics", "extrinsics"))
-    dB, cB, KB, EB = (stack(1, k, head) for k in ("depth", "conf", "intrinsics", "extrinsics"))
-    _, _, H, W = dA.shape
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (dA, cA, KA, EA, dB, cB, KB, EB)]
+    dA, cA, KA, EA, dB, cB, KB, EB = arrs
+    n, o, H, W = dA.shape
+    for a, shp in zip(arrs, [(n, o, H, W), (n, o, H, W), (n, o, 3, 3), (n, o, 3, 4)] * 2):
+        if a.shape != shp:
+            raise ValueError(f"align_pairs_host_arrays: expected shape {shp}, got {a.shape}")
     opts = L.default_opts(**opt_kw)
     need = 4 * dA.nbytes + (256 << 20)
     dev = _device()
@@ -181,7 +178,11 @@ def align_prediction_pairs(pairs, overlap=1, sample_idx=None, **opt_kw):
     rows = np.empty((n, L.ROW_LEN), np.float64)
     si = None
     if opts.n_hyp > 0:
+        if sample_idx is None:
+            raise ValueError("n_hyp > 0 needs sample_idx [n_pairs, n_hyp, 3]")
         si = np.ascontiguousarray(sample_idx, np.int32)
+        if si.shape != (n, opts.n_hyp, 3):
+            raise ValueError(f"sample_idx must be [{n}, {opts.n_hyp}, 3], got {si.shape}")
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     P = C.c_void_p
     rc = ctx.lib.da3s_align_pairs_host(ctx.h, n, o, H, W, P(dA.ctypes.data), P(cA.ctypes.data), P(KA.ctypes.data),
@@ -190,6 +191,20 @@ def align_prediction_pairs(pairs, overlap=1, sample_idx=None, **opt_kw):
                                        P(rows.ctypes.data), st)
     L.check(rc, "da3s_align_pairs_host")
     return rows
+
+
+def align_prediction_pairs(pairs, overlap=1, sample_idx=None, **opt_kw):
+    """pairs: list of (prev_prediction, cur_prediction) with HOST numpy fields.  Goes through
+    da3s_align_pairs_host: host->device copies, the batched device pipeline, rows back.
+    Returns [n,16] float64 rows (include/da3s.h DA3S_ROW_*)."""
+    o = overlap
+
+    def stack(which, key, sl):
+        return np.ascontiguousarray(np.stack([np.asarray(_get(p[which], key))[sl] for p in pairs]), dtype=np.float32)
+    tail, head = slice(-o, None), slice(0, o)
+    dA, cA, KA, EA = (stack(0, k, tail) for k in ("depth", "conf", "intrinsics", "extrinsics"))
+    dB, cB, KB, EB = (stack(1, k, head) for k in ("depth", "conf", "intrinsics", "extrinsics"))
+    return align_pairs_host_arrays(dA, cA, KA, EA, dB, cB, KB, EB, sample_idx=sample_idx, **opt_kw)
 
 
 def align_two_predictions(prev, cur, overlap=1, **opt_kw):

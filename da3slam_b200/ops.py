@@ -58,6 +58,38 @@ def context(device=None, workspace_bytes: int | None = None) -> Context:
     return ctx
 
 
+class _NoRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NVTX = None
+
+
+def nvtx_range(name: str):
+    """NVTX range around a stage (tracing row): visible in nsys / ncu --nvtx timelines.  Enabled with
+    DA3S_NVTX=1 (a push/pop pair costs ~1 us of host time per stage, so it is off in the timed default)."""
+    global _NVTX
+    if _NVTX is None:
+        import os
+        _NVTX = os.environ.get("DA3S_NVTX", "0") not in ("", "0")
+    if not _NVTX:
+        return _NoRange()
+    return torch.cuda.nvtx.range(name)
+
+
+def fp32_peak_tflops(device=None, iters: int = 64) -> float:
+    """float32 FMA throughput of the device measured with the library's microbenchmark kernel (synchronises)."""
+    ctx = context(device)
+    out = C.c_double(0.0)
+    st = C.c_void_p(torch.cuda.current_stream(ctx.device).cuda_stream)
+    L.check(ctx.lib.da3s_measure_fp32_peak(ctx.h, int(iters), C.byref(out), st), "da3s_measure_fp32_peak")
+    return float(out.value)
+
+
 def _stream(t: torch.Tensor):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
@@ -304,12 +336,13 @@ def make_pairs(entries, device) -> torch.Tensor:
 
 
 def align_pairs(pairs: torch.Tensor, n_pairs: int, overlap: int, H: int, W: int, opts: L.AlignOpts,
-                sample_idx: torch.Tensor | None = None, want_aux=False, want_counts=False):
+                sample_idx: torch.Tensor | None = None, want_aux=False, want_counts=False, rows_out=None):
     """Runs the whole pair pipeline asynchronously; returns (rows [n,16] f64, aux [n,8] f64 or None,
-    counts [n,n_hyp] i32 or None) as CUDA tensors."""
+    counts [n,n_hyp] i32 or None) as CUDA tensors.  rows_out: preallocated [n,16] float64 result buffer."""
     dev = pairs.device
     ctx = context(dev)
-    rows = torch.empty((n_pairs, L.ROW_LEN), dtype=torch.float64, device=dev)
+    rows = rows_out if rows_out is not None else torch.empty((n_pairs, L.ROW_LEN), dtype=torch.float64, device=dev)
+    assert rows.shape == (n_pairs, L.ROW_LEN) and rows.dtype == torch.float64 and rows.is_contiguous()
     aux = torch.zeros((n_pairs, L.AUX_DOUBLES), dtype=torch.float64, device=dev) if want_aux else None
     counts = None
     if opts.n_hyp > 0:

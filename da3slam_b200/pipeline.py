@@ -173,7 +173,13 @@ class SequencePlan:
 
     def __init__(self, submaps, overlap=1, voxel=0.02, conf_percentile=65.0, unproject_mode="fast", table_slots=None,
                  max_voxels=None, sample_idx=None, export=True, skip_overlap=True, fuse_export=True, exchange=None,
-                 overlap_percentile=True, **opt_kw):
+                 overlap_percentile=True, pairs=None, export_submaps=None, chain_index=None, n_chain=None,
+                 rows_hook=None, chain=True, **opt_kw):
+        """pairs: list of (i, j) indices into `submaps` (target, source); default = consecutive (k, k + 1).
+        The remaining keywords describe a SHARD of a longer sequence (sharding.shard_sequence): `export_submaps` = the
+        local submaps this rank exports (default all), `chain_index[i]` = position of local submap i in the global
+        chain of `n_chain` submaps (default i), `rows_hook(rows_local) -> rows_global` = the exchange of the Sim(3)
+        rows between ranks (default identity), chain=False skips the accumulation (loop candidates)."""
         self.submaps = submaps
         self.n = len(submaps)
         self.dev = submaps[0].depth.device
@@ -190,26 +196,38 @@ class SequencePlan:
         # False keeps the per-point arrays (self.xyz / self.mask) for callers that want the full cloud
         self.fuse_export = bool(fuse_export) and unproject_mode == "fast"
         self.opts = L.default_opts(**opt_kw)
-        self.n_pairs = self.n - 1
-        self.entries = [pair_entry(submaps[k], submaps[k + 1], overlap) for k in range(self.n_pairs)]
-        self.pair_table = ops.make_pairs(self.entries, self.dev)
+        self.pairs = [(k, k + 1) for k in range(self.n - 1)] if pairs is None else [(int(i), int(j)) for i, j in pairs]
+        self.n_pairs = len(self.pairs)
+        self.rows_hook = rows_hook
+        self.chain = bool(chain)
+        self.chain_index = list(range(self.n)) if chain_index is None else [int(c) for c in chain_index]
+        self.n_chain = int(n_chain) if n_chain is not None else self.n
+        export_ids = list(range(self.n)) if export_submaps is None else [int(i) for i in export_submaps]
+        self.export_ids = export_ids
+        self.entries = [pair_entry(submaps[i], submaps[j], overlap) for i, j in self.pairs]
+        self.pair_table = ops.make_pairs(self.entries, self.dev) if self.entries else None
         self.sample_idx = None
         if self.opts.n_hyp > 0:
+            if sample_idx is None:
+                raise ValueError("SequencePlan: n_hyp > 0 needs sample_idx [n_pairs, n_hyp, 3] (pixel indices drawn by the caller)")
+            if tuple(sample_idx.shape) != (self.n_pairs, self.opts.n_hyp, 3):
+                raise ValueError(f"SequencePlan: sample_idx must be [{self.n_pairs}, {self.opts.n_hyp}, 3], got {tuple(sample_idx.shape)}")
             self.sample_idx = sample_idx.to(self.dev, torch.int32).contiguous()
         self.rows = None
-        self.cum = torch.empty((self.n, 13), dtype=torch.float64, device=self.dev)
+        self.rows_local = torch.empty((max(self.n_pairs, 1), L.ROW_LEN), dtype=torch.float64, device=self.dev)[:self.n_pairs]
+        self.cum = torch.empty((self.n_chain, 13), dtype=torch.float64, device=self.dev)
         if export:
             # frames re-observed by the next submap are exported once (solver.py:100-114 adds them twice)
-            self.first = [0] + [overlap if skip_overlap else 0] * (self.n - 1)
-            segs = [dict(a=sm.conf[f0:], kind=L.SEL_POSITIVE, stat=L.SEL_PERCENTILE, percent=float(min(conf_percentile, 99.9)))
-                    for sm, f0 in zip(submaps, self.first)]
+            self.first = [(overlap if (skip_overlap and self.chain_index[i] > 0) else 0) for i in range(self.n)]
+            segs = [dict(a=submaps[i].conf[self.first[i]:], kind=L.SEL_POSITIVE, stat=L.SEL_PERCENTILE,
+                         percent=float(min(conf_percentile, 99.9))) for i in export_ids]
             # the export thresholds depend on the confidence maps only, not on the alignment: with overlap_percentile
             # the pairs are aligned on a high-priority side stream (its short dependent kernels are scheduled first)
             # while the thresholds are selected on the caller's stream with their own da3s_ctx (= own scratch)
-            self.side = torch.cuda.Stream(self.dev, priority=-1) if overlap_percentile else None
+            self.side = torch.cuda.Stream(self.dev, priority=-1) if (overlap_percentile and self.n_pairs > 0) else None
             self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
             self.percentiles = ops.SelectPlan(segs, self.dev, private_ctx=overlap_percentile)
-            total = sum((self.F - f0) * self.H * self.W for f0 in self.first)
+            total = sum((self.F - self.first[i]) * self.H * self.W for i in export_ids)
             if table_slots is None:
                 table_slots = 1 << max(12, int(np.ceil(np.log2(max(total // 4, 4096)))))
                 table_slots = min(table_slots, 1 << 27)
@@ -218,79 +236,94 @@ class SequencePlan:
             self.grid = ops.VoxelGrid(self.dev, table_slots, max_voxels, submaps[0].images is not None)
             if self.fuse_export:
                 frames = []
-                for k, (sm, f0) in enumerate(zip(submaps, self.first)):
+                for e, i in enumerate(export_ids):
+                    sm, f0 = submaps[i], self.first[i]
                     for f in range(f0, self.F):
-                        frames.append(dict(depth=sm.depth[f], conf=sm.conf[f], cam=sm.cams[f], sim3=self.cum[k],
-                                           conf_thr=self.percentiles.value_ptr_tensor(k),
+                        frames.append(dict(depth=sm.depth[f], conf=sm.conf[f], cam=sm.cams[f], sim3=self.cum[self.chain_index[i]],
+                                           conf_thr=self.percentiles.value_ptr_tensor(e),
                                            rgb=sm.images[f] if sm.images is not None else None))
                 self.export_jobs = self.grid.make_export_jobs(frames)
             else:
-                self.xyz = [torch.empty((self.F - f0, self.H, self.W, 3), dtype=torch.float32, device=self.dev) for f0 in self.first]
-                self.mask = [torch.empty((self.F - f0, self.H, self.W), dtype=torch.uint8, device=self.dev) for f0 in self.first]
+                self.xyz = [torch.empty((self.F - self.first[i], self.H, self.W, 3), dtype=torch.float32, device=self.dev) for i in export_ids]
+                self.mask = [torch.empty((self.F - self.first[i], self.H, self.W), dtype=torch.uint8, device=self.dev) for i in export_ids]
                 # one job per exported frame: static pointers into the submaps, the cumulative Sim(3) table,
                 # the percentile records and the output buffers -> the whole export is ONE unprojection launch
                 jobs = []
-                for k, (sm, f0) in enumerate(zip(submaps, self.first)):
+                for e, i in enumerate(export_ids):
+                    sm, f0 = submaps[i], self.first[i]
                     for f in range(f0, self.F):
-                        jobs.append(dict(depth=sm.depth[f], conf=sm.conf[f], cam=sm.cams[f], sim3=self.cum[k],
-                                         conf_thr=self.percentiles.value_ptr_tensor(k), xyz=self.xyz[k][f - f0],
-                                         mask=self.mask[k][f - f0]))
+                        jobs.append(dict(depth=sm.depth[f], conf=sm.conf[f], cam=sm.cams[f], sim3=self.cum[self.chain_index[i]],
+                                         conf_thr=self.percentiles.value_ptr_tensor(e), xyz=self.xyz[e][f - f0],
+                                         mask=self.mask[e][f - f0]))
                 self.n_jobs = len(jobs)
                 self.job_table = ops.make_frame_jobs(jobs, self.dev)
                 # every submap's cloud goes into the grid in one launch
-                self.rgb_views = [sm.images[f0:] if sm.images is not None else None for sm, f0 in zip(submaps, self.first)]
+                self.rgb_views = [submaps[i].images[self.first[i]:] if submaps[i].images is not None else None for i in export_ids]
                 self.voxel_jobs = self.grid.make_jobs(list(zip(self.xyz, self.rgb_views, self.mask)))
             self.points_per_step = total
         else:
             self.points_per_step = 0
         ops.context(self.dev)            # make sure the context (and its workspace) exists before the first timed run
 
+    def _align(self):
+        if self.n_pairs:
+            ops.align_pairs(self.pair_table, self.n_pairs, self.overlap, self.H, self.W, self.opts, self.sample_idx,
+                            rows_out=self.rows_local)
+
     def run(self, mark=None, after_align=None):
         """Enqueue one step.  `mark(name)` is called between stages (bench.py records CUDA events);
-        `after_align()` right after the Sim(3) rows have been enqueued — the place to start their exchange
-        between ranks so that it overlaps with the export of this rank's own submaps."""
+        `after_align()` right after the Sim(3) rows have been enqueued."""
         mark = mark or (lambda name: None)
         main = torch.cuda.current_stream(self.dev)
         if self.export and self.side is not None:
             self.fork.record(main)                                   # inputs are ready where the caller's stream is now
             self.side.wait_event(self.fork)
-            with torch.cuda.stream(self.side):
-                self.rows, _, _ = ops.align_pairs(self.pair_table, self.n_pairs, self.overlap, self.H, self.W, self.opts,
-                                                  self.sample_idx)
+            with torch.cuda.stream(self.side), ops.nvtx_range("da3s.align"):
+                self._align()
             self.join.record(self.side)
-            self.percentiles.run()
+            with ops.nvtx_range("da3s.export_percentiles"):
+                self.percentiles.run()
             main.wait_event(self.join)
         else:
-            self.rows, _, _ = ops.align_pairs(self.pair_table, self.n_pairs, self.overlap, self.H, self.W, self.opts,
-                                              self.sample_idx)
+            with ops.nvtx_range("da3s.align"):
+                self._align()
         mark("align")
+        # the only data that ever crosses NVLink on the alignment path: the [n,16] rows (sharding.RowExchange)
+        self.rows = self.rows_hook(self.rows_local) if self.rows_hook is not None else self.rows_local
+        if self.rows_hook is not None:
+            mark("row_exchange")
         if after_align is not None:
             after_align()
-        ops.accumulate_sim3(self.rows, out=self.cum)
+        if self.chain:
+            with ops.nvtx_range("da3s.chain"):
+                ops.accumulate_sim3(self.rows, out=self.cum)
         if not self.export:
             mark("chain")
             return
         if self.side is None:
-            self.percentiles.run()
+            with ops.nvtx_range("da3s.export_percentiles"):
+                self.percentiles.run()
         mark("percentile")
         self.grid.begin()
         mark("voxel_clear")
-        if self.fuse_export:
-            self.grid.insert_frames(self.export_jobs, self.H, self.W, self.voxel, world=True, conf_cmp=">=", conf_floor=0.0,
-                                    depth_eps=1e-6)
-            mark("export_fused")
-        else:
-            ops.unproject_filter_jobs(self.job_table, self.n_jobs, self.H, self.W, mode=self.mode, world=True, conf_cmp=">=",
-                                      conf_floor=0.0, depth_eps=1e-6)
-            mark("unproject")
-            self.grid.insert_jobs(self.voxel_jobs, self.voxel, width=self.W)
-            mark("voxel_insert")
-        if self.exchange is not None:
-            self.exchange.merge(self.grid, self.voxel)
-            mark("voxel_merge")
-        else:
-            self.grid.finish(self.voxel)
-            mark("voxel_compact")
+        with ops.nvtx_range("da3s.export"):
+            if self.fuse_export:
+                self.grid.insert_frames(self.export_jobs, self.H, self.W, self.voxel, world=True, conf_cmp=">=", conf_floor=0.0,
+                                        depth_eps=1e-6)
+                mark("export_fused")
+            else:
+                ops.unproject_filter_jobs(self.job_table, self.n_jobs, self.H, self.W, mode=self.mode, world=True, conf_cmp=">=",
+                                          conf_floor=0.0, depth_eps=1e-6)
+                mark("unproject")
+                self.grid.insert_jobs(self.voxel_jobs, self.voxel, width=self.W)
+                mark("voxel_insert")
+        with ops.nvtx_range("da3s.compact"):
+            if self.exchange is not None:
+                self.exchange.merge(self.grid, self.voxel)
+                mark("voxel_merge")
+            else:
+                self.grid.finish(self.voxel)
+                mark("voxel_compact")
 
     @property
     def launches(self) -> int:

@@ -46,6 +46,58 @@ def gather_rows(rows_local: torch.Tensor, n_total: int, group=None) -> torch.Ten
     return torch.cat([o[:n] for o, n in zip(out, sizes)], dim=0)
 
 
+class RowExchange:
+    """The alignment path's only exchange between ranks: every rank's block of [n_local, 16] float64 Sim(3) rows
+    all_gathered into the global [n_total, 16] table (128 B per pair; NCCL over NVLink on GPUs, gloo in the CPU tests).
+    Buffers and the un-padding index are built once, so calling it inside a step only enqueues a copy, the collective
+    and one gather — no allocation, no host synchronisation.  sizes[r] = rows rank r contributes (default: the
+    contiguous block partition of shard_range); blocks are concatenated in rank order."""
+
+    def __init__(self, n_total: int, device, group=None, sizes=None):
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.rank = dist.get_rank(group) if self.active else 0
+        self.sizes = list(sizes) if sizes is not None else shard_sizes(n_total, self.world)
+        assert len(self.sizes) == self.world and sum(self.sizes) == n_total
+        self.n_total = n_total
+        self.pad = max(1, max(self.sizes))
+        dev = torch.device(device)
+        self.send = torch.zeros((self.pad, ROW_LEN), dtype=torch.float64, device=dev)
+        self.recv = torch.zeros((self.world * self.pad, ROW_LEN), dtype=torch.float64, device=dev)
+        idx = [r * self.pad + i for r in range(self.world) for i in range(self.sizes[r])]
+        self.index = torch.tensor(idx, dtype=torch.int64, device=dev)
+        self.out = torch.empty((n_total, ROW_LEN), dtype=torch.float64, device=dev)
+        self.into_tensor = self.active and dist.get_backend(group) == "nccl"
+
+    def __call__(self, rows_local: torch.Tensor) -> torch.Tensor:
+        n_local = self.sizes[self.rank]
+        assert rows_local.shape[0] == n_local
+        if not self.active:
+            return rows_local
+        if n_local:
+            self.send[:n_local].copy_(rows_local)
+        if self.into_tensor:
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        else:
+            dist.all_gather(list(self.recv.view(self.world, self.pad, ROW_LEN).unbind(0)), self.send, group=self.group)
+        torch.index_select(self.recv, 0, self.index, out=self.out)
+        return self.out
+
+
+def shard_sequence(n_submaps: int, rank: int, world: int):
+    """Ownership of ONE sequence of n_submaps spread over the ranks (global map export):
+    rank r owns submaps [a, b) (exports them) and the pairs (k, k + 1) for k in [a, b) with k + 1 < n_submaps, for which
+    it also needs submap b's overlap frames (a halo copy).  Returns dict(a, b, halo, pair_sizes) — pair_sizes[r] for
+    RowExchange (rank order == pair order)."""
+    a, b = shard_range(n_submaps, rank, world)
+    sizes = []
+    for r in range(world):
+        ra, rb = shard_range(n_submaps, r, world)
+        sizes.append(max(0, min(rb, n_submaps - 1) - ra))
+    return dict(a=a, b=b, halo=(b < n_submaps and b > a), pair_sizes=sizes)
+
+
 class VoxelExchange:
     """Inboxes for the multi-GPU voxel merge.  One per rank; built once (collective call).
 

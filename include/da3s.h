@@ -53,6 +53,11 @@ unsigned long long da3s_launch_count(const da3s_ctx* ctx);
  * per peer before da3s_voxel_send is given pointers into that peer's memory */
 int da3s_enable_peer_access(da3s_ctx* ctx, int peer_device);
 
+/* Measures this device's float32 FMA throughput with the library's own microbenchmark kernel (dependent FFMA chains on
+ * every SM, `iters` x 4096 FMAs per thread) and returns TFLOP/s (2 flop per FMA) in *tflops_out (HOST pointer).
+ * Synchronises `stream`.  bench.py uses it as the denominator for the ALU-bound RANSAC scoring kernel. */
+int da3s_measure_fp32_peak(da3s_ctx* ctx, int iters, double* tflops_out, void* stream);
+
 /* ---- camera table ------------------------------------------------------------- */
 /* One entry per frame, device resident.  Built by da3s_build_cams from the network's
  * float32 intrinsics [n,3,3] and world-to-camera extrinsics [n,3,4]
@@ -260,12 +265,13 @@ int da3s_ransac_inlier_mask(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, 
 /* ---- Umeyama on materialised correspondences ----------------------------------------------
  * Replaces utils/align.py:14-40 (weighted_umeyama_alignment; variant 0),
  * align_geometry.py:59-82 (_umeyama_sim3; variant 1) and utils/align.py:224-276
- * (norm-ratio scale + Kabsch; variant 2).  src/dst: [n,3] float32 or float64; weights:
+ * (norm-ratio scale + Kabsch; variant 2) and utils/align.py:42-92 (variant 3).  src/dst: [n,3] float32 or float64; weights:
  * [n] float32/float64 or null (=1); idx_src/idx_dst: optional int64 gather lists of length
  * n_idx (the reference's independent-mask subsample, utils/align.py:145-165). */
 #define DA3S_UMEYAMA_WEIGHTED  0
 #define DA3S_UMEYAMA_MEAN      1
 #define DA3S_UMEYAMA_NORMRATIO 2
+#define DA3S_UMEYAMA_LEGACY_TRACE 3  /* utils/align.py:42-92 (weighted_umeyama_alignment0): scale = trace(Sigma)/var */
 int da3s_umeyama_points(da3s_ctx* ctx, const void* src, const void* dst, int points_f64,
                         const void* weights, int weights_f64, long long n,
                         const long long* idx_src, const long long* idx_dst, long long n_idx,

@@ -75,6 +75,9 @@ def test_umeyama_and_irls_shims(golden, cuda):
     import utils.geometry as ug
     g = golden("umeyama")
     close_sim3(ua.weighted_umeyama_alignment(g["src"], g["dst"], g["w"]), float(g["W_s"]), g["W_R"], g["W_t"])
+    # the legacy solver (utils/align.py:42-92) is reproduced with its trace(Sigma) scale, not replaced by the correct one
+    close_sim3(ua.weighted_umeyama_alignment0(g["src"], g["dst"], g["w"].astype(np.float64)), float(g["W0_s"]), g["W0_R"], g["W0_t"])
+    assert abs(float(g["W0_s"]) - float(g["W_s"])) > 1e-3 * float(g["W_s"])           # the two scales really differ on this input
     close_sim3(ag._umeyama_sim3(g["src"], g["dst"]), float(g["U_s"]), g["U_R"], g["U_t"])
     close_sim3(ua.align_two_point_clouds_umeyama(g["pm1"], g["pm2"]), float(g["N_s"]), g["N_R"], g["N_t"])
     close_sim3(ua.align_two_point_clouds(g["pm1"], g["pm2"]), float(g["Napi_s"]), g["Napi_R"], g["Napi_t"])

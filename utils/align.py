@@ -18,10 +18,10 @@ def weighted_umeyama_alignment(src, dst, w):
 
 
 def weighted_umeyama_alignment0(points1: np.ndarray, points2: np.ndarray, weights: np.ndarray):
-    """Legacy twin (utils/align.py:42-92).  Its scale uses trace(S) instead of the singular
-    values and is wrong for rotated data; kept for API completeness and served
-    by the correct solver."""
-    return _host.umeyama(points1, points2, weights, _L.UMEYAMA_WEIGHTED)
+    """Legacy twin (utils/align.py:42-92), reproduced as the reference computes it: same centroids,
+    covariance and rotation as `weighted_umeyama_alignment`, but scale = trace(Sigma) / (var + 1e-8) — wrong for
+    rotated data, and what callers of this name get upstream."""
+    return _host.umeyama(points1, points2, weights, _L.UMEYAMA_LEGACY_TRACE)
 
 
 def huber_weight(residual: float, delta: float = 1.0) -> float:
