@@ -7,7 +7,7 @@ import math
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libda3s.so")
+LIB_PATH = os.environ.get("DA3S_LIB") or os.path.join(HERE, "libda3s.so")       # DA3S_LIB: a variant build (build.py --out=)
 
 OK, EINVAL, EALIGN, ENOMEM, ECUDA, ETOOFEW = 0, -1, -2, -3, -4, -5
 
@@ -88,6 +88,7 @@ SIGNATURES = {
     "da3s_unproject_filter_jobs": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
     "da3s_apply_sim3": (_I, [_P, _P, _I, _L, _P, _P, _I, _P]),
     "da3s_select": (_I, [_P, _P, _I, _L, _P, _P]),
+    "da3s_filter_points": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _L, _P, _P, _P, _P]),
     "da3s_align_opts_default": (None, [C.POINTER(AlignOpts)]),
     "da3s_align_pairs": (_I, [_P, _P, _I, _I, _I, _I, C.POINTER(AlignOpts), _P, _P, _P, _P, _P]),
     "da3s_accumulate_sim3": (_I, [_P, _P, _I, _P, _P]),
@@ -101,8 +102,8 @@ SIGNATURES = {
     "da3s_voxel_insert": (_I, [_P, _P, _P, _P, _L, _F, _P]),
     "da3s_voxel_insert_jobs": (_I, [_P, _P, _I, _L, _I, _F, _P]),
     "da3s_icp_points": (_I, [_P, _P, _L, _P, _L, _I, _I, _D, _D, _I, _P, _P]),
-    "da3s_voxel_send": (_I, [_P, _I, _I, _P, _P, _L, _P]),
-    "da3s_voxel_merge_inbox": (_I, [_P, _P, _P, _I, _L, _P]),
+    "da3s_voxel_send": (_I, [_P, _I, _I, _P, _P, _P, _ULL, _L, _P]),
+    "da3s_voxel_merge_inbox": (_I, [_P, _P, _P, _P, _ULL, _I, _L, _P]),
     "da3s_unproject_voxel_jobs": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P]),
     "da3s_voxel_finish": (_I, [_P, _F, _L, _P, _P, _P, _P, _P, _P, _P]),
     "da3s_align_pairs_host": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(AlignOpts), _P, _P, _P]),

@@ -39,38 +39,43 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """defines / out: build a VARIANT of the library (extra -D flags) next to the product, e.g. for A/B timing on the
+    GPU box; select it at run time with the environment variable DA3S_LIB (da3slam_b200/_lib.py)."""
+    if out is None and not defines and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
-    build_dir = os.path.join(HERE, "_build")
+    build_dir = os.path.join(HERE, "_build" if out is None else "_build_" + os.path.basename(out).replace(".so", ""))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for s in SOURCES:
         obj = os.path.join(build_dir, s.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, obj, p in procs:
-        out, _ = p.communicate()
-        log.append(f"==== {s} ====\n{out}")
+        text, _ = p.communicate()
+        log.append(f"==== {s} ====\n{text}")
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {s}")
         objs.append(obj)
     with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    target = LIB if out is None else out
+    cmd = [nvcc, "-shared", "-o", target, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
     if verbose:
         print("\n".join(log))
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None)
     print(path)

@@ -35,7 +35,7 @@ extern "C" int da3s_create(int device, size_t workspace_bytes, da3s_ctx** out) {
     cudaError_t e = cudaMalloc((void**)&c->ws, workspace_bytes);
     if (e != cudaSuccess) { int rc = (e == cudaErrorMemoryAllocation) ? DA3S_ENOMEM : DA3S_ECUDA; cudaGetLastError(); delete c; return rc; }
     c->ws_top = 0; c->ws_floor = 0; c->last_cuda_error = 0; c->launches = 0;
-    c->vox_keys = nullptr; c->vox_acc = nullptr; c->vox_rgbn = nullptr; c->vox_slots = 0; c->vox_dropped = nullptr; c->vox_bytes = 0; c->vox_occ = nullptr; c->vox_clean = false; c->vox_active = false;
+    c->vox_acc = nullptr; c->vox_slots = 0; c->vox_counters = nullptr; c->vox_groups = nullptr; c->vox_bytes = 0; c->vox_clean = false; c->vox_active = false;
     *out = c;
     return DA3S_OK;
 }
@@ -74,21 +74,22 @@ extern "C" int da3s_enable_peer_access(da3s_ctx* ctx, int peer_device) {
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fp32_peak_kernel(int iters, float seed, float* sink) {
-    // 16 independent chains per thread hide the 4-cycle FFMA latency; 8 resident blocks of 256 threads per SM
-    float a[16];
+    // 8 independent packed chains per thread hide the 4-cycle FFMA latency; 8 resident blocks of 256 threads per SM
+    // packed float32 (FFMA2 on register pairs: two IEEE FMAs per lane and instruction) — the form the RANSAC kernel uses
+    float2 a[8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) a[k] = seed + (float)(threadIdx.x + k);
-    const float m = 1.0000001f, c = 1e-7f;
+    for (int k = 0; k < 8; ++k) a[k] = make_float2(seed + (float)(threadIdx.x + k), seed - (float)k);
+    const float2 m = make_float2(1.0000001f + seed * 1e-9f, 0.9999999f), c = make_float2(1e-7f * seed, -1e-7f);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int r = 0; r < 256; ++r) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) a[k] = fmaf(a[k], m, c);
+            for (int k = 0; k < 8; ++k) a[k] = __ffma2_rn(a[k], m, c);
         }
     }
     float s = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s += a[k];
+    for (int k = 0; k < 8; ++k) s += a[k].x + a[k].y;
     if (s == 123.456f) sink[0] = s;             // never true: keeps the chains alive
 }
 

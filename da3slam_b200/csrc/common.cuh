@@ -20,13 +20,11 @@ struct da3s_ctx {
     size_t ws_floor;            // ws_reset() returns here: a caller's staging area below it survives nested entry points
     int last_cuda_error;
     unsigned long long launches;
-    // voxel hash-table state (lives at the END of the workspace between begin/finish)
-    unsigned long long* vox_keys;
-    unsigned long long* vox_acc;    // [slots][4]: sum_qx, sum_qy, sum_qz, (count | rgb sums packed separately)
-    unsigned int* vox_rgbn;         // [slots][4]: count, sum_r, sum_g, sum_b
+    // voxel hash-table state (lives at the END of the workspace between begin/finish; layout: voxel.cu)
+    unsigned long long* vox_acc;        // records [slots][8] u64, then the occupancy bitmap [slots/32] u32
     long long vox_slots;
-    unsigned long long* vox_dropped;   // counters[4]: occupied, dropped, -, -
-    unsigned int* vox_occ;             // occupied-slot list [slots]
+    unsigned long long* vox_counters;   // [32] u64: [0] voxels emitted, [1] points dropped (table full), [2] send ticket
+    unsigned int* vox_groups;           // per 512-slot group: occupied count [n] u32, then output offset [n] u64
     size_t vox_bytes;
     bool vox_clean, vox_active;
 };

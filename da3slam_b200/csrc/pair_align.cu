@@ -827,93 +827,158 @@ __global__ void ransac_hyp_kernel(RansacArgs a) {
     }
 }
 
-#define RS_THREADS 256
+#ifndef RS_THREADS
+#define RS_THREADS 64                       // small blocks: the hypothesis range is cut to the VALID hypotheses with 128-wide granularity
+#endif
 #define RS_SUB 512                          // correspondences staged per shared-memory sub-tile
-#define RS_HPT 4                            // hypotheses per thread -> 1024 per launch slice
+#ifndef RS_HPT
+#define RS_HPT 4                            // hypotheses per thread (even: two share every packed instruction)
+#endif
+#define RS_HYP_PER_BLOCK (RS_THREADS * RS_HPT)
+
+// Valid hypotheses of every pair, compacted (stable): coefficient rows [n_pairs][n_hyp][12] (A row-major, then t), their
+// original indices, and the count.  About a third of uniformly drawn 3-pixel samples touch a masked pixel (SPEC 4: such a
+// hypothesis scores 0), and scoring them costs exactly what a valid one costs — so the scoring kernel never sees them.
+__global__ void __launch_bounds__(256)
+ransac_compact_kernel(const float* __restrict__ hyp_A, const float* __restrict__ hyp_t, const uint8_t* __restrict__ hyp_ok, int n_hyp,
+                      float* __restrict__ chyp, int32_t* __restrict__ cidx, int32_t* __restrict__ n_valid) {
+    __shared__ int wsum[8];
+    __shared__ int base_sh;
+    const int pair = blockIdx.x;
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_sh = 0;
+    __syncthreads();
+    for (int h0 = 0; h0 < n_hyp; h0 += 256) {
+        const int h = h0 + threadIdx.x;
+        const bool ok = h < n_hyp && hyp_ok[(size_t)pair * n_hyp + h];
+        const unsigned int m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int before = base_sh;
+        for (unsigned int w = 0; w < warp; ++w) before += wsum[w];
+        if (ok) {
+            const int pos = before + __popc(m & ((1u << lane) - 1u));
+            const size_t o = (size_t)pair * n_hyp + h, d = ((size_t)pair * n_hyp + pos) * 12;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) chyp[d + k] = hyp_A[o * 9 + k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) chyp[d + 9 + k] = hyp_t[o * 3 + k];
+            cidx[(size_t)pair * n_hyp + pos] = h;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += wsum[w]; base_sh += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_valid[pair] = base_sh;
+}
+
+// 1.0f / 0.0f for a < b in ONE instruction (FSET.BF): inlier counts are accumulated as packed float32 (exact: a block
+// counts at most 16384 correspondences), which replaces compare + predicated integer add per hypothesis by 1.5 instructions
+__device__ __forceinline__ float set_lt(float a, float b) { float r; asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
 // Threads own hypotheses (coefficients in registers), points are broadcast from shared
 // memory.  Two hypotheses share every arithmetic instruction: sm_100's packed float32 pipe
 // (FFMA2 / FADD2 / FMUL2 on register pairs, each half an ordinary IEEE operation, so SPEC 4's
 // fma chain is reproduced bit for bit) evaluates the residual of a point under a PAIR of
 // hypotheses in 15 instructions; the point is stored duplicated (v, v) so that one LDS.128
-// delivers two broadcast operands.  Per (point, hypothesis): 7.5 FP + compare + add + 0.75 LDS.
-__global__ void __launch_bounds__(RS_THREADS, 2)
-ransac_score_kernel(RansacArgs a) {
+// delivers two broadcast operands.  Only correspondences that passed the joint mask are staged (warp-aggregated
+// compaction into the sub-tile), only valid hypotheses are scored (ransac_compact_kernel), blockIdx.z selects a slice of
+// RS_HYP_PER_BLOCK of them and warps beyond the last valid hypothesis leave at once.
+__global__ void __launch_bounds__(RS_THREADS)
+ransac_score_kernel(RansacArgs a, const float* __restrict__ chyp, const int32_t* __restrict__ cidx, const int32_t* __restrict__ n_valid) {
     __shared__ FrameConst fc;
     __shared__ float4 pts[RS_SUB][3];       // (x0,x0,x1,x1) (x2,x2,-y0,-y0) (-y1,-y1,-y2,-y2)
+    __shared__ int n_sh;
     const int pair = blockIdx.y;
+    const int nv = n_valid[pair];
+    const int hyp0 = blockIdx.z * RS_HYP_PER_BLOCK;
+    if (hyp0 >= nv) return;                 // block-uniform
     const da3s_pair pr = a.pairs[pair];
     const int frame = blockIdx.x / a.tiles_per_frame;
     const int tile = blockIdx.x - frame * a.tiles_per_frame;
-    if (threadIdx.x == 0) frame_const_basic(fc, pr, frame, a.thr, a.dscale, pair);
+    if (threadIdx.x == 0) { frame_const_basic(fc, pr, frame, a.thr, a.dscale, pair); n_sh = 0; }
     __syncthreads();
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // this warp's hypotheses: lane-interleaved inside the warp so that a warp covers 32 * RS_HPT consecutive valid ones
+    const int wbase = hyp0 + (int)warp * 32 * RS_HPT;
+    const bool warp_live = wbase < nv;      // warp-uniform; dead warps still help staging
 
     float2 A[RS_HPT / 2][12];               // .x: hypothesis 2q, .y: hypothesis 2q + 1
-    int cnt[RS_HPT];
-    bool hok[RS_HPT];
+    float2 cnt[RS_HPT / 2];
+    int hid[RS_HPT];
 #pragma unroll
     for (int m = 0; m < RS_HPT; ++m) {
-        int h = a.hyp_base + m * RS_THREADS + threadIdx.x;
-        cnt[m] = 0;
-        hok[m] = h < a.n_hyp && a.hyp_ok[(size_t)pair * a.n_hyp + h];
-        const float* hA = a.hyp_A + ((size_t)pair * a.n_hyp + (hok[m] ? h : 0)) * 9;
-        const float* ht = a.hyp_t + ((size_t)pair * a.n_hyp + (hok[m] ? h : 0)) * 3;
+        const int j = wbase + m * 32 + (int)lane;
+        hid[m] = j < nv ? j : -1;
+        const float* hc = chyp + ((size_t)pair * a.n_hyp + (j < nv ? j : 0)) * 12;
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
-            const float c = k < 9 ? hA[k] : ht[k - 9];
+            const float c = warp_live ? hc[k] : 0.0f;
             if (m & 1) A[m >> 1][k].y = c; else A[m >> 1][k].x = c;
         }
     }
+#pragma unroll
+    for (int q = 0; q < RS_HPT / 2; ++q) cnt[q] = make_float2(0.0f, 0.0f);
 
     const size_t foff = (size_t)frame * (size_t)a.P;
     const long long p_begin = (long long)tile * PA_GROUPS_PER_BLOCK * 4;
     long long p_end = p_begin + (long long)PA_GROUPS_PER_BLOCK * 4;
     if (p_end > a.P) p_end = a.P;
-    const float inf = __int_as_float(0x7f800000);
+    const float2 thr2 = make_float2(a.thr2, a.thr2);
     for (long long sb = p_begin; sb < p_end; sb += RS_SUB) {
-        // stage RS_SUB correspondences (4 per thread)
-#pragma unroll
+        // stage the KEPT correspondences of this sub-tile (RS_SUB / RS_THREADS per thread), compacted
+#pragma unroll 2
         for (int j = 0; j < RS_SUB / RS_THREADS; ++j) {
-            int slot = j * RS_THREADS + threadIdx.x;
-            long long pix = sb + slot;
-            float xs[3] = {0, 0, 0}, ys[3] = {inf, inf, inf};
+            const long long pix = sb + j * RS_THREADS + threadIdx.x;
+            float xs[3] = {0, 0, 0}, ys[3] = {0, 0, 0};
+            bool keep = false;
             if (pix < p_end) {
                 int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
                 float x[3], y[3], dbs;
-                bool keep = corr_points(fc, a.valid_depth, a.depth_eps, u, v,
-                                        ldg_stream1(pr.depth_a + foff + pix), ldg_stream1(pr.conf_a + foff + pix),
-                                        ldg_stream1(pr.depth_b + foff + pix), ldg_stream1(pr.conf_b + foff + pix), x, y, dbs);
+                keep = corr_points(fc, a.valid_depth, a.depth_eps, u, v,
+                                   ldg_stream1(pr.depth_a + foff + pix), ldg_stream1(pr.conf_a + foff + pix),
+                                   ldg_stream1(pr.depth_b + foff + pix), ldg_stream1(pr.conf_b + foff + pix), x, y, dbs);
                 if (keep) ransac_points(fc, a.world, x, y, xs, ys);
             }
-            pts[slot][0] = make_float4(xs[0], xs[0], xs[1], xs[1]);
-            pts[slot][1] = make_float4(xs[2], xs[2], -ys[0], -ys[0]);      // d = p - y  ==  p + (-y), exactly
-            pts[slot][2] = make_float4(-ys[1], -ys[1], -ys[2], -ys[2]);
-        }
-        __syncthreads();
-        long long rem = p_end - sb;
-        const int n_here = rem < RS_SUB ? (int)rem : RS_SUB;
-#pragma unroll 8
-        for (int i = 0; i < n_here; ++i) {
-            const float4 p0 = pts[i][0], p1 = pts[i][1], p2 = pts[i][2];
-            const float2 X0 = make_float2(p0.x, p0.y), X1 = make_float2(p0.z, p0.w), X2 = make_float2(p1.x, p1.y);
-            const float2 N0 = make_float2(p1.z, p1.w), N1 = make_float2(p2.x, p2.y), N2 = make_float2(p2.z, p2.w);
-#pragma unroll
-            for (int q = 0; q < RS_HPT / 2; ++q) {
-                // residual2_f32 (SPEC 4) for two hypotheses at once
-                const float2 d0 = __fadd2_rn(__ffma2_rn(A[q][0], X0, __ffma2_rn(A[q][1], X1, __ffma2_rn(A[q][2], X2, A[q][9]))), N0);
-                const float2 d1 = __fadd2_rn(__ffma2_rn(A[q][3], X0, __ffma2_rn(A[q][4], X1, __ffma2_rn(A[q][5], X2, A[q][10]))), N1);
-                const float2 d2 = __fadd2_rn(__ffma2_rn(A[q][6], X0, __ffma2_rn(A[q][7], X1, __ffma2_rn(A[q][8], X2, A[q][11]))), N2);
-                const float2 r2 = __ffma2_rn(d0, d0, __ffma2_rn(d1, d1, __fmul2_rn(d2, d2)));
-                cnt[2 * q] += (r2.x < a.thr2) ? 1 : 0;
-                cnt[2 * q + 1] += (r2.y < a.thr2) ? 1 : 0;
+            const unsigned int m = __ballot_sync(0xffffffffu, keep);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&n_sh, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                pts[slot][0] = make_float4(xs[0], xs[0], xs[1], xs[1]);
+                pts[slot][1] = make_float4(xs[2], xs[2], -ys[0], -ys[0]);      // d = p - y  ==  p + (-y), exactly
+                pts[slot][2] = make_float4(-ys[1], -ys[1], -ys[2], -ys[2]);
             }
         }
         __syncthreads();
+        const int n_here = n_sh;
+        if (warp_live) {
+#pragma unroll 8
+            for (int i = 0; i < n_here; ++i) {
+                const float4 p0 = pts[i][0], p1 = pts[i][1], p2 = pts[i][2];
+                const float2 X0 = make_float2(p0.x, p0.y), X1 = make_float2(p0.z, p0.w), X2 = make_float2(p1.x, p1.y);
+                const float2 N0 = make_float2(p1.z, p1.w), N1 = make_float2(p2.x, p2.y), N2 = make_float2(p2.z, p2.w);
+#pragma unroll
+                for (int q = 0; q < RS_HPT / 2; ++q) {
+                    // residual2_f32 (SPEC 4) for two hypotheses at once
+                    const float2 d0 = __fadd2_rn(__ffma2_rn(A[q][0], X0, __ffma2_rn(A[q][1], X1, __ffma2_rn(A[q][2], X2, A[q][9]))), N0);
+                    const float2 d1 = __fadd2_rn(__ffma2_rn(A[q][3], X0, __ffma2_rn(A[q][4], X1, __ffma2_rn(A[q][5], X2, A[q][10]))), N1);
+                    const float2 d2 = __fadd2_rn(__ffma2_rn(A[q][6], X0, __ffma2_rn(A[q][7], X1, __ffma2_rn(A[q][8], X2, A[q][11]))), N2);
+                    const float2 r2 = __ffma2_rn(d0, d0, __ffma2_rn(d1, d1, __fmul2_rn(d2, d2)));
+                    cnt[q] = __fadd2_rn(cnt[q], make_float2(set_lt(r2.x, thr2.x), set_lt(r2.y, thr2.y)));
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) n_sh = 0;
+        __syncthreads();
     }
+    if (!warp_live) return;
 #pragma unroll
     for (int m = 0; m < RS_HPT; ++m) {
-        int h = a.hyp_base + m * RS_THREADS + threadIdx.x;
-        if (hok[m] && cnt[m]) atomicAdd(&a.counts[(size_t)pair * a.n_hyp + h], cnt[m]);
+        const int c = (int)((m & 1) ? cnt[m >> 1].y : cnt[m >> 1].x);
+        if (hid[m] >= 0 && c) atomicAdd(&a.counts[(size_t)pair * a.n_hyp + cidx[(size_t)pair * a.n_hyp + hid[m]]], c);
     }
 }
 
@@ -1082,12 +1147,18 @@ extern "C" int da3s_ransac_score(da3s_ctx* ctx, const da3s_pair* pairs, int n_pa
     fill_ransac_args(r, pairs, n_pairs, overlap, H, W, P, tpf, world, valid_depth, depth_eps, conf_thr, depth_scale, n_hyp, ransac_thr);
     r.hyp_A = const_cast<float*>(hyp_A); r.hyp_t = const_cast<float*>(hyp_t); r.hyp_ok = const_cast<uint8_t*>(hyp_ok); r.counts = counts;
     DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_pairs * n_hyp, st));
-    dim3 grid(tpf * overlap, n_pairs);
-    for (int base = 0; base < n_hyp; base += RS_THREADS * RS_HPT) {
-        r.hyp_base = base;
-        ransac_score_kernel<<<grid, RS_THREADS, 0, st>>>(r);
-        DA3S_LAUNCH_CHECK(ctx);
-    }
+    size_t save_top = ctx->ws_top;
+    WS_ALLOC(ctx, float, chyp, (size_t)n_pairs * n_hyp * 12);
+    WS_ALLOC(ctx, int32_t, cidx, (size_t)n_pairs * n_hyp);
+    WS_ALLOC(ctx, int32_t, n_valid, n_pairs);
+    ransac_compact_kernel<<<n_pairs, 256, 0, st>>>(hyp_A, hyp_t, hyp_ok, n_hyp, chyp, cidx, n_valid);
+    DA3S_LAUNCH_CHECK(ctx);
+    const int zs = (n_hyp + RS_HYP_PER_BLOCK - 1) / RS_HYP_PER_BLOCK;
+    if (zs > 65535) return DA3S_EINVAL;
+    dim3 grid(tpf * overlap, n_pairs, zs);
+    ransac_score_kernel<<<grid, RS_THREADS, 0, st>>>(r, chyp, cidx, n_valid);
+    DA3S_LAUNCH_CHECK(ctx);
+    ctx->ws_top = save_top;     // consumed in stream order
     return DA3S_OK;
 }
 

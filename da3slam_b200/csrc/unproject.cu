@@ -380,3 +380,120 @@ extern "C" int da3s_apply_sim3(da3s_ctx* ctx, const void* xyz_in, int in_f64, lo
     DA3S_LAUNCH_CHECK(ctx);
     return DA3S_OK;
 }
+
+// ---------------------------------------------------------------------------------
+// Ordered filter + compaction of a resident cloud (the viewer's map push, viewer.py:333-355): keep point i iff
+// valid[i] (nullable) and conf[i] >= thr (when use_thr), write the kept points and colours densely IN INPUT ORDER.
+//   count  one block per 2048 points: kept count
+//   scan   single block over the block counts (exclusive offsets + total)
+//   write  every block recomputes its predicate, ranks its points with ballot / popc and stores
+// Algorithmic bytes: 5 B/point read twice (conf + valid) + 15 B per kept point read and written.
+// ---------------------------------------------------------------------------------
+#define FP_THREADS 256
+#define FP_PER_BLOCK 2048
+
+__device__ __forceinline__ bool fp_keep(const float* conf, const uint8_t* valid, long long i, bool use_thr, float thr) {
+    bool k = valid ? valid[i] != 0 : true;
+    if (use_thr) k = k && (conf[i] >= thr);
+    return k;
+}
+
+__global__ void __launch_bounds__(FP_THREADS)
+filter_count_kernel(const float* __restrict__ conf, const uint8_t* __restrict__ valid, long long n, int use_thr, float thr,
+                    unsigned int* __restrict__ block_counts) {
+    __shared__ unsigned int wsum[FP_THREADS / 32];
+    const long long base = (long long)blockIdx.x * FP_PER_BLOCK;
+    unsigned int c = 0;
+    for (int j = 0; j < FP_PER_BLOCK / FP_THREADS; ++j) {
+        const long long i = base + j * FP_THREADS + threadIdx.x;
+        c += (i < n && fp_keep(conf, valid, i, use_thr, thr)) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < FP_THREADS / 32; ++w) t += wsum[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+filter_scan_kernel(const unsigned int* __restrict__ counts, int n, unsigned long long* __restrict__ offsets, unsigned long long* __restrict__ total) {
+    __shared__ unsigned long long carry;
+    __shared__ unsigned long long wsum[32];
+    if (threadIdx.x == 0) carry = 0ull;
+    __syncthreads();
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < n ? counts[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long before = carry;
+        for (unsigned int w = 0; w < warp; ++w) before += wsum[w];
+        if (i < n) offsets[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(FP_THREADS)
+filter_write_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ rgb, const float* __restrict__ conf,
+                    const uint8_t* __restrict__ valid, long long n, int use_thr, float thr,
+                    const unsigned long long* __restrict__ offsets, long long max_out,
+                    float* __restrict__ xyz_out, uint8_t* __restrict__ rgb_out) {
+    __shared__ unsigned int wsum[FP_THREADS / 32];
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long base = (long long)blockIdx.x * FP_PER_BLOCK;
+    unsigned long long out = offsets[blockIdx.x];
+    for (int j = 0; j < FP_PER_BLOCK / FP_THREADS; ++j) {          // rounds in input order
+        const long long i = base + j * FP_THREADS + threadIdx.x;
+        const bool k = i < n && fp_keep(conf, valid, i, use_thr, thr);
+        const unsigned int m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        unsigned int before = 0, round_total = 0;
+        for (unsigned int w = 0; w < FP_THREADS / 32; ++w) { if (w < warp) before += wsum[w]; round_total += wsum[w]; }
+        if (k) {
+            const unsigned long long o = out + before + __popc(m & ((1u << lane) - 1u));
+            if ((long long)o < max_out) {
+                xyz_out[3 * o] = xyz[3 * i]; xyz_out[3 * o + 1] = xyz[3 * i + 1]; xyz_out[3 * o + 2] = xyz[3 * i + 2];
+                if (rgb_out) { rgb_out[3 * o] = rgb[3 * i]; rgb_out[3 * o + 1] = rgb[3 * i + 1]; rgb_out[3 * o + 2] = rgb[3 * i + 2]; }
+            }
+        }
+        out += round_total;
+        __syncthreads();
+    }
+}
+
+extern "C" int da3s_filter_points(da3s_ctx* ctx, const float* xyz, const uint8_t* rgb, const float* conf, const uint8_t* valid,
+                                  long long n, int use_thr, float thr, long long max_out, float* xyz_out, uint8_t* rgb_out,
+                                  unsigned long long* n_out, void* stream) {
+    if (!ctx || !xyz || !xyz_out || !n_out || n < 0 || max_out < 0 || (use_thr && !conf) || ((rgb == nullptr) != (rgb_out == nullptr)))
+        return DA3S_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(n_out, 0, 8, st)); return DA3S_OK; }
+    const long long nb = (n + FP_PER_BLOCK - 1) / FP_PER_BLOCK;
+    if (nb > 2147483647LL) return DA3S_EINVAL;
+    size_t save_top = ctx->ws_top;
+    WS_ALLOC(ctx, unsigned int, counts, (size_t)nb);
+    WS_ALLOC(ctx, unsigned long long, offsets, (size_t)nb);
+    filter_count_kernel<<<(unsigned int)nb, FP_THREADS, 0, st>>>(conf, valid, n, use_thr, thr, counts);
+    DA3S_LAUNCH_CHECK(ctx);
+    filter_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)nb, offsets, n_out);
+    DA3S_LAUNCH_CHECK(ctx);
+    filter_write_kernel<<<(unsigned int)nb, FP_THREADS, 0, st>>>(xyz, rgb, conf, valid, n, use_thr, thr, offsets, max_out, xyz_out, rgb_out);
+    DA3S_LAUNCH_CHECK(ctx);
+    ctx->ws_top = save_top;     // consumed in stream order
+    return DA3S_OK;
+}

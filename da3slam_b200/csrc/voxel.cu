@@ -1,132 +1,136 @@
 // voxel.cu — K6: voxel-grid downsample on a GPU hash grid (oracle/SPEC.md section 5).
 //
-// key    = floor(f64(p) / f64(voxel)) per axis, 21 bits per axis, bias 2^20
-// table  = rec[slots], one 64-byte record (= one DRAM atom) per slot:
-//          key | sum_qx | sum_qy | sum_qz | (count,sum_r) | (sum_g,sum_b) | pad | pad
-//          sum_q = sum of llrint(frac * 2^32), frac = p/voxel - floor(p/voxel)  (exact int64)
-//          The key lives INSIDE the record: probe, claim and the five additions of a point touch one
-//          DRAM atom (a separate key array cost a second random atom per point, and the insert stage
-//          is bound by exactly that random traffic: profiles/r1_*).
-// Integer accumulation makes the result independent of insertion order (bit-identical
-// run to run and across GPUs), which floating-point atomics would not be.
+// key    = floor(f64(p) / f64(voxel)) per axis, 21 bits per axis, bias 2^20 (63 bits; all ones = EMPTY)
+// table  = rec[slots], one 64-byte record (two 32-byte sectors) per slot:
+//            sector 0:  key | sum_qx | sum_qy | sum_qz          sum_q = sum of llrint(frac * 2^32), exact int64
+//            sector 1:  (count, sum_r) | (sum_g, sum_b) | pad | pad
+//          followed by ONE OCCUPANCY BIT per slot (slots / 8 bytes: 4 MB for 2^25 slots, L2 resident).
+// Integer accumulation makes the result independent of insertion order (bit-identical run to run and
+// across GPUs), which floating-point atomics would not be.
 //
-// Contention is cut before it reaches L2: points of one warp that fall in the same voxel
-// (neighbouring pixels of a frame usually do) are combined (match.any + shuffles) and issue
-// one commit per distinct voxel (vox_commit: the claimer of a slot writes the record, later
-// contributions add to it).  Compaction (count / scan / emit over the dense key array) resets the
-// keys it emits, so no separate clearing pass is needed between uses.
+// Protocol (vox_commit).  The occupancy bit arbitrates: `atomicOr` on the bitmap word is the ONLY read a claim
+// needs, so claiming a cold slot never fetches its record from DRAM.  The winner writes both sectors of the record
+// as whole 256-bit stores (sector 0 with key | BUSY) and then publishes the key with st.release.gpu; a thread
+// that finds the bit already set reads the key with ld.acquire.gpu (spinning while bit 63 is set: EMPTY or BUSY,
+// i.e. while the claimer has not published), and if it is its own key adds five 64-bit integers with RED — ordered
+// after the claimer's stores by the release / acquire pair.  Records are never cleared: the compaction resets
+// only the key word of the records it emits and the bitmap words it has walked.
 //
-// Algorithmic bytes: 12 (+3 rgb, +1 mask) per input point read; 12 (+3) + 4 (+8 key) per
-// occupied voxel written.  Hash-table traffic (random 64 B records in L2/HBM) is what
-// actually bounds this kernel and is not counted as algorithmic.
+// Contention is cut before it reaches L2: points of one warp that fall in the same voxel (neighbouring pixels
+// of a frame usually do) are combined (match.any + warp reductions) and issue one commit per distinct voxel.
+//
+// Algorithmic bytes: 12 (+3 rgb, +1 mask) per input point read (fused export: 8 per pixel + 3 per kept point);
+// 12 (+3) + 4 (+8 key) per occupied voxel written.  Table traffic is not algorithmic; per voxel it is one 64-byte
+// record written by the claim and read by the compaction.
 #include "common.cuh"
 #include "unproject_frame.cuh"
 
 #define VOX_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define VOX_BUSY 0x8000000000000000ull      // keys use 63 bits; EMPTY has the bit set too: "bit 63 set" == not (yet) a published key
+#ifndef VOX_EXP_NOFENCE
+#define VOX_EXP_NOFENCE 0                   // measurement only (NOT correct): publish without release semantics
+#endif
+#ifndef VOX_EXP_NOCOMMIT
+#define VOX_EXP_NOCOMMIT 0                  // measurement only: 1 = no table access at all, 2 = bitmap atomics + key reads only
+#endif
+#ifndef VOX_MERGE_PULL
+#define VOX_MERGE_PULL 1                    // 1: leaders pull their peers' 32-bit point values (4 shuffles per round); 0: 64-bit partial sums (10)
+#endif
 #define VOX_BIAS (1 << 20)
 #define VOX_REC 8                           // u64 words per record
 #define VOX_MAX_PROBE 4096
 #ifndef VOX_REDUX_GROUPS
 #define VOX_REDUX_GROUPS 4                  // batches with at most this many distinct voxels merge by masked warp reductions
 #endif
-// Table addressing.  VOX_INTERLEAVE = 0 (default): one dense key array behind all records; 1: every group of 64 slots
-// keeps its 64 keys (512 B) directly in front of its 64 records (4 KB) — measured equal within noise
-// (export 1.46 vs 1.44 ms), so the simpler layout stays.
-#ifndef VOX_INTERLEAVE
-#define VOX_INTERLEAVE 0
+#ifndef VOX_DIV_FAST
+#define VOX_DIV_FAST 1                      // 1: correctly rounded p / voxel by two Markstein corrections (5 DP ops); 0: __ddiv_rn
 #endif
-#if VOX_INTERLEAVE
-#define VOX_KEY_PTR(acc, slots, s) ((acc) + ((size_t)(s) >> 6) * (64 * (VOX_REC + 1)) + ((size_t)(s) & 63))
-#define VOX_REC_PTR(acc, slots, s) ((acc) + ((size_t)(s) >> 6) * (64 * (VOX_REC + 1)) + 64 + ((size_t)(s) & 63) * VOX_REC)
-#else
-#define VOX_KEY_PTR(acc, slots, s) ((acc) + (size_t)(slots) * VOX_REC + (size_t)(s))
-#define VOX_REC_PTR(acc, slots, s) ((acc) + (size_t)(s) * VOX_REC)
+#ifndef VOX_HASH32
+#define VOX_HASH32 1                        // 1: 32-bit multiplicative hash of the coarse cell; 0: 64-bit murmur finaliser
 #endif
+#define VOX_REC_PTR(acc, s) ((acc) + (size_t)(s) * VOX_REC)
+#define VOX_BITMAP(acc, slots) (reinterpret_cast<unsigned int*>(const_cast<unsigned long long*>(acc) + (size_t)(slots) * VOX_REC))
 
 // Locality-preserving slot: the 4 x 4 x 4 block of voxels a key belongs to is hashed to a REGION of 64 consecutive
-// slots, the position inside the region is the voxel's position inside its block; on a collision the probe moves
-// to the next region (same position).  Neighbouring voxels — what a warp's batch of neighbouring pixels hits — then
-// share key sectors and DRAM rows instead of being scattered over the whole table.
-#ifndef VOX_LOCAL
-#define VOX_LOCAL 1
-#endif
-#ifndef VOX_LOCAL_BITS
+// slots (4 KB of records, two bitmap words), the position inside the region is the voxel's position inside its block;
+// on a collision the probe moves to the next region (same position).  Neighbouring voxels — what a warp's batch of
+// neighbouring pixels hits — then share DRAM rows and bitmap sectors instead of being scattered over the whole table.
 #define VOX_LOCAL_BITS 2                    // 4 x 4 x 4 voxels per region
-#endif
-__device__ __forceinline__ unsigned long long vox_hash(unsigned long long k);
-__device__ __forceinline__ unsigned long long vox_slot0(unsigned long long key, long long slots) {
-#if VOX_LOCAL
-    const unsigned long long m = (1ull << VOX_LOCAL_BITS) - 1ull;
-    const unsigned long long coarse = key & ~((m << 42) | (m << 21) | m);
-    const unsigned long long local = (((key >> 42) & m) << (2 * VOX_LOCAL_BITS)) | (((key >> 21) & m) << VOX_LOCAL_BITS) | (key & m);
-    return ((vox_hash(coarse) << (3 * VOX_LOCAL_BITS)) | local) & (unsigned long long)(slots - 1);
-#else
-    return vox_hash(key) & (unsigned long long)(slots - 1);
-#endif
-}
-#if VOX_LOCAL
 #define VOX_STEP (1ull << (3 * VOX_LOCAL_BITS))
-#else
-#define VOX_STEP 1ull
-#endif
 
 __device__ __forceinline__ unsigned long long vox_hash(unsigned long long k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
     return k;
 }
+__device__ __forceinline__ unsigned long long vox_slot0(unsigned long long key, long long slots) {
+    const unsigned long long m = (1ull << VOX_LOCAL_BITS) - 1ull;
+    const unsigned long long local = (((key >> 42) & m) << (2 * VOX_LOCAL_BITS)) | (((key >> 21) & m) << VOX_LOCAL_BITS) | (key & m);
+#if VOX_HASH32
+    // 19-bit coarse cell coordinates -> one 32-bit word (three multiplies, one finishing mix)
+    const unsigned int cx = (unsigned int)(key >> (42 + VOX_LOCAL_BITS)), cy = (unsigned int)(key >> (21 + VOX_LOCAL_BITS)) & 0x7FFFFu,
+                       cz = (unsigned int)(key >> VOX_LOCAL_BITS) & 0x7FFFFu;
+    unsigned int h = (cx * 0x9E3779B1u) ^ (cy * 0x85EBCA77u) ^ (cz * 0xC2B2AE3Du);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+    return (((unsigned long long)h << (3 * VOX_LOCAL_BITS)) | local) & (unsigned long long)(slots - 1);
+#else
+    const unsigned long long coarse = key & ~((m << 42) | (m << 21) | m);
+    return ((vox_hash(coarse) << (3 * VOX_LOCAL_BITS)) | local) & (unsigned long long)(slots - 1);
+#endif
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 __global__ void voxel_clear_kernel(unsigned long long* acc, long long slots) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one slot per thread
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one slot per thread: key word + its share of the bitmap
+    unsigned int* bm = VOX_BITMAP(acc, slots);
     for (; i < slots; i += (long long)gridDim.x * blockDim.x) {
-        *VOX_KEY_PTR(acc, slots, i) = VOX_EMPTY;
-        unsigned long long* rec = VOX_REC_PTR(acc, slots, i);
-#pragma unroll
-        for (int k = 0; k < VOX_REC; k += 2) *reinterpret_cast<ulonglong2*>(rec + k) = make_ulonglong2(0ull, 0ull);
+        *VOX_REC_PTR(acc, i) = VOX_EMPTY;
+        if ((i & 31) == 0) bm[i >> 5] = 0u;
     }
 }
 
-// One launch inserts any number of clouds (a job table) — e.g. every submap of a sequence.  Each
-// warp streams 128 mask bytes at a time (one 4-byte load per lane), queues the indices of the
-// points that pass in shared memory, and runs the expensive part — coordinates, float64
-// quantisation, hash probe, atomics — only on full batches of 32 queued points: with a 35 %
-// confidence keep rate that is ~3x fewer trips through the dependent load chain
-// (mask -> xyz -> key -> record) that bounds this kernel.
-#define VI_THREADS 256
-#ifndef VI_MIN_BLOCKS
-#define VI_MIN_BLOCKS 6
-#endif
-#define VI_QUEUE 256                        // per-warp ring of point indices (>= 31 left over + 128 new)
-
-// Add one (already merged) contribution to the voxel `key`.  The thread that claims an empty slot WRITES the
-// record (all 64 bytes, so the line is never fetched from DRAM and never needs clearing between uses) while the key
-// carries VOX_BUSY, fences, then publishes the key; every later contribution is five 64-bit integer additions.
-// A thread that meets its own key with VOX_BUSY set waits for the publication (a few hundred cycles; the claimer is
-// in another warp — lanes of one warp never hold the same key here — and always makes progress).
-#define VOX_BUSY 0x8000000000000000ull      // keys use 63 bits
+// Add one (already merged) contribution to the voxel `key` (protocol: file header).
 __device__ __forceinline__ bool vox_commit(unsigned long long* __restrict__ acc, long long slots, unsigned long long key,
                                            unsigned long long sx, unsigned long long sy, unsigned long long sz,
                                            unsigned long long cr, unsigned long long gb) {
+    unsigned int* __restrict__ bm = VOX_BITMAP(acc, slots);
     unsigned long long slot = vox_slot0(key, slots);
     for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
-        unsigned long long* rec = VOX_REC_PTR(acc, slots, slot);
-        unsigned long long* kp = VOX_KEY_PTR(acc, slots, slot);
-        unsigned long long cur = *((volatile unsigned long long*)kp);
-        if (cur == VOX_EMPTY) {
-            cur = atomicCAS(kp, VOX_EMPTY, key | VOX_BUSY);
-            if (cur == VOX_EMPTY) {
-                // two 256-bit stores = two whole 32-byte sectors (sm_100): nothing to merge with, nothing fetched
-                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec), "l"(0ull), "l"(sx), "l"(sy), "l"(sz) : "memory");
-                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + 4), "l"(cr), "l"(gb), "l"(0ull), "l"(0ull) : "memory");
-                // release store: the record is visible device-wide before the key is (no L1 invalidation, unlike __threadfence)
-                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(kp), "l"(key) : "memory");
-                return true;
-            }
+        unsigned long long* rec = VOX_REC_PTR(acc, slot);
+        const unsigned int bit = 1u << (slot & 31);
+        const unsigned int old = atomicOr(bm + (slot >> 5), bit);
+        if (!(old & bit)) {
+#if VOX_EXP_NOCOMMIT >= 2
+            return true;
+#endif
+            // ours: both sectors as whole 256-bit stores (a full-sector write allocates in L2 without fetching the line
+            // from DRAM; a partial one does not) — sector 0 carries the key with VOX_BUSY set — then the key alone with
+            // release semantics: everything above is visible device-wide before the key loses its BUSY bit
+            asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec + 4), "l"(cr), "l"(gb), "l"(0ull), "l"(0ull) : "memory");
+            asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec), "l"(key | VOX_BUSY), "l"(sx), "l"(sy), "l"(sz) : "memory");
+#if VOX_EXP_NOFENCE
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(rec), "l"(key) : "memory");
+#else
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(rec), "l"(key) : "memory");
+#endif
+            return true;
         }
-        if ((cur & ~VOX_BUSY) == key) {
-            while (cur & VOX_BUSY) cur = *((volatile unsigned long long*)kp);
-            atomicAdd(rec + 1, sx); atomicAdd(rec + 2, sy); atomicAdd(rec + 3, sz);
-            atomicAdd(rec + 4, cr);
-            if (gb) atomicAdd(rec + 5, gb);
+        unsigned long long cur = ld_acquire_u64(rec);
+        while (cur & VOX_BUSY) { __nanosleep(32); cur = ld_acquire_u64(rec); }       // EMPTY or key | BUSY: claimed, not yet published
+        if (cur == key) {
+#if VOX_EXP_NOCOMMIT >= 2
+            return true;
+#endif
+            red_add_u64(rec + 1, sx); red_add_u64(rec + 2, sy); red_add_u64(rec + 3, sz);
+            red_add_u64(rec + 4, cr);
+            if (gb) red_add_u64(rec + 5, gb);
             return true;
         }
         slot = (slot + VOX_STEP) & (unsigned long long)(slots - 1);
@@ -134,24 +138,52 @@ __device__ __forceinline__ bool vox_commit(unsigned long long* __restrict__ acc,
     return false;
 }
 
+// SPEC 5 quantisation of one coordinate: q = f64(p) / f64(voxel) correctly rounded, k = floor(q), f = llrint((q - k) 2^32).
+// VOX_DIV_FAST: q by Markstein's iteration instead of the division routine: q0 = p * y with y = RN(1 / voxel), then twice
+// r = fma(-q, v, p) (the exact residual), q = fma(r, y, q).  After the first correction q is within one ulp of p / v, and
+// for such a q the second correction returns the correctly rounded quotient (Markstein 1990, Theorem: y = RN(1 / v), v's
+// significand not all ones — checked on the host, the division routine is used otherwise).  5 DP operations instead of ~40.
+struct VoxQuant { double v, y; bool fast; };
+__device__ __forceinline__ double vox_div(double p, const VoxQuant& qz) {
+#if VOX_DIV_FAST
+    if (qz.fast) {
+        double q = p * qz.y;
+        double r = fma(-q, qz.v, p);
+        q = fma(r, qz.y, q);
+        r = fma(-q, qz.v, p);
+        return fma(r, qz.y, q);
+    }
+#endif
+    return __ddiv_rn(p, qz.v);
+}
+static VoxQuant make_quant(float voxel) {
+    VoxQuant q;
+    q.v = (double)voxel;
+    q.y = 1.0 / q.v;                                         // IEEE division on the host: correctly rounded reciprocal
+    unsigned long long bits;
+    memcpy(&bits, &q.v, sizeof(bits));
+    q.fast = (bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull;
+    return q;
+}
+
 // one batch of up to 32 points held in registers: float64 quantisation, in-warp merge of the lanes that fall
 // in the same voxel, then probe / claim / five additions by the merged lanes.  Every lane of the warp calls it.
-__device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py, float pz, unsigned int rgb, bool has_rgb, double vd,
+__device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py, float pz, unsigned int rgb, bool has_rgb, const VoxQuant& qz,
                                                  unsigned long long* __restrict__ acc, long long slots,
                                                  unsigned long long* __restrict__ counters) {
     const unsigned int lane = threadIdx.x & 31;
     unsigned long long key = 0, sx = 0, sy = 0, sz = 0, cr = 1ull << 32, gb = 0ull;
     active = active && is_finite_f(px) && is_finite_f(py) && is_finite_f(pz);
     if (active) {
-        const double qx = __ddiv_rn((double)px, vd), qy = __ddiv_rn((double)py, vd), qz = __ddiv_rn((double)pz, vd);
-        const double kx = floor(qx), ky = floor(qy), kz = floor(qz);
+        const double qx = vox_div((double)px, qz), qy = vox_div((double)py, qz), qzz = vox_div((double)pz, qz);
+        const double kx = floor(qx), ky = floor(qy), kz = floor(qzz);
         active = (fabs(kx) < (double)VOX_BIAS) && (fabs(ky) < (double)VOX_BIAS) && (fabs(kz) < (double)VOX_BIAS);
         if (active) {
             key = ((unsigned long long)((long long)kx + VOX_BIAS) << 42) | ((unsigned long long)((long long)ky + VOX_BIAS) << 21) |
                   (unsigned long long)((long long)kz + VOX_BIAS);
             sx = (unsigned long long)__double2ll_rn((qx - kx) * 4294967296.0);
             sy = (unsigned long long)__double2ll_rn((qy - ky) * 4294967296.0);
-            sz = (unsigned long long)__double2ll_rn((qz - kz) * 4294967296.0);
+            sz = (unsigned long long)__double2ll_rn((qzz - kz) * 4294967296.0);
             cr |= (unsigned long long)(rgb & 0xFFu);
             gb = ((unsigned long long)((rgb >> 8) & 0xFFu) << 32) | (unsigned long long)((rgb >> 16) & 0xFFu);
         }
@@ -186,6 +218,20 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
         }
     } else if (peers != (1u << lane)) {
         unsigned int rest = peers & ~(1u << leader);                // identical for every lane of the group
+#if VOX_MERGE_PULL
+        // every lane still holds ONE point: its three fractions are < 2^32 and its colour is 24 bits, so the leader pulls
+        // four 32-bit words per peer and accumulates in 64 bits (the peers never accumulate)
+        const unsigned int fx = (unsigned int)sx, fy = (unsigned int)sy, fz = (unsigned int)sz;
+        while (rest) {
+            const int src = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const unsigned int ax = __shfl_sync(peers, fx, src), ay = __shfl_sync(peers, fy, src), az = __shfl_sync(peers, fz, src);
+            const unsigned int ac = __shfl_sync(peers, rgb, src);
+            sx += ax; sy += ay; sz += az;
+            cr += (1ull << 32) | (unsigned long long)(ac & 0xFFu);
+            gb += ((unsigned long long)((ac >> 8) & 0xFFu) << 32) | (unsigned long long)((ac >> 16) & 0xFFu);
+        }
+#else
         while (rest) {
             const int src = __ffs(rest) - 1;
             rest &= rest - 1;
@@ -194,13 +240,17 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
             const unsigned long long ag = __shfl_sync(peers, gb, src);
             if (lane == leader) { sx += ax; sy += ay; sz += az; cr += ac; gb += ag; }
         }
+#endif
         if (lane != leader) return;
     }
+#if VOX_EXP_NOCOMMIT == 1
+    return;
+#endif
     if (vox_commit(acc, slots, key, sx, sy, sz, cr, gb)) return;
     atomicAdd(&counters[1], cr >> 32);                              // table full: reported by finish
 }
 
-__device__ __forceinline__ void voxel_insert_point(bool active, long long i, const da3s_voxel_job& job, double vd,
+__device__ __forceinline__ void voxel_insert_point(bool active, long long i, const da3s_voxel_job& job, const VoxQuant& qz,
                                                    unsigned long long* __restrict__ acc,
                                                    long long slots, unsigned long long* __restrict__ counters) {
     float px = 0.0f, py = 0.0f, pz = 0.0f;
@@ -209,25 +259,30 @@ __device__ __forceinline__ void voxel_insert_point(bool active, long long i, con
         px = job.xyz[3 * i]; py = job.xyz[3 * i + 1]; pz = job.xyz[3 * i + 2];
         if (job.rgb) rgb = (unsigned int)job.rgb[3 * i] | ((unsigned int)job.rgb[3 * i + 1] << 8) | ((unsigned int)job.rgb[3 * i + 2] << 16);
     }
-    voxel_insert_xyz(active, px, py, pz, rgb, job.rgb != nullptr, vd, acc, slots, counters);
+    voxel_insert_xyz(active, px, py, pz, rgb, job.rgb != nullptr, qz, acc, slots, counters);
 }
 
-// Work unit of a warp = a TILE of 128 points: 128 consecutive points of an unstructured cloud, or — when
-// the cloud is an image sequence of row length `width` — 8 rows x 16 pixels.  The 2-D tile matters:
-// a voxel's footprint is a patch of pixels, and the in-warp combination (match.any) only sees the
-// batch of 32 queued points; with row-major tiles it merged ~2 points per voxel, with patches several
-// times more, and every merged point saves one probe and five L2 atomics (what bounds this stage:
-// ablation in profiles/r1_voxel_insert_ablation.md).
+// One launch inserts any number of clouds (a job table) — e.g. every submap of a sequence.  Work unit of a warp = a
+// TILE of 128 points: 128 consecutive points of an unstructured cloud, or — when the cloud is an image sequence of row
+// length `width` — 8 rows x 16 pixels.  The 2-D tile matters: a voxel's footprint is a patch of pixels, and the in-warp
+// combination (match.any) only sees the batch of 32 queued points; with row-major tiles it merged ~2 points per voxel,
+// with patches several times more, and every merged point saves one probe and five L2 atomics.  Each warp streams the
+// mask bytes of a tile (one 4-byte load per lane), queues the indices of the points that pass in shared memory, and runs
+// the expensive part — coordinates, float64 quantisation, hash probe, atomics — only on full batches of 32 queued points.
 // Blocks sweep the tiles of all jobs in order (block b takes block-chunks b, b + G, ...).
+#define VI_THREADS 256
+#ifndef VI_MIN_BLOCKS
+#define VI_MIN_BLOCKS 6
+#endif
+#define VI_QUEUE 256                        // per-warp ring of point indices (>= 31 left over + 128 new)
 #define VI_TILES_PER_WARP 2
 #define VI_TILES_PER_BLOCK (VI_TILES_PER_WARP * VI_THREADS / 32)
 
 __global__ void __launch_bounds__(VI_THREADS, VI_MIN_BLOCKS)
 voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job single, int n_jobs, long long chunks_per_job,
-                    int width, float voxel, unsigned long long* __restrict__ acc,
+                    int width, VoxQuant qz, unsigned long long* __restrict__ acc,
                     long long slots, unsigned long long* __restrict__ counters /* [0]=voxels (set by finish) [1]=dropped */) {
     __shared__ long long queue[VI_THREADS / 32][VI_QUEUE];
-    const double vd = (double)voxel;
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long* q = queue[warp];
     const long long total = chunks_per_job * n_jobs;
@@ -281,7 +336,7 @@ voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job sing
             __syncwarp();
             while (count >= 32) {
                 const long long i = q[(head + lane) & (VI_QUEUE - 1)];
-                voxel_insert_point(true, i, job, vd, acc, slots, counters);
+                voxel_insert_point(true, i, job, qz, acc, slots, counters);
                 __syncwarp();
                 head += 32; count -= 32;
             }
@@ -289,7 +344,7 @@ voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job sing
         if (count) {                                                // the queue never crosses a job boundary
             const bool active = lane < count;
             const long long i = active ? q[(head + lane) & (VI_QUEUE - 1)] : 0;
-            voxel_insert_point(active, i, job, vd, acc, slots, counters);
+            voxel_insert_point(active, i, job, qz, acc, slots, counters);
             __syncwarp();
         }
     }
@@ -301,7 +356,7 @@ voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job sing
 // (shared device functions), so the grid is bit-identical to the two-kernel route; what disappears
 // is 13 B/pixel of K1 stores and ~16 B/kept point of insert loads.
 // ---------------------------------------------------------------------------------
-#define EX_CONST 20                         // floats per frame: cu cv 1/fu 1/fv | Mf[9] | mf[3] | thr | pad
+#define EX_CONST 20                         // floats per frame: cu cv 1/fu 1/fv | Mf[9] | mf[3] | thr | use_conf | pad
 
 __global__ void export_frame_const_kernel(const da3s_export_job* __restrict__ jobs, int n_frames, int world, float conf_thr,
                                           float* __restrict__ fcs) {
@@ -314,14 +369,20 @@ __global__ void export_frame_const_kernel(const da3s_export_job* __restrict__ jo
     o[0] = fr.cuf; o[1] = fr.cvf; o[2] = fr.ifu; o[3] = fr.ifv;
     for (int k = 0; k < 9; ++k) o[4 + k] = fr.Mf[k];
     for (int k = 0; k < 3; ++k) o[13 + k] = fr.mf[k];
-    o[16] = j.conf_thr ? *j.conf_thr : conf_thr;
-    o[17] = o[18] = o[19] = 0.0f;
+    const float thr = j.conf_thr ? *j.conf_thr : conf_thr;
+    // a NaN threshold = a selection over no usable confidence (da3s_select): the reference keeps every point then
+    // (viewer.py:333-338), so the confidence tests are switched off for this frame
+    const bool use_conf = j.conf != nullptr && !(thr != thr);
+    o[16] = use_conf ? thr : 0.0f;
+    o[17] = use_conf ? 1.0f : 0.0f;
+    o[18] = o[19] = 0.0f;
 }
 
 struct ExportArgs {
     const da3s_export_job* jobs; const float* fcs;
     int n_frames, H, W, flags;
-    float conf_floor, depth_eps, voxel;
+    float conf_floor, depth_eps;
+    VoxQuant qz;
     long long chunks_per_frame;
     unsigned long long* acc; long long slots; unsigned long long* counters;
 };
@@ -330,7 +391,7 @@ __global__ void __launch_bounds__(VI_THREADS, VI_MIN_BLOCKS)
 export_voxel_kernel(ExportArgs a) {
     __shared__ unsigned long long queue[VI_THREADS / 32][VI_QUEUE];     // (depth bits << 32) | (v << 16) | u
     __shared__ float fc_sh[VI_THREADS / 32][EX_CONST];
-    const double vd = (double)a.voxel;
+    const VoxQuant qz = a.qz;
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long* q = queue[warp];
     float* fc = fc_sh[warp];
@@ -339,7 +400,6 @@ export_voxel_kernel(ExportArgs a) {
     const long long total = a.chunks_per_frame * a.n_frames;
     const bool f_gt = a.flags & DA3S_MASK_CONF_GT, f_ge = a.flags & DA3S_MASK_CONF_GE;
     const bool f_floor = a.flags & DA3S_MASK_CONF_FLOOR, f_depth = a.flags & DA3S_MASK_DEPTH;
-    const bool xform = true;
     for (long long c = blockIdx.x; c < total; c += gridDim.x) {
         const int f = (int)(c / a.chunks_per_frame);
         const da3s_export_job job = a.jobs[f];
@@ -347,6 +407,7 @@ export_voxel_kernel(ExportArgs a) {
         if (lane < EX_CONST) fc[lane] = a.fcs[(size_t)f * EX_CONST + lane];
         __syncwarp();
         const float thr = fc[16];
+        const bool use_conf = fc[17] != 0.0f;
         const long long t_begin = (c - (long long)f * a.chunks_per_frame) * VI_TILES_PER_BLOCK + (long long)warp * VI_TILES_PER_WARP;
         unsigned int head = 0, count = 0;                           // warp-uniform ring state
         auto batch = [&](bool active, unsigned long long e) {
@@ -360,13 +421,10 @@ export_voxel_kernel(ExportArgs a) {
             // K1 fast path (unproject_pixel<DA3S_UNPROJ_FAST> with the composed float32 transform)
             float x, y;
             cam_fast((float)u, (float)v, d, fc[0], fc[1], fc[2], fc[3], x, y);
-            float X = x, Y = y, Z = d;
-            if (xform) {
-                X = fmaf(fc[4], x, fmaf(fc[5], y, fmaf(fc[6], d, fc[13])));
-                Y = fmaf(fc[7], x, fmaf(fc[8], y, fmaf(fc[9], d, fc[14])));
-                Z = fmaf(fc[10], x, fmaf(fc[11], y, fmaf(fc[12], d, fc[15])));
-            }
-            voxel_insert_xyz(active, X, Y, Z, rgb, job.rgb != nullptr, vd, a.acc, a.slots, a.counters);
+            const float X = fmaf(fc[4], x, fmaf(fc[5], y, fmaf(fc[6], d, fc[13])));
+            const float Y = fmaf(fc[7], x, fmaf(fc[8], y, fmaf(fc[9], d, fc[14])));
+            const float Z = fmaf(fc[10], x, fmaf(fc[11], y, fmaf(fc[12], d, fc[15])));
+            voxel_insert_xyz(active, X, Y, Z, rgb, job.rgb != nullptr, qz, a.acc, a.slots, a.counters);
         };
 #pragma unroll 1
         for (int tt = 0; tt < VI_TILES_PER_WARP; ++tt) {
@@ -402,7 +460,7 @@ export_voxel_kernel(ExportArgs a) {
             for (int b = 0; b < 4; ++b) {
                 const float cc = c4[b], dd = d4[b];
                 bool k = b < lim;
-                if (job.conf) k = k & (!f_gt || cc > thr) & (!f_ge || cc >= thr) & (!f_floor || cc > a.conf_floor);
+                if (use_conf) k = k & (!f_gt || cc > thr) & (!f_ge || cc >= thr) & (!f_floor || cc > a.conf_floor);
                 k = k & (!f_depth || ((dd > a.depth_eps) & is_finite_f(dd)));
                 flags |= k ? (1u << b) : 0u;
             }
@@ -452,10 +510,10 @@ extern "C" int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* j
     DA3S_LAUNCH_CHECK(ctx);
     ExportArgs a;
     a.jobs = jobs_dev; a.fcs = fcs; a.n_frames = n_frames; a.H = H; a.W = W; a.flags = flags;
-    a.conf_floor = conf_floor; a.depth_eps = depth_eps; a.voxel = voxel;
+    a.conf_floor = conf_floor; a.depth_eps = depth_eps; a.qz = make_quant(voxel);
     const long long tiles = (long long)((H + 7) / 8) * ((W + 15) / 16);
     a.chunks_per_frame = (tiles + VI_TILES_PER_BLOCK - 1) / VI_TILES_PER_BLOCK;
-    a.acc = ctx->vox_acc; a.slots = ctx->vox_slots; a.counters = ctx->vox_dropped;
+    a.acc = ctx->vox_acc; a.slots = ctx->vox_slots; a.counters = ctx->vox_counters;
     int per_sm = 0;
     DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, export_voxel_kernel, VI_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
@@ -466,14 +524,12 @@ extern "C" int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* j
     return DA3S_OK;
 }
 
-// Compaction without atomics or barriers, two streaming passes over the DENSE key array:
-//   count  every WARP counts the occupied slots of its fixed range of 512 slots
+// Compaction without atomics or barriers, driven by the occupancy bitmap (never by the records):
+//   count  every WARP counts the set bits of its fixed range of 512 slots (16 bitmap words)
 //   scan   one block turns the per-warp counts into output offsets (and the total)
-//   emit   every warp walks the occupied slots of its range densely (occupancy bitmap of the count
-//          pass), reads key + record, emits, and resets the KEY: records are rewritten by the next
-//          claimer, so the table is ready for the next begin() without a clearing pass.
-//          No __syncthreads: the previous block-synchronous version was bound by exposed
-//          DRAM latency (profiles/r1_*: long_scoreboard 70, issue 8 %).
+//   emit   every warp walks the occupied slots of its range densely, reads key + record, emits, resets the
+//          KEY and finally its 16 bitmap words: records are rewritten by the next claimer, so the table is
+//          ready for the next begin() without a clearing pass.
 // Output order = slot order (which of two colliding keys gets the earlier slot depends on the insertion race;
 // the canonical order is ascending key — ops.VoxelGrid.read(sort=True)).
 #define VC_THREADS 256
@@ -482,23 +538,18 @@ extern "C" int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* j
 #define VC_PER_BLOCK (VC_PER_WARP * VC_THREADS / 32)
 
 __global__ void __launch_bounds__(VC_THREADS)
-voxel_count_kernel(const unsigned long long* __restrict__ acc, long long slots, unsigned int* __restrict__ warp_counts,
-                   unsigned int* __restrict__ occ_bits /* [n_warps][VC_ROUNDS] */) {
-    const unsigned int lane = threadIdx.x & 31;
-    const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
-    const long long base = wid * VC_PER_WARP;
-    if (base >= slots) return;
-    unsigned int c = 0, mine = 0;
+voxel_count_kernel(const unsigned int* __restrict__ bitmap, long long n_warps, unsigned int* __restrict__ warp_counts) {
+    // one THREAD per 512-slot group: four 128-bit loads of its 16 bitmap words
+    const long long wid = (long long)blockIdx.x * VC_THREADS + threadIdx.x;
+    if (wid >= n_warps) return;
+    const uint4* p = reinterpret_cast<const uint4*>(bitmap + wid * VC_ROUNDS);
+    unsigned int c = 0;
 #pragma unroll
-    for (int j = 0; j < VC_ROUNDS; ++j) {                       // 16 independent loads per lane, one key per record
-        const long long s = base + (long long)j * 32 + lane;
-        const bool occ = s < slots && __ldcs(VOX_KEY_PTR(acc, slots, s)) != VOX_EMPTY;
-        const unsigned int word = __ballot_sync(0xffffffffu, occ);       // occupancy of round j: the emit pass reads
-        if ((int)lane == j) mine = word;                                 // 64 bytes per warp instead of 4 KB of keys
-        c += __popc(word);
+    for (int j = 0; j < VC_ROUNDS / 4; ++j) {
+        const uint4 w = p[j];
+        c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
     }
-    if (lane < VC_ROUNDS) occ_bits[wid * VC_ROUNDS + lane] = mine;
-    if (lane == 0) warp_counts[wid] = c;
+    warp_counts[wid] = c;
 }
 
 #define VS_ITEMS 8                          // counts per thread and round: 8192 per round of the single scan block
@@ -536,9 +587,25 @@ voxel_scan_kernel(const unsigned int* __restrict__ counts, int n, unsigned long 
     if (threadIdx.x == 0) counters[0] = carry;
 }
 
+// rank-th occupied slot of a warp's 512-slot range from its 16 occupancy words (shared memory: words + exclusive counts)
+__device__ __forceinline__ int vox_nth_slot(const unsigned int* s_word, const unsigned int* s_excl, unsigned int rank) {
+    int w = 0;                                                   // word holding the rank-th occupied slot: last excl <= rank
+#pragma unroll
+    for (int step = VC_ROUNDS / 2; step >= 1; step >>= 1)
+        if (s_excl[w + step] <= rank) w += step;
+    const unsigned int word = s_word[w];
+    unsigned int n = rank - s_excl[w], pos = 0;
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) {                       // position of the n-th set bit of `word`
+        const unsigned int c = __popc((word >> pos) & ((1u << sh) - 1u));
+        if (n >= c) { n -= c; pos += sh; }
+    }
+    return w * 32 + (int)pos;
+}
+
 __global__ void __launch_bounds__(VC_THREADS)
 voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
-                  const unsigned long long* __restrict__ warp_offsets, const unsigned int* __restrict__ occ_bits,
+                  const unsigned long long* __restrict__ warp_offsets, const unsigned int* __restrict__ warp_counts,
                   float voxel, long long max_voxels,
                   float* __restrict__ xyz_out, uint8_t* __restrict__ rgb_out, int32_t* __restrict__ count_out,
                   long long* __restrict__ key_out) {
@@ -548,10 +615,12 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
     const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + warp;
     const long long base = wid * VC_PER_WARP;
     if (base >= slots) return;
+    if (warp_counts[wid] == 0u) return;                           // nothing in these 512 slots (warp-uniform): 4 bytes read
+    unsigned int* bm = VOX_BITMAP(acc, slots) + wid * VC_ROUNDS;
     // The warp's 512 slots as 16 occupancy words.  The occupied slots are handled DENSELY: lane l of dense round r
     // takes the (32 r + l)-th occupied slot, so the number of rounds — and of record loads in flight per warp —
-    // follows the voxels, not the table size (a sparser table costs the bitmap and the key scan of the count pass only).
-    const unsigned int my_word = lane < VC_ROUNDS ? occ_bits[wid * VC_ROUNDS + lane] : 0u;
+    // follows the voxels, not the table size.
+    const unsigned int my_word = lane < VC_ROUNDS ? bm[lane] : 0u;
     const unsigned int my_cnt = __popc(my_word);
     unsigned int incl = my_cnt;
 #pragma unroll
@@ -560,48 +629,36 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
         if ((int)lane >= o) incl += t;
     }
     const unsigned int total = __shfl_sync(0xffffffffu, incl, VC_ROUNDS - 1);
-    if (total == 0u) return;                                      // nothing in these 512 slots (warp-uniform)
-    if (lane < VC_ROUNDS) { s_word[warp][lane] = my_word; s_excl[warp][lane] = incl - my_cnt; }
+    if (lane < VC_ROUNDS) { s_word[warp][lane] = my_word; s_excl[warp][lane] = incl - my_cnt; bm[lane] = 0u; }
     __syncwarp();
     const unsigned long long out0 = warp_offsets[wid];
     for (unsigned int r0 = 0; r0 < total; r0 += 128u) {          // 4 dense rounds at a time: their record loads overlap
-        ulonglong2 ra[4], rb[4];                                // (sum_y, sum_z), ((n, sum_r), (sum_g, sum_b))
-        unsigned long long rx[4], key[4];
-        long long sidx[4];
+        ulonglong2 r01[4], r23[4], r45[4];                        // (key, sum_x), (sum_y, sum_z), ((n, sum_r), (sum_g, sum_b))
+        unsigned long long* recs[4];
         bool occ[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const unsigned int rank = r0 + 32u * q + lane;
             occ[q] = rank < total;
             if (occ[q]) {
-                int w = 0;                                       // word holding the rank-th occupied slot: last excl <= rank
-#pragma unroll
-                for (int step = VC_ROUNDS / 2; step >= 1; step >>= 1)
-                    if (s_excl[warp][w + step] <= rank) w += step;
-                const unsigned int word = s_word[warp][w];
-                unsigned int n = rank - s_excl[warp][w], pos = 0;
-#pragma unroll
-                for (int sh = 16; sh >= 1; sh >>= 1) {           // position of the n-th set bit of `word`
-                    const unsigned int c = __popc((word >> pos) & ((1u << sh) - 1u));
-                    if (n >= c) { n -= c; pos += sh; }
-                }
-                sidx[q] = base + (long long)w * 32 + pos;
-                key[q] = *VOX_KEY_PTR(acc, slots, sidx[q]);
-                const unsigned long long* rec = VOX_REC_PTR(acc, slots, sidx[q]);
-                rx[q] = rec[1];
-                ra[q] = *reinterpret_cast<const ulonglong2*>(rec + 2);
-                rb[q] = *reinterpret_cast<const ulonglong2*>(rec + 4);
+                unsigned long long* rec = VOX_REC_PTR(acc, base + vox_nth_slot(s_word[warp], s_excl[warp], rank));
+                r01[q] = *reinterpret_cast<const ulonglong2*>(rec);
+                r23[q] = *reinterpret_cast<const ulonglong2*>(rec + 2);
+                r45[q] = *reinterpret_cast<const ulonglong2*>(rec + 4);
+                recs[q] = rec;
             }
         }
 #pragma unroll
+        for (int q = 0; q < 4; ++q)                                // after ALL loads of the four rounds have been issued
+            if (occ[q]) *recs[q] = VOX_EMPTY;                      // the record itself is rewritten by the next claimer (vox_commit)
+#pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (!occ[q]) continue;
-            (*VOX_KEY_PTR(acc, slots, sidx[q])) = VOX_EMPTY; // the record itself is rewritten by the next claimer (vox_commit)
             const unsigned long long o = out0 + r0 + 32u * q + lane;
             if ((long long)o >= max_voxels) continue;
-            const unsigned long long k64 = key[q], cr = rb[q].x, gb = rb[q].y, cnt = cr >> 32;
+            const unsigned long long k64 = r01[q].x, cr = r45[q].x, gb = r45[q].y, cnt = cr >> 32;
             const double inv = 1.0 / 4294967296.0;
-            const unsigned long long sq[3] = {rx[q], ra[q].x, ra[q].y};
+            const unsigned long long sq[3] = {r01[q].y, r23[q].x, r23[q].y};
             const double k[3] = {(double)((long long)((k64 >> 42) & 0x1FFFFF) - VOX_BIAS),
                                  (double)((long long)((k64 >> 21) & 0x1FFFFF) - VOX_BIAS),
                                  (double)((long long)(k64 & 0x1FFFFF) - VOX_BIAS)};
@@ -634,11 +691,23 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
 // owner folds its inbox into its (clean) table.  The sums are integers, so the merged grid is
 // bit-identical to inserting all points on one GPU.
 //   count  per warp and destination: occupied slots whose owner is d
-//   scan   one block per destination: exclusive offsets in slot order (deterministic inbox content)
-//   send   re-read keys, read records, reset keys, store 48-byte records at inbox[owner][rank*cap + offset]
+//   scan   one block per destination: exclusive offsets in slot order (deterministic inbox content); its last
+//          thread publishes this rank's record count for destination d in the owner's `counts`
+//   send   read records, reset keys and bitmap, store 48-byte records at inbox[owner][rank*cap + offset], then
+//          signal arrival: every block, after a device-wide fence over its stores, bumps a local ticket; the LAST
+//          block writes the step number into flags[rank] of every destination (system-scope release).  The owner's
+//          merge kernel spins on its `world` flags (system-scope acquire) before it reads the inbox: no host
+//          synchronisation and no process-group barrier in the data path.
+// Inboxes are double-buffered by step parity: a sender's stores of step k + 1 can never land in the buffer the
+// owner is still merging for step k (a rank cannot start step k + 2 before every rank has merged step k, because
+// its own merge of step k + 1 waits for every peer's send of step k + 1, which follows that peer's merge of step k).
 // ---------------------------------------------------------------------------------
 #define VOX_MAX_WORLD 16
-struct VoxPeers { unsigned long long* inbox[VOX_MAX_WORLD]; unsigned long long* counts[VOX_MAX_WORLD]; };
+struct VoxPeers {
+    unsigned long long* inbox[VOX_MAX_WORLD];       // this step's inbox half of every rank
+    unsigned long long* counts[VOX_MAX_WORLD];      // [world] record counts, this step's half
+    unsigned long long* flags[VOX_MAX_WORLD];       // [world] arrival flags (step numbers), this step's half
+};
 
 __device__ __forceinline__ int vox_owner(unsigned long long key, int world) {
     return (int)((vox_hash(key) >> 40) % (unsigned long long)world);      // high bits: independent of the slot index
@@ -651,15 +720,21 @@ voxel_count_dest_kernel(const unsigned long long* __restrict__ acc, long long sl
     const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
     const long long base = wid * VC_PER_WARP;
     if (base >= slots) return;
+    const unsigned int* bm = VOX_BITMAP(acc, slots) + wid * VC_ROUNDS;
+    const unsigned int my_word = lane < VC_ROUNDS ? bm[lane] : 0u;
     unsigned int mine = 0;                                       // lane d counts destination d
+    if (__ballot_sync(0xffffffffu, my_word != 0u)) {
 #pragma unroll 4
-    for (int j = 0; j < VC_ROUNDS; ++j) {
-        const long long s = base + (long long)j * 32 + lane;
-        const unsigned long long k = s < slots ? __ldcs(VOX_KEY_PTR(acc, slots, s)) : VOX_EMPTY;
-        const int owner = k != VOX_EMPTY ? vox_owner(k, world) : -1;
-        for (int d = 0; d < world; ++d) {
-            const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
-            if ((int)lane == d) mine += __popc(m);
+        for (int j = 0; j < VC_ROUNDS; ++j) {
+            const unsigned int word = __shfl_sync(0xffffffffu, my_word, j);
+            if (word == 0u) continue;                            // warp-uniform
+            const bool occ = (word >> lane) & 1u;
+            const unsigned long long k = occ ? __ldcs(VOX_REC_PTR(acc, base + (long long)j * 32 + lane)) : VOX_EMPTY;
+            const int owner = occ ? vox_owner(k, world) : -1;
+            for (int d = 0; d < world; ++d) {
+                const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
+                if ((int)lane == d) mine += __popc(m);
+            }
         }
     }
     if ((int)lane < world) warp_counts[wid * world + lane] = mine;
@@ -696,44 +771,72 @@ voxel_scan_dest_kernel(const unsigned int* __restrict__ counts, int n, int world
     if (threadIdx.x == 0) {
         unsigned long long total = carry;
         if ((long long)total > cap) { atomicAdd(&counters[1], total - (unsigned long long)cap); total = (unsigned long long)cap; }
-        peers.counts[d][rank] = total;                           // peer store: the owner learns how many records we sent
+        peers.counts[d][rank] = total;                           // peer store; made visible by the send kernel's flag (stream order + fence)
     }
 }
 
 __global__ void __launch_bounds__(VC_THREADS)
 voxel_send_kernel(unsigned long long* __restrict__ acc, long long slots, const unsigned long long* __restrict__ offsets,
-                  int world, int rank, long long cap, VoxPeers peers) {
+                  int world, int rank, long long cap, VoxPeers peers, unsigned int* __restrict__ ticket, unsigned long long step) {
     const unsigned int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
     const long long base = wid * VC_PER_WARP;
-    if (base >= slots) return;
-    unsigned long long out = (int)lane < world ? offsets[wid * world + lane] : 0ull;    // lane d: next index for destination d
-#pragma unroll 2
-    for (int j = 0; j < VC_ROUNDS; ++j) {
-        const long long s = base + (long long)j * 32 + lane;
-        const unsigned long long k = s < slots ? (*VOX_KEY_PTR(acc, slots, s)) : VOX_EMPTY;
-        const bool occ = k != VOX_EMPTY;
-        const int owner = occ ? vox_owner(k, world) : -1;
-        unsigned long long my_idx = 0;
-        for (int d = 0; d < world; ++d) {
-            const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
-            const unsigned long long start = __shfl_sync(0xffffffffu, out, d);
-            if (owner == d) my_idx = start + __popc(m & ((1u << lane) - 1u));
-            if ((int)lane == d) out += __popc(m);
-        }
-        if (occ) {
-            unsigned long long* rec = VOX_REC_PTR(acc, slots, s);
-            const unsigned long long sx = rec[1];
-            const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rec + 2);
-            const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(rec + 4);
-            (*VOX_KEY_PTR(acc, slots, s)) = VOX_EMPTY;
-            if ((long long)my_idx < cap) {
-                unsigned long long* dst = peers.inbox[owner] + ((size_t)rank * (size_t)cap + my_idx) * 6;   // NVLink stores
-                *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(k, sx);
-                *reinterpret_cast<ulonglong2*>(dst + 2) = a;
-                *reinterpret_cast<ulonglong2*>(dst + 4) = b;
+    if (base < slots) {
+        unsigned int* bm = VOX_BITMAP(acc, slots) + wid * VC_ROUNDS;
+        const unsigned int my_word = lane < VC_ROUNDS ? bm[lane] : 0u;
+        if (__ballot_sync(0xffffffffu, my_word != 0u)) {
+            unsigned long long out = (int)lane < world ? offsets[wid * world + lane] : 0ull;    // lane d: next index for destination d
+            for (int j = 0; j < VC_ROUNDS; ++j) {
+                const unsigned int word = __shfl_sync(0xffffffffu, my_word, j);
+                if (word == 0u) continue;                        // warp-uniform
+                const bool occ = (word >> lane) & 1u;
+                unsigned long long* rec = VOX_REC_PTR(acc, base + (long long)j * 32 + lane);
+                ulonglong2 r01 = make_ulonglong2(VOX_EMPTY, 0ull), r23 = make_ulonglong2(0ull, 0ull), r45 = make_ulonglong2(0ull, 0ull);
+                if (occ) {
+                    r01 = *reinterpret_cast<const ulonglong2*>(rec);
+                    r23 = *reinterpret_cast<const ulonglong2*>(rec + 2);
+                    r45 = *reinterpret_cast<const ulonglong2*>(rec + 4);
+                    *rec = VOX_EMPTY;
+                }
+                const int owner = occ ? vox_owner(r01.x, world) : -1;
+                unsigned long long my_idx = 0;
+                for (int d = 0; d < world; ++d) {
+                    const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
+                    const unsigned long long start = __shfl_sync(0xffffffffu, out, d);
+                    if (owner == d) my_idx = start + __popc(m & ((1u << lane) - 1u));
+                    if ((int)lane == d) out += __popc(m);
+                }
+                if (occ && (long long)my_idx < cap) {
+                    unsigned long long* dst = peers.inbox[owner] + ((size_t)rank * (size_t)cap + my_idx) * 6;   // NVLink stores
+                    *reinterpret_cast<ulonglong2*>(dst) = r01;
+                    *reinterpret_cast<ulonglong2*>(dst + 2) = r23;
+                    *reinterpret_cast<ulonglong2*>(dst + 4) = r45;
+                }
             }
+            if (lane < VC_ROUNDS) bm[lane] = 0u;
         }
+    }
+    // arrival: all of this block's peer stores are performed (system scope) before its ticket; the last block signals
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && (int)threadIdx.x < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flags[threadIdx.x] + rank), "l"(step) : "memory");
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+// owner side: wait until every rank's records of this step have arrived (device-side, no host involvement)
+__global__ void voxel_wait_kernel(const unsigned long long* __restrict__ flags, int world, unsigned long long step) {
+    if ((int)threadIdx.x < world) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v < step) __nanosleep(200);
+        } while (v < step);
     }
 }
 
@@ -754,15 +857,17 @@ voxel_merge_kernel(const unsigned long long* __restrict__ inbox, const unsigned 
 }
 
 extern "C" int da3s_voxel_send(da3s_ctx* ctx, int world, int rank, void* const* inbox_ptrs, void* const* count_ptrs,
-                               long long cap, void* stream) {
-    if (!ctx || world < 1 || world > VOX_MAX_WORLD || rank < 0 || rank >= world || !inbox_ptrs || !count_ptrs || cap < 1) return DA3S_EINVAL;
+                               void* const* flag_ptrs, unsigned long long step, long long cap, void* stream) {
+    if (!ctx || world < 1 || world > VOX_MAX_WORLD || rank < 0 || rank >= world || !inbox_ptrs || !count_ptrs || !flag_ptrs || cap < 1)
+        return DA3S_EINVAL;
     if (!ctx->vox_active) return DA3S_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     VoxPeers peers;
     for (int d = 0; d < VOX_MAX_WORLD; ++d) {
         peers.inbox[d] = d < world ? (unsigned long long*)inbox_ptrs[d] : nullptr;
         peers.counts[d] = d < world ? (unsigned long long*)count_ptrs[d] : nullptr;
-        if (d < world && (!peers.inbox[d] || !peers.counts[d])) return DA3S_EINVAL;
+        peers.flags[d] = d < world ? (unsigned long long*)flag_ptrs[d] : nullptr;
+        if (d < world && (!peers.inbox[d] || !peers.counts[d] || !peers.flags[d])) return DA3S_EINVAL;
     }
     const int n_warps = (int)((ctx->vox_slots + VC_PER_WARP - 1) / VC_PER_WARP);
     const int n_cblocks = (n_warps + VC_THREADS / 32 - 1) / (VC_THREADS / 32);
@@ -771,22 +876,29 @@ extern "C" int da3s_voxel_send(da3s_ctx* ctx, int world, int rank, void* const* 
     WS_ALLOC(ctx, unsigned long long, warp_offsets, (size_t)n_warps * world);
     voxel_count_dest_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, world, warp_counts);
     DA3S_LAUNCH_CHECK(ctx);
-    voxel_scan_dest_kernel<<<world, 1024, 0, st>>>(warp_counts, n_warps, world, rank, cap, warp_offsets, peers, ctx->vox_dropped);
+    voxel_scan_dest_kernel<<<world, 1024, 0, st>>>(warp_counts, n_warps, world, rank, cap, warp_offsets, peers, ctx->vox_counters);
     DA3S_LAUNCH_CHECK(ctx);
-    voxel_send_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_offsets, world, rank, cap, peers);
+    voxel_send_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_offsets, world, rank, cap, peers,
+                                                       (unsigned int*)(ctx->vox_counters + 2), step);
     DA3S_LAUNCH_CHECK(ctx);
     ctx->ws_top = save_top;
     ctx->vox_clean = false;         // clean again, but the table stays active: the merge inserts into it
     return DA3S_OK;
 }
 
-extern "C" int da3s_voxel_merge_inbox(da3s_ctx* ctx, const void* inbox, const void* counts, int world, long long cap, void* stream) {
+extern "C" int da3s_voxel_merge_inbox(da3s_ctx* ctx, const void* inbox, const void* counts, const void* flags,
+                                      unsigned long long step, int world, long long cap, void* stream) {
     if (!ctx || !inbox || !counts || world < 1 || world > VOX_MAX_WORLD || cap < 1) return DA3S_EINVAL;
     if (!ctx->vox_active) return DA3S_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (flags) {                                                  // null: the caller has synchronised by other means
+        voxel_wait_kernel<<<1, 32, 0, st>>>((const unsigned long long*)flags, world, step);
+        DA3S_LAUNCH_CHECK(ctx);
+    }
     long long want = (cap + 255) / 256, lim = (long long)ctx->sm_count * 8;
     dim3 grid((unsigned int)(want > lim ? lim : want), (unsigned int)world);
-    voxel_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)inbox, (const unsigned long long*)counts, world, cap,
-                                                               ctx->vox_acc, ctx->vox_slots, ctx->vox_dropped);
+    voxel_merge_kernel<<<grid, 256, 0, st>>>((const unsigned long long*)inbox, (const unsigned long long*)counts, world, cap,
+                                             ctx->vox_acc, ctx->vox_slots, ctx->vox_counters);
     DA3S_LAUNCH_CHECK(ctx);
     return DA3S_OK;
 }
@@ -794,10 +906,10 @@ extern "C" int da3s_voxel_merge_inbox(da3s_ctx* ctx, const void* inbox, const vo
 extern "C" int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots, void* stream) {
     if (!ctx || table_slots < 1024 || (table_slots & (table_slots - 1)) || table_slots > (1ll << 31)) return DA3S_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    // layout of the reserved tail: records [slots][8] u64 | counters [4] u64 (256 B) |
-    // warp counts [slots/512] u32 | warp offsets [slots/512] u64 | occupancy bits [slots/32] u32
-    const long long n_cblocks = (table_slots + VC_PER_WARP - 1) / VC_PER_WARP;
-    size_t bytes = (size_t)table_slots * (VOX_REC + 1) * 8 + 256 + (size_t)n_cblocks * (16 + 4 * VC_ROUNDS) + 512;
+    // layout of the reserved tail: records [slots][8] u64 | occupancy bitmap [slots/32] u32 | counters [32] u64 (256 B:
+    // voxels, dropped, send ticket) | group counts [slots/512] u32 | group offsets [slots/512] u64
+    const long long n_groups = (table_slots + VC_PER_WARP - 1) / VC_PER_WARP;
+    size_t bytes = (size_t)table_slots * VOX_REC * 8 + (size_t)table_slots / 8 + 256 + (size_t)n_groups * 12 + 512;
     const bool reuse = (ctx->vox_slots == table_slots) && ctx->vox_clean && ctx->vox_bytes > 0;
     if (!reuse) {
         if (bytes > ctx->ws_bytes) return DA3S_ENOMEM;
@@ -806,15 +918,15 @@ extern "C" int da3s_voxel_begin(da3s_ctx* ctx, long long table_slots, void* stre
         size_t start = (ctx->ws_bytes - bytes) & ~(size_t)255;
         ctx->vox_bytes = ctx->ws_bytes - start;               // stays reserved until a different size is requested
         ctx->vox_acc = (unsigned long long*)(ctx->ws + start);
-        ctx->vox_keys = ctx->vox_acc;                          // the key is word 0 of each record
-        ctx->vox_dropped = ctx->vox_acc + (size_t)table_slots * (VOX_REC + 1);       // counters[4]
-        ctx->vox_occ = (unsigned int*)(ctx->vox_dropped + 32);                 // block counts, then block offsets
+        ctx->vox_counters = (unsigned long long*)(ctx->ws + start + (size_t)table_slots * VOX_REC * 8 + (size_t)table_slots / 8);
+        ctx->vox_groups = (unsigned int*)(ctx->vox_counters + 32);             // group counts, then group offsets
         ctx->vox_slots = table_slots;
         long long want = (table_slots + 255) / 256, cap = (long long)ctx->sm_count * 32;
         voxel_clear_kernel<<<(int)(want > cap ? cap : want), 256, 0, st>>>(ctx->vox_acc, table_slots);
         DA3S_LAUNCH_CHECK(ctx);
+        DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->vox_counters, 0, 256, st));
     }
-    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->vox_dropped, 0, 32, st));
+    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->vox_counters, 0, 16, st));    // voxels, dropped (the send ticket resets itself)
     ctx->vox_clean = false;
     ctx->vox_active = true;
     return DA3S_OK;
@@ -836,7 +948,7 @@ static int voxel_insert_launch(da3s_ctx* ctx, const da3s_voxel_job* jobs_dev, in
     if (per_sm < 1) per_sm = 1;
     const long long total = chunks_per_job * n_jobs, cap = (long long)ctx->sm_count * per_sm;
     voxel_insert_kernel<<<(unsigned int)(total > cap ? cap : total), VI_THREADS, 0, (cudaStream_t)stream>>>(
-        jobs_dev, single, n_jobs, chunks_per_job, width, voxel, ctx->vox_acc, ctx->vox_slots, ctx->vox_dropped);
+        jobs_dev, single, n_jobs, chunks_per_job, width, make_quant(voxel), ctx->vox_acc, ctx->vox_slots, ctx->vox_counters);
     DA3S_LAUNCH_CHECK(ctx);
     return DA3S_OK;
 }
@@ -867,22 +979,22 @@ extern "C" int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxel
     if (!ctx || !xyz_out || !count_out || !n_voxels || max_voxels <= 0 || !(voxel > 0.0f)) return DA3S_EINVAL;
     if (!ctx->vox_active) return DA3S_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_warps = (int)((ctx->vox_slots + VC_PER_WARP - 1) / VC_PER_WARP);
-    const int n_cblocks = (n_warps + VC_THREADS / 32 - 1) / (VC_THREADS / 32);
-    unsigned int* warp_counts = ctx->vox_occ;
-    unsigned long long* warp_offsets = (unsigned long long*)(warp_counts + ((n_warps + 1) & ~1));
-    unsigned int* occ_bits = (unsigned int*)(warp_offsets + n_warps);
-    voxel_count_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_counts, occ_bits);
+    const long long n_warps = (ctx->vox_slots + VC_PER_WARP - 1) / VC_PER_WARP;
+    const int n_cblocks = (int)((n_warps + VC_THREADS / 32 - 1) / (VC_THREADS / 32));
+    unsigned int* warp_counts = ctx->vox_groups;
+    unsigned long long* warp_offsets = (unsigned long long*)(warp_counts + ((n_warps + 1) & ~1ll));
+    voxel_count_kernel<<<(int)((n_warps + VC_THREADS - 1) / VC_THREADS), VC_THREADS, 0, st>>>(VOX_BITMAP(ctx->vox_acc, ctx->vox_slots), n_warps,
+                                                                                             warp_counts);
     DA3S_LAUNCH_CHECK(ctx);
-    voxel_scan_kernel<<<1, 1024, 0, st>>>(warp_counts, n_warps, warp_offsets, ctx->vox_dropped);
+    voxel_scan_kernel<<<1, 1024, 0, st>>>(warp_counts, (int)n_warps, warp_offsets, ctx->vox_counters);
     DA3S_LAUNCH_CHECK(ctx);
-    voxel_emit_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_offsets, occ_bits, voxel, max_voxels,
+    voxel_emit_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_offsets, warp_counts, voxel, max_voxels,
                                                        xyz_out, rgb_out, count_out, key_out);
     DA3S_LAUNCH_CHECK(ctx);
-    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_voxels, ctx->vox_dropped, 8, cudaMemcpyDeviceToDevice, st));
+    DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_voxels, ctx->vox_counters, 8, cudaMemcpyDeviceToDevice, st));
     if (n_dropped)
-        DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_dropped, ctx->vox_dropped + 1, 8, cudaMemcpyDeviceToDevice, st));
+        DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_dropped, ctx->vox_counters + 1, 8, cudaMemcpyDeviceToDevice, st));
     ctx->vox_active = false;
-    ctx->vox_clean = true;          // every occupied key was reset in place by the compaction pass
+    ctx->vox_clean = true;          // every occupied key and every bitmap word was reset in place by the compaction pass
     return DA3S_OK;
 }

@@ -229,6 +229,28 @@ def apply_sim3(points: torch.Tensor, sim3: torch.Tensor, out_f64: bool | None = 
     return out
 
 
+def filter_points(xyz, rgb, conf, valid, thr=None, xyz_out=None, rgb_out=None):
+    """Ordered compaction of a resident cloud (da3s_filter_points): keep point i iff valid[i] (None = all) and, when thr is
+    given, conf[i] >= thr.  xyz [n,3] f32, rgb [n,3] u8 or None, conf [n] f32, valid [n] u8/bool or None.  Returns
+    (xyz_kept, rgb_kept) trimmed to the kept count (this helper synchronises to learn it)."""
+    n = xyz.shape[0]
+    dev = xyz.device
+    ctx = context(dev)
+    if valid is not None and valid.dtype == torch.bool:
+        valid = valid.view(torch.uint8)
+    out_xyz = xyz_out if xyz_out is not None else torch.empty((n, 3), dtype=torch.float32, device=dev)
+    out_rgb = None
+    if rgb is not None:
+        out_rgb = rgb_out if rgb_out is not None else torch.empty((n, 3), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int64, device=dev)
+    rc = ctx.lib.da3s_filter_points(ctx.h, _ptr(xyz, "xyz", torch.float32), _ptr(rgb, "rgb", torch.uint8), _ptr(conf, "conf", torch.float32),
+                                    _ptr(valid, "valid", torch.uint8), n, int(thr is not None), float(thr if thr is not None else 0.0),
+                                    out_xyz.shape[0], _ptr(out_xyz), _ptr(out_rgb), _ptr(cnt), _stream(xyz))
+    L.check(rc, "da3s_filter_points")
+    k = int(cnt.item())
+    return out_xyz[:k], (out_rgb[:k] if out_rgb is not None else None)
+
+
 # ------------------------------------------------------------------------------------------
 # exact selection
 # ------------------------------------------------------------------------------------------
@@ -506,7 +528,7 @@ class VoxelGrid:
         self.device = device
         self.table_slots = table_slots
         self.max_voxels = max_voxels
-        need = table_slots * 73 + (256 << 20)
+        need = table_slots * 66 + (256 << 20)
         if private_ctx:                  # its own da3s_ctx (= its own table): several grids on one device
             with torch.cuda.device(device):
                 self.ctx = Context(device, need)
@@ -578,18 +600,21 @@ class VoxelGrid:
                                                     float(conf_floor or 0.0), float(depth_eps or 0.0), float(voxel), self._st())
         L.check(rc, "da3s_unproject_voxel_jobs")
 
-    def send(self, world, rank, inboxes, counts, cap):
+    def send(self, world, rank, inboxes, counts, flags, step, cap):
         """Multi-GPU merge, step 1: compact this rank's table and write every record into the inbox of the rank
-        that owns its key.  inboxes[d] / counts[d]: rank d's [world, cap, 6] int64 inbox and [world] int64 counters
-        as tensors mapped in THIS process (own tensors for d == rank, CUDA-IPC mappings for the peers)."""
+        that owns its key.  inboxes[d] / counts[d] / flags[d]: rank d's [world, cap, 6] int64 inbox, [world] int64 record
+        counts and [world] int64 arrival flags (this step's half) as tensors mapped in THIS process (own tensors for
+        d == rank, CUDA-IPC mappings for the peers).  After its stores the kernel writes `step` into flags[d][rank]."""
         ip = (C.c_void_p * world)(*[t.data_ptr() for t in inboxes])
         cp = (C.c_void_p * world)(*[t.data_ptr() for t in counts])
-        rc = self.ctx.lib.da3s_voxel_send(self.ctx.h, world, rank, ip, cp, cap, self._st())
+        fp = (C.c_void_p * world)(*[t.data_ptr() for t in flags])
+        rc = self.ctx.lib.da3s_voxel_send(self.ctx.h, world, rank, ip, cp, fp, int(step), cap, self._st())
         L.check(rc, "da3s_voxel_send")
 
-    def merge_inbox(self, inbox, counts, world, cap):
-        """Multi-GPU merge, step 2 (after every rank's send has completed): fold the own inbox into the table."""
-        rc = self.ctx.lib.da3s_voxel_merge_inbox(self.ctx.h, _ptr(inbox), _ptr(counts), world, cap, self._st())
+    def merge_inbox(self, inbox, counts, world, cap, flags=None, step=0):
+        """Multi-GPU merge, step 2: wait on the device until every rank's records of `step` have arrived (flags given),
+        then fold the own inbox into the table."""
+        rc = self.ctx.lib.da3s_voxel_merge_inbox(self.ctx.h, _ptr(inbox), _ptr(counts), _ptr(flags), int(step), world, cap, self._st())
         L.check(rc, "da3s_voxel_merge_inbox")
 
     def finish(self, voxel):
@@ -621,7 +646,7 @@ def voxel_downsample(clouds, voxel: float, table_slots: int | None = None, max_v
     if table_slots is None:
         table_slots = 1 << max(10, int(math.ceil(math.log2(max(2 * total, 1024)))))
         table_slots = min(table_slots, 1 << 28)
-    need = table_slots * 73 + (64 << 20)
+    need = table_slots * 66 + (64 << 20)
     ctx = context(dev, need)
     if max_voxels is None:
         max_voxels = min(total, table_slots)

@@ -104,18 +104,26 @@ class VoxelExchange:
     cap = records any one rank may send to any other one (>= voxels_of_a_rank / world, with slack).
     local=True: every rank lives in THIS process (several grids on one device — the single-GPU test);
     call attach_local() with all of them, no process group is used.  Otherwise the inbox storages are
-    shared through CUDA IPC and mapped into every rank of `group`."""
+    shared through CUDA IPC and mapped into every rank of `group`.
+
+    No host synchronisation in a merge: the send kernel of rank s raises flags[d][s] = step in rank d's memory after a
+    system-scope fence over its peer stores, and rank d's merge waits for its `world` flags ON THE DEVICE.  Inbox, counts
+    and flags are double-buffered by step parity, so the records a fast peer sends for step k + 1 can never land in the
+    buffer a slow owner is still merging for step k (csrc/voxel.cu explains why one spare buffer is enough)."""
 
     def __init__(self, device, world: int, rank: int, cap: int, group=None, local: bool = False):
         self.device, self.world, self.rank, self.cap, self.group = torch.device(device), world, rank, int(cap), group
-        self.inbox = torch.zeros((world, self.cap, 6), dtype=torch.int64, device=self.device)
-        self.counts = torch.zeros((world,), dtype=torch.int64, device=self.device)
-        self.peer_inbox, self.peer_counts = [None] * world, [None] * world
+        # [parity][...]: one allocation each, so that ONE IPC handle per array covers both halves
+        self.inbox = torch.zeros((2, world, self.cap, 6), dtype=torch.int64, device=self.device)
+        self.counts = torch.zeros((2, world), dtype=torch.int64, device=self.device)
+        self.flags = torch.zeros((2, world), dtype=torch.int64, device=self.device)
+        self.peer_inbox, self.peer_counts, self.peer_flags = [None] * world, [None] * world, [None] * world
         self._keep = []
         self._peer_devices, self._enabled_for = set(), None
         self.local = bool(local)
+        self.step = 0
         if world == 1:
-            self.peer_inbox, self.peer_counts = [self.inbox], [self.counts]
+            self.peer_inbox, self.peer_counts, self.peer_flags = [self.inbox], [self.counts], [self.flags]
         elif not self.local:
             self._map_ipc()
 
@@ -123,41 +131,51 @@ class VoxelExchange:
         """peers: the VoxelExchange of every rank, all in this process."""
         self.peer_inbox = [p.inbox for p in peers]
         self.peer_counts = [p.counts for p in peers]
+        self.peer_flags = [p.flags for p in peers]
 
     def _map_ipc(self):
-        mine = (self.inbox.untyped_storage()._share_cuda_(), self.counts.untyped_storage()._share_cuda_())
+        mine = tuple(t.untyped_storage()._share_cuda_() for t in (self.inbox, self.counts, self.flags))
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=self.group)
-        for r, (hi, hc) in enumerate(everyone):
+        shapes = ((2, self.world, self.cap, 6), (2, self.world), (2, self.world))
+        for r, handles in enumerate(everyone):
             if r == self.rank:
-                self.peer_inbox[r], self.peer_counts[r] = self.inbox, self.counts
+                self.peer_inbox[r], self.peer_counts[r], self.peer_flags[r] = self.inbox, self.counts, self.flags
                 continue
-            # open the handles with OUR device current (first field of the tuple): the mapping is then made for the
-            # device whose kernels will store through it (cudaIpcOpenMemHandle + lazy peer access over NVLink)
-            si = torch.UntypedStorage._new_shared_cuda(self.device.index, *hi[1:])
-            sc = torch.UntypedStorage._new_shared_cuda(self.device.index, *hc[1:])
-            self._keep += [si, sc]
-            self._peer_devices.add(hi[0])
-            # the mapping belongs to the peer's device; only its address is used (by kernels running on OUR device)
-            self.peer_inbox[r] = torch.empty(0, dtype=torch.int64, device=si.device).set_(si).view(self.world, self.cap, 6)
-            self.peer_counts[r] = torch.empty(0, dtype=torch.int64, device=sc.device).set_(sc).view(self.world)
+            views = []
+            for h, shp in zip(handles, shapes):
+                # open the handles with OUR device current (first field of the tuple): the mapping is then made for the
+                # device whose kernels will store through it (cudaIpcOpenMemHandle + lazy peer access over NVLink)
+                st = torch.UntypedStorage._new_shared_cuda(self.device.index, *h[1:])
+                self._keep.append(st)
+                self._peer_devices.add(h[0])
+                # the mapping belongs to the peer's device; only its address is used (by kernels running on OUR device)
+                views.append(torch.empty(0, dtype=torch.int64, device=st.device).set_(st).view(*shp))
+            self.peer_inbox[r], self.peer_counts[r], self.peer_flags[r] = views
         dist.barrier(group=self.group)                               # nobody frees a storage before it is mapped
 
     def send(self, grid):
+        """Starts merge number self.step + 1: enqueue this rank's send (compaction + peer stores + arrival flags)."""
         if self._peer_devices and self._enabled_for is not grid.ctx:
             from . import _lib
             for d in sorted(self._peer_devices):
                 _lib.check(grid.ctx.lib.da3s_enable_peer_access(grid.ctx.h, d), "da3s_enable_peer_access")
             self._enabled_for = grid.ctx
-        grid.send(self.world, self.rank, self.peer_inbox, self.peer_counts, self.cap)
+        self.step += 1
+        p = self.step & 1
+        grid.send(self.world, self.rank, [t[p] for t in self.peer_inbox], [t[p] for t in self.peer_counts],
+                  [t[p] for t in self.peer_flags], self.step, self.cap)
+
+    def fold(self, grid):
+        """Enqueue the owner side of the current merge: device-side wait for every rank's arrival flag, then the fold."""
+        p = self.step & 1
+        grid.merge_inbox(self.inbox[p], self.counts[p], self.world, self.cap, flags=self.flags[p], step=self.step)
 
     def merge(self, grid, voxel: float):
-        """Collective: after it, `grid.read()` returns this rank's share of the global map (voxels whose key it owns)."""
-        self.send(grid)
+        """Collective (every rank calls it once per step), enqueue-only: after it, `grid.read()` returns this rank's share
+        of the global map (the voxels whose key it owns)."""
         if self.local and self.world > 1:
-            raise RuntimeError("local exchanges are driven rank by rank: send() all, then merge_inbox() + finish() each")
-        if self.world > 1:
-            torch.cuda.synchronize(self.device)                      # my peer stores have landed
-            dist.barrier(group=self.group)                           # ... and so have everybody else's
-        grid.merge_inbox(self.inbox, self.counts, self.world, self.cap)
+            raise RuntimeError("local exchanges are driven rank by rank: send() all, then fold() + finish() each")
+        self.send(grid)
+        self.fold(grid)
         grid.finish(voxel)

@@ -128,6 +128,14 @@ int da3s_unproject_filter_jobs(da3s_ctx* ctx, const da3s_frame_job* jobs, int n_
 int da3s_apply_sim3(da3s_ctx* ctx, const void* xyz_in, int in_f64, long long n_points,
                     const double* sim3 /* device [13] */, void* xyz_out, int out_f64, void* stream);
 
+/* ---- ordered filter + compaction of a resident cloud --------------------------------------
+ * Replaces the map push of viewer.py:333-355 (`points[conf >= thr]`): keeps point i iff valid[i] != 0 (nullable = all) and,
+ * when use_thr, conf[i] >= thr; writes the kept points (and colours, nullable pair) densely in INPUT order and their number
+ * to *n_out (device).  At most max_out points are written (n_out still reports the full count). */
+int da3s_filter_points(da3s_ctx* ctx, const float* xyz /* [n,3] */, const uint8_t* rgb /* [n,3] or null */,
+                       const float* conf /* [n] */, const uint8_t* valid /* [n] or null */, long long n, int use_thr, float thr,
+                       long long max_out, float* xyz_out, uint8_t* rgb_out, unsigned long long* n_out, void* stream);
+
 /* ---- exact selection: medians and percentiles --------------------------------------------
  * Replaces np.median (utils/align.py:140-141, align_geometry.py:329,
  * utils/align_geometry_single.py:46) and np.percentile (viewer.py:334-335,
@@ -343,14 +351,22 @@ int da3s_icp_points(da3s_ctx* ctx, const void* src, long long n_src, const void*
  *                           48-byte record {key, sum_qx, sum_qy, sum_qz, (n,sum_r), (sum_g,sum_b)} into the
  *                           inbox of the rank that owns its key: inbox_ptrs[d] is rank d's inbox
  *                           [world][cap][6] u64 mapped into this process (peer memory over NVLink, e.g. a
- *                           CUDA-IPC mapping), count_ptrs[d] its [world] u64 counters; rank r writes
- *                           segment r and counts[r].  Records beyond `cap` are dropped and reported by finish.
- *   (the callers synchronise: every rank's send must have completed)
- *   da3s_voxel_merge_inbox  folds this rank's own inbox into its table; da3s_voxel_finish then emits the
- *                           rank's share of the global map.  Integer sums => bit-identical to one GPU. */
+ *                           CUDA-IPC mapping), count_ptrs[d] its [world] u64 record counts, flag_ptrs[d] its
+ *                           [world] u64 arrival flags; rank r writes segment r, counts[r] and — after a
+ *                           system-scope fence over all its stores — flags[r] = step.  Records beyond `cap`
+ *                           are dropped and reported by finish.
+ *   da3s_voxel_merge_inbox  waits ON THE DEVICE until flags[s] >= step for every source rank s (no host
+ *                           synchronisation, no process-group barrier; flags = null skips the wait when the
+ *                           caller has synchronised otherwise), then folds this rank's own inbox into its table;
+ *                           da3s_voxel_finish emits the rank's share of the global map.
+ * `step` must increase by one per merge; callers alternate between two inbox/counts/flags buffers by step parity so
+ * that a peer's stores of step k+1 never land in the buffer being merged for step k (sharding.VoxelExchange).
+ * Integer sums => bit-identical to one GPU. */
 int da3s_voxel_send(da3s_ctx* ctx, int world, int rank, void* const* inbox_ptrs /* host array [world] */,
-                    void* const* count_ptrs /* host array [world] */, long long cap, void* stream);
-int da3s_voxel_merge_inbox(da3s_ctx* ctx, const void* inbox, const void* counts, int world, long long cap, void* stream);
+                    void* const* count_ptrs /* host array [world] */, void* const* flag_ptrs /* host array [world] */,
+                    unsigned long long step, long long cap, void* stream);
+int da3s_voxel_merge_inbox(da3s_ctx* ctx, const void* inbox, const void* counts, const void* flags /* nullable */,
+                           unsigned long long step, int world, long long cap, void* stream);
 int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxels, float* xyz_out, uint8_t* rgb_out,
                       int32_t* count_out, long long* key_out, unsigned long long* n_voxels,
                       unsigned long long* n_dropped /* nullable: points lost to a full table */, void* stream);

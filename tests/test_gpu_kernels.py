@@ -436,6 +436,25 @@ def test_voxel_dense_cloud_warp_reduction(cuda, centre):
             assert np.array_equal(out[1].cpu().numpy(), col)
 
 
+@pytest.mark.parametrize("voxel", [0.02, 0.05, 1.0 / 3.0, 0.1, 1.0, 0.0078125, 0.3, 1e-3, 7.25])
+def test_voxel_quantisation_is_the_correctly_rounded_division(cuda, voxel):
+    """SPEC 5 keys and fractions come from q = f64(p) / f64(f32(voxel)) CORRECTLY ROUNDED; the kernel evaluates it with two
+    Markstein corrections instead of the division routine.  Adversarial coordinates: exact multiples of the voxel size and
+    their float32 neighbours (floor flips with the last bit of q), every binade from 1e-30 to the key range, both signs."""
+    rng = np.random.default_rng(int(voxel * 1e6) % 9973)
+    v32 = np.float32(voxel)
+    k = rng.integers(-(1 << 19), 1 << 19, size=60000).astype(np.float64)
+    edge = (k * np.float64(v32)).astype(np.float32)
+    near = np.concatenate([edge, np.nextafter(edge, np.float32(np.inf)), np.nextafter(edge, np.float32(-np.inf))])
+    mags = (10.0 ** rng.uniform(-30, np.log10(float(v32) * (1 << 19)), size=60000) * rng.choice([-1.0, 1.0], size=60000)).astype(np.float32)
+    col = np.concatenate([near, mags, rng.normal(0, 5 * float(v32), 60000).astype(np.float32)])
+    pts = np.stack([col, rng.permutation(col), rng.permutation(col)], axis=1)
+    xyz, _, cnt, key = ops.voxel_downsample([(dev_t(pts, cuda), None, None)], float(v32), table_slots=1 << 21)
+    e_xyz, _, e_cnt, e_key = sp.voxel_downsample(pts, float(v32), None, None)
+    assert np.array_equal(key.cpu().numpy(), e_key) and np.array_equal(cnt.cpu().numpy(), e_cnt)
+    assert np.array_equal(xyz.cpu().numpy(), e_xyz)
+
+
 def test_voxel_accumulates_across_clouds(cuda):
     rng = np.random.default_rng(4)
     a = rng.normal(0, 0.5, (5000, 3)).astype(np.float32)
@@ -494,14 +513,14 @@ def test_voxel_multi_rank_merge_is_bit_exact(cuda):
         grids[r].begin()
         grids[r].insert(dev_t(pts[r], cuda), dev_t(rgb[r], cuda), None, voxel)
     for r in range(world):
-        ex[r].send(grids[r])
-    torch.cuda.synchronize()
-    shares = []
+        ex[r].send(grids[r])                                                  # every send is enqueued before the first fold:
+    shares = []                                                               # the device-side waits below find their flags set
     for r in range(world):
-        grids[r].merge_inbox(ex[r].inbox, ex[r].counts, world, cap)
+        ex[r].fold(grids[r])
         grids[r].finish(voxel)
         shares.append([t.cpu().numpy() for t in grids[r].read(sort=True)])
-    assert int(sum(int(e.counts.sum()) for e in ex)) >= sum(len(s_[3]) for s_ in shares)
+    assert int(sum(int(e.counts[1].sum()) for e in ex)) >= sum(len(s_[3]) for s_ in shares)       # step 1 -> parity 1
+    assert all(int(v) == 1 for e in ex for v in e.flags[1].cpu())             # every rank saw every rank's arrival flag
     key = np.concatenate([s_[3] for s_ in shares])
     assert len(np.unique(key)) == len(key)                                   # every voxel has exactly one owner
     order = np.argsort(key)
@@ -517,12 +536,13 @@ def test_voxel_multi_rank_merge_is_bit_exact(cuda):
 
 def test_voxel_merge_across_gpus():
     """The real thing: one process per GPU, inboxes mapped through CUDA IPC, records stored over NVLink
-    (tests/multi_gpu_voxel_check.py).  Needs two GPUs; profiles/r1_multi_gpu_voxel_merge_2gpu.json is a recorded run."""
+    (tests/multi_gpu_voxel_check.py): five merges back to back without host synchronisation, one rank held back per step.
+    Needs two GPUs; profiles/r2_multi_gpu_voxel_merge_*.json are recorded runs on 2, 4 and 8 GPUs."""
     import json, os, subprocess, sys
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, POINTS="500000")
+    env = dict(os.environ, POINTS="500000", STEPS="5")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29577", os.path.join(here, "multi_gpu_voxel_check.py")], capture_output=True, text=True,
                        env=env, timeout=600)
@@ -739,3 +759,20 @@ def test_unproject_jobs_equals_flat_launch(cuda):
     ops.unproject_filter_jobs(ops.make_frame_jobs(jobs, cuda), n, H, W, mode="fast", world=True, conf_cmp=">=", conf_floor=0.0,
                               depth_eps=1e-6, n_kept=kept)
     assert torch.equal(xyz, torch.cat(ref_xyz)) and torch.equal(mask.bool(), torch.cat(ref_mask)) and int(kept.item()) == ref_cnt
+
+
+@pytest.mark.parametrize("n", [0, 1, 2047, 2048, 2049, 300001])
+def test_filter_points_is_an_ordered_compaction(cuda, n):
+    """da3s_filter_points == points[valid & (conf >= thr)] in input order (viewer.py:333-355), bit for bit."""
+    rng = np.random.default_rng(n + 3)
+    xyz = rng.normal(size=(n, 3)).astype(np.float32)
+    rgb = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    conf = rng.random(n).astype(np.float32)
+    valid = rng.random(n) < 0.7
+    d = [dev_t(a, cuda) for a in (xyz, rgb, conf, valid)]
+    for thr in (None, 0.35, 2.0):
+        want = valid if thr is None else valid & (conf >= np.float32(thr))
+        p, c = ops.filter_points(d[0], d[1], d[2], d[3], thr=thr)
+        assert np.array_equal(p.cpu().numpy(), xyz[want]) and np.array_equal(c.cpu().numpy(), rgb[want])
+    p, c = ops.filter_points(d[0], None, d[2], None, thr=0.5)                   # no validity bytes, no colours
+    assert c is None and np.array_equal(p.cpu().numpy(), xyz[conf >= np.float32(0.5)])

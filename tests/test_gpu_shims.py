@@ -196,6 +196,18 @@ def test_viewer_against_restated_reference(cuda):
     assert 0 < len(v.visible_points()[0]) < len(pts)
     v.clear()
     assert v.total_points == 0 and len(v.visible_points()[0]) == 0
+    # the map is append-only: adding F frames re-allocates O(log F) times and never re-stacks what is already stored
+    # (the reference vstacks the whole map per frame, viewer.py:323-330)
+    v = viewer.SLAMViewer(port=0)
+    caps, ptrs = set(), set()
+    for f in range(40):
+        v.add_frame(img[f % n], depth[f % n], conf[f % n], E[f % n], K[f % n])
+        caps.add(v._cap); ptrs.add(v._xyz.data_ptr())
+    assert len(v.frames) == 40 and v._used == 40 * H * W and len(caps) <= 3 and len(ptrs) <= 3
+    v.frame_selector = "39"
+    one = v.visible_points()[0]
+    v.frame_selector = "All"
+    assert 0 < len(one) < len(v.visible_points()[0])
 
 
 @pytest.mark.gpu
