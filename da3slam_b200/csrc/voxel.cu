@@ -33,6 +33,9 @@
 #ifndef VOX_EXP_NOCOMMIT
 #define VOX_EXP_NOCOMMIT 0                  // measurement only: 1 = no table access at all, 2 = bitmap atomics + key reads only
 #endif
+#ifndef VOX_SPEC_LOAD
+#define VOX_SPEC_LOAD 0
+#endif
 #ifndef VOX_MERGE_PULL
 #define VOX_MERGE_PULL 1                    // 1: leaders pull their peers' 32-bit point values (4 shuffles per round); 0: 64-bit partial sums (10)
 #endif
@@ -105,11 +108,15 @@ __device__ __forceinline__ bool vox_commit(unsigned long long* __restrict__ acc,
     for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
         unsigned long long* rec = VOX_REC_PTR(acc, slot);
         const unsigned int bit = 1u << (slot & 31);
+#if VOX_SPEC_LOAD
+        // the key is read in parallel with the arbitration (two independent round trips in flight instead of two in a
+        // row for every contribution that turns out to be an addition); for a claim the value is ignored
+        unsigned long long cur = ld_acquire_u64(rec);
         const unsigned int old = atomicOr(bm + (slot >> 5), bit);
-        if (!(old & bit)) {
-#if VOX_EXP_NOCOMMIT >= 2
-            return true;
+#else
+        const unsigned int old = atomicOr(bm + (slot >> 5), bit);
 #endif
+        if (!(old & bit)) {
             // ours: both sectors as whole 256-bit stores (a full-sector write allocates in L2 without fetching the line
             // from DRAM; a partial one does not) — sector 0 carries the key with VOX_BUSY set — then the key alone with
             // release semantics: everything above is visible device-wide before the key loses its BUSY bit
@@ -122,7 +129,9 @@ __device__ __forceinline__ bool vox_commit(unsigned long long* __restrict__ acc,
 #endif
             return true;
         }
+#if !VOX_SPEC_LOAD
         unsigned long long cur = ld_acquire_u64(rec);
+#endif
         while (cur & VOX_BUSY) { __nanosleep(32); cur = ld_acquire_u64(rec); }       // EMPTY or key | BUSY: claimed, not yet published
         if (cur == key) {
 #if VOX_EXP_NOCOMMIT >= 2
@@ -170,7 +179,7 @@ static VoxQuant make_quant(float voxel) {
 // in the same voxel, then probe / claim / five additions by the merged lanes.  Every lane of the warp calls it.
 __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py, float pz, unsigned int rgb, bool has_rgb, const VoxQuant& qz,
                                                  unsigned long long* __restrict__ acc, long long slots,
-                                                 unsigned long long* __restrict__ counters) {
+                                                 unsigned long long* __restrict__ counters, uint4* __restrict__ gather /* [32], this warp's */) {
     const unsigned int lane = threadIdx.x & 31;
     unsigned long long key = 0, sx = 0, sy = 0, sz = 0, cr = 1ull << 32, gb = 0ull;
     active = active && is_finite_f(px) && is_finite_f(py) && is_finite_f(pz);
@@ -219,17 +228,23 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
     } else if (peers != (1u << lane)) {
         unsigned int rest = peers & ~(1u << leader);                // identical for every lane of the group
 #if VOX_MERGE_PULL
-        // every lane still holds ONE point: its three fractions are < 2^32 and its colour is 24 bits, so the leader pulls
-        // four 32-bit words per peer and accumulates in 64 bits (the peers never accumulate)
-        const unsigned int fx = (unsigned int)sx, fy = (unsigned int)sy, fz = (unsigned int)sz;
+        // every lane still holds ONE point: its three fractions are <= 2^32 (llrint of a fraction just below 1 gives 2^32:
+        // bit 32 travels in the colour word's top byte) and its colour is 24 bits.  Every lane of a multi-point group
+        // publishes its point as one 128-bit word in the warp's scratch; the leader then reads one LDS.128 per peer and
+        // accumulates in 64 bits (the peers never accumulate, and leave).
+        gather[lane] = make_uint4((unsigned int)sx, (unsigned int)sy, (unsigned int)sz,
+                                  (rgb & 0xFFFFFFu) | ((unsigned int)(sx >> 32) << 24) | ((unsigned int)(sy >> 32) << 25) | ((unsigned int)(sz >> 32) << 26));
+        __syncwarp(peers);
+        if (lane != leader) return;
         while (rest) {
             const int src = __ffs(rest) - 1;
             rest &= rest - 1;
-            const unsigned int ax = __shfl_sync(peers, fx, src), ay = __shfl_sync(peers, fy, src), az = __shfl_sync(peers, fz, src);
-            const unsigned int ac = __shfl_sync(peers, rgb, src);
-            sx += ax; sy += ay; sz += az;
-            cr += (1ull << 32) | (unsigned long long)(ac & 0xFFu);
-            gb += ((unsigned long long)((ac >> 8) & 0xFFu) << 32) | (unsigned long long)((ac >> 16) & 0xFFu);
+            const uint4 g = gather[src];
+            sx += (unsigned long long)g.x + ((unsigned long long)((g.w >> 24) & 1u) << 32);
+            sy += (unsigned long long)g.y + ((unsigned long long)((g.w >> 25) & 1u) << 32);
+            sz += (unsigned long long)g.z + ((unsigned long long)((g.w >> 26) & 1u) << 32);
+            cr += (1ull << 32) | (unsigned long long)(g.w & 0xFFu);
+            gb += ((unsigned long long)((g.w >> 8) & 0xFFu) << 32) | (unsigned long long)((g.w >> 16) & 0xFFu);
         }
 #else
         while (rest) {
@@ -252,14 +267,14 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
 
 __device__ __forceinline__ void voxel_insert_point(bool active, long long i, const da3s_voxel_job& job, const VoxQuant& qz,
                                                    unsigned long long* __restrict__ acc,
-                                                   long long slots, unsigned long long* __restrict__ counters) {
+                                                   long long slots, unsigned long long* __restrict__ counters, uint4* __restrict__ gather) {
     float px = 0.0f, py = 0.0f, pz = 0.0f;
     unsigned int rgb = 0u;
     if (active) {
         px = job.xyz[3 * i]; py = job.xyz[3 * i + 1]; pz = job.xyz[3 * i + 2];
         if (job.rgb) rgb = (unsigned int)job.rgb[3 * i] | ((unsigned int)job.rgb[3 * i + 1] << 8) | ((unsigned int)job.rgb[3 * i + 2] << 16);
     }
-    voxel_insert_xyz(active, px, py, pz, rgb, job.rgb != nullptr, qz, acc, slots, counters);
+    voxel_insert_xyz(active, px, py, pz, rgb, job.rgb != nullptr, qz, acc, slots, counters, gather);
 }
 
 // One launch inserts any number of clouds (a job table) — e.g. every submap of a sequence.  Work unit of a warp = a
@@ -283,8 +298,10 @@ voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job sing
                     int width, VoxQuant qz, unsigned long long* __restrict__ acc,
                     long long slots, unsigned long long* __restrict__ counters /* [0]=voxels (set by finish) [1]=dropped */) {
     __shared__ long long queue[VI_THREADS / 32][VI_QUEUE];
+    __shared__ uint4 gather_sh[VI_THREADS / 32][32];
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long* q = queue[warp];
+    uint4* gather = gather_sh[warp];
     const long long total = chunks_per_job * n_jobs;
     const int tiles_per_band = width > 0 ? (width + 15) / 16 : 1;
     for (long long c = blockIdx.x; c < total; c += gridDim.x) {
@@ -336,7 +353,7 @@ voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job sing
             __syncwarp();
             while (count >= 32) {
                 const long long i = q[(head + lane) & (VI_QUEUE - 1)];
-                voxel_insert_point(true, i, job, qz, acc, slots, counters);
+                voxel_insert_point(true, i, job, qz, acc, slots, counters, gather);
                 __syncwarp();
                 head += 32; count -= 32;
             }
@@ -344,7 +361,7 @@ voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job sing
         if (count) {                                                // the queue never crosses a job boundary
             const bool active = lane < count;
             const long long i = active ? q[(head + lane) & (VI_QUEUE - 1)] : 0;
-            voxel_insert_point(active, i, job, qz, acc, slots, counters);
+            voxel_insert_point(active, i, job, qz, acc, slots, counters, gather);
             __syncwarp();
         }
     }
@@ -356,10 +373,13 @@ voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job sing
 // (shared device functions), so the grid is bit-identical to the two-kernel route; what disappears
 // is 13 B/pixel of K1 stores and ~16 B/kept point of insert loads.
 // ---------------------------------------------------------------------------------
-#define EX_CONST 20                         // floats per frame: cu cv 1/fu 1/fv | Mf[9] | mf[3] | thr | use_conf | pad
+#define EX_CONST 24                         // floats per frame: cu cv 1/fu 1/fv | Mf[9] | mf[3] | thr_ge thr_gt d_lo d_hi | pad
 
-__global__ void export_frame_const_kernel(const da3s_export_job* __restrict__ jobs, int n_frames, int world, float conf_thr,
-                                          float* __restrict__ fcs) {
+// Per-frame constants of the fused export.  The filter flags become four thresholds, so the per-pixel test is four
+// compares and no flag logic:  keep = conf >= thr_ge & conf > thr_gt & depth > d_lo & depth <= d_hi  (a disabled test
+// gets -inf / +inf; a frame without confidences is given conf = 1).
+__global__ void export_frame_const_kernel(const da3s_export_job* __restrict__ jobs, int n_frames, int world, int flags, float conf_thr,
+                                          float conf_floor, float depth_eps, float* __restrict__ fcs) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     const da3s_export_job j = jobs[f];
@@ -373,50 +393,72 @@ __global__ void export_frame_const_kernel(const da3s_export_job* __restrict__ jo
     // a NaN threshold = a selection over no usable confidence (da3s_select): the reference keeps every point then
     // (viewer.py:333-338), so the confidence tests are switched off for this frame
     const bool use_conf = j.conf != nullptr && !(thr != thr);
-    o[16] = use_conf ? thr : 0.0f;
-    o[17] = use_conf ? 1.0f : 0.0f;
-    o[18] = o[19] = 0.0f;
+    const float ninf = __int_as_float(0xff800000), pinf = __int_as_float(0x7f800000);
+    float thr_ge = ninf, thr_gt = ninf;
+    if (use_conf) {
+        if (flags & DA3S_MASK_CONF_GE) thr_ge = thr;
+        if (flags & DA3S_MASK_CONF_GT) thr_gt = thr;
+        if (flags & DA3S_MASK_CONF_FLOOR) thr_gt = fmaxf(thr_gt, conf_floor);
+    }
+    o[16] = thr_ge; o[17] = thr_gt;
+    o[18] = (flags & DA3S_MASK_DEPTH) ? depth_eps : ninf;          // depth > eps and finite  ==  eps < depth <= FLT_MAX
+    o[19] = (flags & DA3S_MASK_DEPTH) ? 3.402823466e+38f : pinf;   // without the test non-finite depths go on and are dropped as points
+    o[20] = use_conf ? 1.0f : 0.0f;
+    o[21] = o[22] = o[23] = 0.0f;
 }
 
 struct ExportArgs {
     const da3s_export_job* jobs; const float* fcs;
-    int n_frames, H, W, flags;
-    float conf_floor, depth_eps;
+    int n_frames, H, W;
     VoxQuant qz;
-    long long chunks_per_frame;
+    int chunks_per_frame, tiles_per_band;
     unsigned long long* acc; long long slots; unsigned long long* counters;
 };
 
 __global__ void __launch_bounds__(VI_THREADS, VI_MIN_BLOCKS)
 export_voxel_kernel(ExportArgs a) {
-    __shared__ unsigned long long queue[VI_THREADS / 32][VI_QUEUE];     // (depth bits << 32) | (v << 16) | u
+    __shared__ unsigned int qd[VI_THREADS / 32][VI_QUEUE];        // depth bits of the queued pixels
+    __shared__ unsigned int qp[VI_THREADS / 32][VI_QUEUE];        // (v << 16) | u
     __shared__ float fc_sh[VI_THREADS / 32][EX_CONST];
+    __shared__ uint4 gather_sh[VI_THREADS / 32][32];
     const VoxQuant qz = a.qz;
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long* q = queue[warp];
+    unsigned int* qdw = qd[warp];
+    unsigned int* qpw = qp[warp];
     float* fc = fc_sh[warp];
+    uint4* gather = gather_sh[warp];
     const int W = a.W, H = a.H;
-    const int tiles_per_band = (W + 15) / 16;
-    const long long total = a.chunks_per_frame * a.n_frames;
-    const bool f_gt = a.flags & DA3S_MASK_CONF_GT, f_ge = a.flags & DA3S_MASK_CONF_GE;
-    const bool f_floor = a.flags & DA3S_MASK_CONF_FLOOR, f_depth = a.flags & DA3S_MASK_DEPTH;
-    for (long long c = blockIdx.x; c < total; c += gridDim.x) {
-        const int f = (int)(c / a.chunks_per_frame);
+    const int total = a.chunks_per_frame * a.n_frames;
+    const int lrow = (int)(lane >> 2), lcol = (int)(lane & 3) * 4;
+    for (int c = blockIdx.x; c < total; c += gridDim.x) {
+        const int f = c / a.chunks_per_frame;
         const da3s_export_job job = a.jobs[f];
         __syncwarp();
         if (lane < EX_CONST) fc[lane] = a.fcs[(size_t)f * EX_CONST + lane];
         __syncwarp();
-        const float thr = fc[16];
-        const bool use_conf = fc[17] != 0.0f;
-        const long long t_begin = (c - (long long)f * a.chunks_per_frame) * VI_TILES_PER_BLOCK + (long long)warp * VI_TILES_PER_WARP;
+        const float thr_ge = fc[16], thr_gt = fc[17], d_lo = fc[18], d_hi = fc[19];
+        const bool use_conf = fc[20] != 0.0f;
+        // word-wise colour loads need a 4-byte aligned frame whose size is a multiple of 4 (the last pixel's second word)
+        const bool rgb_words = job.rgb && ((reinterpret_cast<uintptr_t>(job.rgb) & 3) == 0) && (((unsigned int)(H * W) * 3u) & 3u) == 0u;
+        const int t_begin = (c - f * a.chunks_per_frame) * VI_TILES_PER_BLOCK + (int)warp * VI_TILES_PER_WARP;
         unsigned int head = 0, count = 0;                           // warp-uniform ring state
-        auto batch = [&](bool active, unsigned long long e) {
-            const int u = (int)(e & 0xFFFFu), v = (int)((e >> 16) & 0xFFFFu);
-            const float d = __uint_as_float((unsigned int)(e >> 32));
+        auto batch = [&](bool active, unsigned int dbits, unsigned int uv) {
+            const int u = (int)(uv & 0xFFFFu), v = (int)(uv >> 16);
+            const float d = __uint_as_float(dbits);
             unsigned int rgb = 0u;
             if (active && job.rgb) {
-                const uint8_t* p = job.rgb + 3 * ((size_t)v * W + u);
-                rgb = (unsigned int)p[0] | ((unsigned int)p[1] << 8) | ((unsigned int)p[2] << 16);
+                const unsigned int off = 3u * (unsigned int)(v * W + u);
+                if (rgb_words) {
+                    // the pixel's three bytes from one or two aligned 32-bit loads (half the requests of three byte loads)
+                    const unsigned int* wp = reinterpret_cast<const unsigned int*>(job.rgb + (off & ~3u));
+                    const unsigned int sh = (off & 3u) * 8u;
+                    rgb = __ldg(wp) >> sh;
+                    if (sh > 8u) rgb |= __ldg(wp + 1) << (32u - sh);
+                    rgb &= 0xFFFFFFu;
+                } else {
+                    const uint8_t* p = job.rgb + off;
+                    rgb = (unsigned int)p[0] | ((unsigned int)p[1] << 8) | ((unsigned int)p[2] << 16);
+                }
             }
             // K1 fast path (unproject_pixel<DA3S_UNPROJ_FAST> with the composed float32 transform)
             float x, y;
@@ -424,27 +466,26 @@ export_voxel_kernel(ExportArgs a) {
             const float X = fmaf(fc[4], x, fmaf(fc[5], y, fmaf(fc[6], d, fc[13])));
             const float Y = fmaf(fc[7], x, fmaf(fc[8], y, fmaf(fc[9], d, fc[14])));
             const float Z = fmaf(fc[10], x, fmaf(fc[11], y, fmaf(fc[12], d, fc[15])));
-            voxel_insert_xyz(active, X, Y, Z, rgb, job.rgb != nullptr, qz, a.acc, a.slots, a.counters);
+            voxel_insert_xyz(active, X, Y, Z, rgb, job.rgb != nullptr, qz, a.acc, a.slots, a.counters, gather);
         };
 #pragma unroll 1
         for (int tt = 0; tt < VI_TILES_PER_WARP; ++tt) {
-            const long long t = t_begin + tt;
-            const long long band = t / tiles_per_band;
-            const int tx = (int)(t - band * tiles_per_band);
-            const int col = tx * 16 + (int)(lane & 3) * 4;
-            const int row = (int)band * 8 + (int)(lane >> 2);
+            const int t = t_begin + tt;
+            const int band = t / a.tiles_per_band;
+            const int col = (t - band * a.tiles_per_band) * 16 + lcol;
+            const int row = band * 8 + lrow;
+            if (band * 8 >= H) break;                               // past the end of this frame (warp-uniform)
             int lim = W - col;
             if (lim > 4) lim = 4;
             if (row >= H) lim = 0;
-            if (__ballot_sync(0xffffffffu, lim > 0) == 0) break;    // past the end of this frame (warp-uniform)
-            float d4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
+            float d4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {1.f, 1.f, 1.f, 1.f};
             if (lim > 0) {
-                const size_t i0 = (size_t)row * W + col;
-                if (lim == 4 && ((i0 & 1) == 0)) {                  // 8-byte aligned pairs (frames are 16-byte aligned)
+                const unsigned int i0 = (unsigned int)(row * W + col);
+                if (lim == 4 && ((i0 & 1u) == 0u)) {                // 8-byte aligned pairs (frames are 16-byte aligned)
                     const float2 da = ldg_stream(reinterpret_cast<const float2*>(job.depth + i0));
                     const float2 db = ldg_stream(reinterpret_cast<const float2*>(job.depth + i0 + 2));
                     d4[0] = da.x; d4[1] = da.y; d4[2] = db.x; d4[3] = db.y;
-                    if (job.conf) {
+                    if (use_conf) {
                         const float2 ca = ldg_stream(reinterpret_cast<const float2*>(job.conf + i0));
                         const float2 cb = ldg_stream(reinterpret_cast<const float2*>(job.conf + i0 + 2));
                         c4[0] = ca.x; c4[1] = ca.y; c4[2] = cb.x; c4[3] = cb.y;
@@ -452,16 +493,13 @@ export_voxel_kernel(ExportArgs a) {
                 } else {
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
-                        if (b < lim) { d4[b] = job.depth[i0 + b]; if (job.conf) c4[b] = job.conf[i0 + b]; }
+                        if (b < lim) { d4[b] = job.depth[i0 + b]; if (use_conf) c4[b] = job.conf[i0 + b]; }
                 }
             }
             unsigned int flags = 0;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const float cc = c4[b], dd = d4[b];
-                bool k = b < lim;
-                if (use_conf) k = k & (!f_gt || cc > thr) & (!f_ge || cc >= thr) & (!f_floor || cc > a.conf_floor);
-                k = k & (!f_depth || ((dd > a.depth_eps) & is_finite_f(dd)));
+                const bool k = (b < lim) & (c4[b] >= thr_ge) & (c4[b] > thr_gt) & (d4[b] > d_lo) & (d4[b] <= d_hi);
                 flags |= k ? (1u << b) : 0u;
             }
             const unsigned int cnt = __popc(flags);
@@ -473,24 +511,27 @@ export_voxel_kernel(ExportArgs a) {
             }
             const unsigned int total_new = __shfl_sync(0xffffffffu, incl, 31);
             unsigned int pos = head + count + incl - cnt;
+            const unsigned int uv0 = ((unsigned int)row << 16) | (unsigned int)col;
 #pragma unroll
             for (int b = 0; b < 4; ++b)
                 if ((flags >> b) & 1u) {
-                    q[pos & (VI_QUEUE - 1)] = ((unsigned long long)__float_as_uint(d4[b]) << 32) | ((unsigned long long)row << 16) |
-                                              (unsigned long long)(col + b);
+                    qdw[pos & (VI_QUEUE - 1)] = __float_as_uint(d4[b]);
+                    qpw[pos & (VI_QUEUE - 1)] = uv0 + b;
                     ++pos;
                 }
             count += total_new;
             __syncwarp();
             while (count >= 32) {
-                batch(true, q[(head + lane) & (VI_QUEUE - 1)]);
+                const unsigned int qi = (head + lane) & (VI_QUEUE - 1);
+                batch(true, qdw[qi], qpw[qi]);
                 __syncwarp();
                 head += 32; count -= 32;
             }
         }
         if (count) {                                                // the queue never crosses a frame boundary
             const bool active = lane < count;
-            batch(active, active ? q[(head + lane) & (VI_QUEUE - 1)] : 0ull);
+            const unsigned int qi = (head + lane) & (VI_QUEUE - 1);
+            batch(active, active ? qdw[qi] : 0u, active ? qpw[qi] : 0u);
             __syncwarp();
         }
     }
@@ -506,18 +547,22 @@ extern "C" int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* j
     cudaStream_t st = (cudaStream_t)stream;
     size_t save_top = ctx->ws_top;
     WS_ALLOC(ctx, float, fcs, (size_t)n_frames * EX_CONST);
-    export_frame_const_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(jobs_dev, n_frames, (flags & DA3S_UNPROJ_WORLD) ? 1 : 0, conf_thr, fcs);
+    export_frame_const_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(jobs_dev, n_frames, (flags & DA3S_UNPROJ_WORLD) ? 1 : 0, flags, conf_thr,
+                                                                      conf_floor, depth_eps, fcs);
     DA3S_LAUNCH_CHECK(ctx);
     ExportArgs a;
-    a.jobs = jobs_dev; a.fcs = fcs; a.n_frames = n_frames; a.H = H; a.W = W; a.flags = flags;
-    a.conf_floor = conf_floor; a.depth_eps = depth_eps; a.qz = make_quant(voxel);
-    const long long tiles = (long long)((H + 7) / 8) * ((W + 15) / 16);
-    a.chunks_per_frame = (tiles + VI_TILES_PER_BLOCK - 1) / VI_TILES_PER_BLOCK;
+    a.jobs = jobs_dev; a.fcs = fcs; a.n_frames = n_frames; a.H = H; a.W = W;
+    a.qz = make_quant(voxel);
+    a.tiles_per_band = (W + 15) / 16;
+    const long long tiles = (long long)((H + 7) / 8) * a.tiles_per_band;
+    const long long cpf = (tiles + VI_TILES_PER_BLOCK - 1) / VI_TILES_PER_BLOCK;
+    if (cpf * n_frames > 2147483647LL || (long long)H * W > 1400000000LL) return DA3S_EINVAL;     // 32-bit tile / pixel indices in the kernel
+    a.chunks_per_frame = (int)cpf;
     a.acc = ctx->vox_acc; a.slots = ctx->vox_slots; a.counters = ctx->vox_counters;
     int per_sm = 0;
     DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, export_voxel_kernel, VI_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
-    const long long total = a.chunks_per_frame * n_frames, cap = (long long)ctx->sm_count * per_sm;
+    const long long total = (long long)a.chunks_per_frame * n_frames, cap = (long long)ctx->sm_count * per_sm;
     export_voxel_kernel<<<(unsigned int)(total > cap ? cap : total), VI_THREADS, 0, st>>>(a);
     DA3S_LAUNCH_CHECK(ctx);
     ctx->ws_top = save_top;     // the constants are consumed in stream order
@@ -615,12 +660,13 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
     const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + warp;
     const long long base = wid * VC_PER_WARP;
     if (base >= slots) return;
-    if (warp_counts[wid] == 0u) return;                           // nothing in these 512 slots (warp-uniform): 4 bytes read
     unsigned int* bm = VOX_BITMAP(acc, slots) + wid * VC_ROUNDS;
     // The warp's 512 slots as 16 occupancy words.  The occupied slots are handled DENSELY: lane l of dense round r
     // takes the (32 r + l)-th occupied slot, so the number of rounds — and of record loads in flight per warp —
-    // follows the voxels, not the table size.
-    const unsigned int my_word = lane < VC_ROUNDS ? bm[lane] : 0u;
+    // follows the voxels, not the table size.  The three per-group loads are independent: issued together.
+    const unsigned int my_word = lane < VC_ROUNDS ? __ldcs(bm + lane) : 0u;
+    const unsigned long long out0 = __ldcs(warp_offsets + wid);
+    if (__ldcs(warp_counts + wid) == 0u) return;                  // nothing in these 512 slots (warp-uniform)
     const unsigned int my_cnt = __popc(my_word);
     unsigned int incl = my_cnt;
 #pragma unroll
@@ -631,7 +677,6 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
     const unsigned int total = __shfl_sync(0xffffffffu, incl, VC_ROUNDS - 1);
     if (lane < VC_ROUNDS) { s_word[warp][lane] = my_word; s_excl[warp][lane] = incl - my_cnt; bm[lane] = 0u; }
     __syncwarp();
-    const unsigned long long out0 = warp_offsets[wid];
     for (unsigned int r0 = 0; r0 < total; r0 += 128u) {          // 4 dense rounds at a time: their record loads overlap
         ulonglong2 r01[4], r23[4], r45[4];                        // (key, sum_x), (sum_y, sum_z), ((n, sum_r), (sum_g, sum_b))
         unsigned long long* recs[4];
@@ -648,9 +693,6 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
                 recs[q] = rec;
             }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)                                // after ALL loads of the four rounds have been issued
-            if (occ[q]) *recs[q] = VOX_EMPTY;                      // the record itself is rewritten by the next claimer (vox_commit)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (!occ[q]) continue;
@@ -681,6 +723,11 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
             count_out[o] = (int32_t)cnt;
             if (key_out) key_out[o] = (long long)k64;
         }
+        // key resets LAST, when the loads above have long returned (a store to a sector whose fill is still in flight
+        // stalls behind it); the record itself is rewritten by the next claimer (vox_commit)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (occ[q]) *recs[q] = VOX_EMPTY;
     }
 }
 
@@ -713,24 +760,41 @@ __device__ __forceinline__ int vox_owner(unsigned long long key, int world) {
     return (int)((vox_hash(key) >> 40) % (unsigned long long)world);      // high bits: independent of the slot index
 }
 
+// this warp's 512-slot group as dense occupancy ranks (shared: words + exclusive popcounts); returns the occupied count
+__device__ __forceinline__ unsigned int vox_group_ranks(const unsigned int* bm, unsigned int lane, unsigned int* s_word, unsigned int* s_excl) {
+    const unsigned int my_word = lane < VC_ROUNDS ? bm[lane] : 0u;
+    const unsigned int my_cnt = __popc(my_word);
+    unsigned int incl = my_cnt;
+#pragma unroll
+    for (int o = 1; o < VC_ROUNDS; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    if (lane < VC_ROUNDS) { s_word[lane] = my_word; s_excl[lane] = incl - my_cnt; }
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, incl, VC_ROUNDS - 1);
+}
+
 __global__ void __launch_bounds__(VC_THREADS)
 voxel_count_dest_kernel(const unsigned long long* __restrict__ acc, long long slots, int world,
                         unsigned int* __restrict__ warp_counts /* [n_warps][world] */) {
-    const unsigned int lane = threadIdx.x & 31;
-    const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
+    __shared__ unsigned int s_word[VC_THREADS / 32][VC_ROUNDS], s_excl[VC_THREADS / 32][VC_ROUNDS];
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + warp;
     const long long base = wid * VC_PER_WARP;
     if (base >= slots) return;
-    const unsigned int* bm = VOX_BITMAP(acc, slots) + wid * VC_ROUNDS;
-    const unsigned int my_word = lane < VC_ROUNDS ? bm[lane] : 0u;
+    const unsigned int total = vox_group_ranks(VOX_BITMAP(acc, slots) + wid * VC_ROUNDS, lane, s_word[warp], s_excl[warp]);
     unsigned int mine = 0;                                       // lane d counts destination d
-    if (__ballot_sync(0xffffffffu, my_word != 0u)) {
-#pragma unroll 4
-        for (int j = 0; j < VC_ROUNDS; ++j) {
-            const unsigned int word = __shfl_sync(0xffffffffu, my_word, j);
-            if (word == 0u) continue;                            // warp-uniform
-            const bool occ = (word >> lane) & 1u;
-            const unsigned long long k = occ ? __ldcs(VOX_REC_PTR(acc, base + (long long)j * 32 + lane)) : VOX_EMPTY;
-            const int owner = occ ? vox_owner(k, world) : -1;
+    for (unsigned int r0 = 0; r0 < total; r0 += 128u) {          // dense walk, four rounds of key loads in flight
+        unsigned long long k[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned int rank = r0 + 32u * q + lane;
+            k[q] = rank < total ? __ldcs(VOX_REC_PTR(acc, base + vox_nth_slot(s_word[warp], s_excl[warp], rank))) : VOX_EMPTY;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int owner = k[q] != VOX_EMPTY ? vox_owner(k[q], world) : -1;
             for (int d = 0; d < world; ++d) {
                 const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
                 if ((int)lane == d) mine += __popc(m);
@@ -778,40 +842,52 @@ voxel_scan_dest_kernel(const unsigned int* __restrict__ counts, int n, int world
 __global__ void __launch_bounds__(VC_THREADS)
 voxel_send_kernel(unsigned long long* __restrict__ acc, long long slots, const unsigned long long* __restrict__ offsets,
                   int world, int rank, long long cap, VoxPeers peers, unsigned int* __restrict__ ticket, unsigned long long step) {
-    const unsigned int lane = threadIdx.x & 31;
-    const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + (threadIdx.x >> 5);
+    __shared__ unsigned int s_word[VC_THREADS / 32][VC_ROUNDS], s_excl[VC_THREADS / 32][VC_ROUNDS];
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long wid = (long long)blockIdx.x * (VC_THREADS / 32) + warp;
     const long long base = wid * VC_PER_WARP;
     if (base < slots) {
         unsigned int* bm = VOX_BITMAP(acc, slots) + wid * VC_ROUNDS;
-        const unsigned int my_word = lane < VC_ROUNDS ? bm[lane] : 0u;
-        if (__ballot_sync(0xffffffffu, my_word != 0u)) {
+        const unsigned int total = vox_group_ranks(bm, lane, s_word[warp], s_excl[warp]);
+        if (total) {
             unsigned long long out = (int)lane < world ? offsets[wid * world + lane] : 0ull;    // lane d: next index for destination d
-            for (int j = 0; j < VC_ROUNDS; ++j) {
-                const unsigned int word = __shfl_sync(0xffffffffu, my_word, j);
-                if (word == 0u) continue;                        // warp-uniform
-                const bool occ = (word >> lane) & 1u;
-                unsigned long long* rec = VOX_REC_PTR(acc, base + (long long)j * 32 + lane);
-                ulonglong2 r01 = make_ulonglong2(VOX_EMPTY, 0ull), r23 = make_ulonglong2(0ull, 0ull), r45 = make_ulonglong2(0ull, 0ull);
-                if (occ) {
-                    r01 = *reinterpret_cast<const ulonglong2*>(rec);
-                    r23 = *reinterpret_cast<const ulonglong2*>(rec + 2);
-                    r45 = *reinterpret_cast<const ulonglong2*>(rec + 4);
-                    *rec = VOX_EMPTY;
+            for (unsigned int r0 = 0; r0 < total; r0 += 128u) {  // dense walk in slot order (the order the count pass used)
+                ulonglong2 r01[4], r23[4], r45[4];
+                unsigned long long* recs[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned int rk = r0 + 32u * q + lane;
+                    recs[q] = nullptr;
+                    r01[q] = make_ulonglong2(VOX_EMPTY, 0ull);
+                    if (rk < total) {
+                        unsigned long long* rec = VOX_REC_PTR(acc, base + vox_nth_slot(s_word[warp], s_excl[warp], rk));
+                        r01[q] = *reinterpret_cast<const ulonglong2*>(rec);
+                        r23[q] = *reinterpret_cast<const ulonglong2*>(rec + 2);
+                        r45[q] = *reinterpret_cast<const ulonglong2*>(rec + 4);
+                        recs[q] = rec;
+                    }
                 }
-                const int owner = occ ? vox_owner(r01.x, world) : -1;
-                unsigned long long my_idx = 0;
-                for (int d = 0; d < world; ++d) {
-                    const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
-                    const unsigned long long start = __shfl_sync(0xffffffffu, out, d);
-                    if (owner == d) my_idx = start + __popc(m & ((1u << lane) - 1u));
-                    if ((int)lane == d) out += __popc(m);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool occ = recs[q] != nullptr;
+                    const int owner = occ ? vox_owner(r01[q].x, world) : -1;
+                    unsigned long long my_idx = 0;
+                    for (int d = 0; d < world; ++d) {
+                        const unsigned int m = __ballot_sync(0xffffffffu, owner == d);
+                        const unsigned long long start = __shfl_sync(0xffffffffu, out, d);
+                        if (owner == d) my_idx = start + __popc(m & ((1u << lane) - 1u));
+                        if ((int)lane == d) out += __popc(m);
+                    }
+                    if (occ && (long long)my_idx < cap) {
+                        unsigned long long* dst = peers.inbox[owner] + ((size_t)rank * (size_t)cap + my_idx) * 6;   // NVLink stores
+                        *reinterpret_cast<ulonglong2*>(dst) = r01[q];
+                        *reinterpret_cast<ulonglong2*>(dst + 2) = r23[q];
+                        *reinterpret_cast<ulonglong2*>(dst + 4) = r45[q];
+                    }
                 }
-                if (occ && (long long)my_idx < cap) {
-                    unsigned long long* dst = peers.inbox[owner] + ((size_t)rank * (size_t)cap + my_idx) * 6;   // NVLink stores
-                    *reinterpret_cast<ulonglong2*>(dst) = r01;
-                    *reinterpret_cast<ulonglong2*>(dst + 2) = r23;
-                    *reinterpret_cast<ulonglong2*>(dst + 4) = r45;
-                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)                        // key resets last (see voxel_emit_kernel)
+                    if (recs[q]) *recs[q] = VOX_EMPTY;
             }
             if (lane < VC_ROUNDS) bm[lane] = 0u;
         }

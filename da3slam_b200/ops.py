@@ -236,6 +236,8 @@ def filter_points(xyz, rgb, conf, valid, thr=None, xyz_out=None, rgb_out=None):
     n = xyz.shape[0]
     dev = xyz.device
     ctx = context(dev)
+    if n == 0:
+        return xyz[:0], (rgb[:0] if rgb is not None else None)
     if valid is not None and valid.dtype == torch.bool:
         valid = valid.view(torch.uint8)
     out_xyz = xyz_out if xyz_out is not None else torch.empty((n, 3), dtype=torch.float32, device=dev)
