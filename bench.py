@@ -642,6 +642,8 @@ def gpu_arm(args, w, rank, world):
     # pinned host buffers are allocated after this: first touch places them next to the GPU
     numa_node = bind_to_gpu_numa(local) if world > 1 else gpu_numa_node(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"                        # keeps NCCL's version banner off stdout (ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
     timer = Timer(dev, world)
     out = main_section(args, w, rank, world, dev, local, timer, numa_node)

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "sim3_math.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, long long max_n,
                      da3s_select_out* out, cudaStream_t st);
@@ -350,6 +351,15 @@ pair_moments_kernel(PairArgs a) {
 // ---------------------------------------------------------------------------------
 #define PM_THREADS 128
 #define PM_NMOM 22                          // S0, Sx[3], Sy[3], Syx[9], Sxx[6]
+#ifndef PM_DEPTH
+#define PM_DEPTH 3                          // groups (64 B each) a thread keeps in flight through cp.async; 0 = two register buffers
+#endif
+#define PM_RING_BYTES ((PM_DEPTH > 0 ? (PM_DEPTH + 1) : 0) * 4 * PM_THREADS * 16)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -358,8 +368,16 @@ __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.app
 // (pair, tile) work items of the pairs that have not converged, the last block of a pair
 // (ticket) solves it, a grid-wide barrier separates iterations, and the kernel ends as soon as
 // no pair is active — no empty launches, no host involvement between iterations.
-template <bool VEC, bool GATE, bool HUBER>
-__global__ void __launch_bounds__(PM_THREADS, 4)
+//
+// PK (default whenever W is even): the two horizontally adjacent pixels of a float4 half share every float32
+// instruction — packed FFMA2 / FMUL2 / FADD2 on register pairs (.x = pixel 2i, .y = pixel 2i + 1; W even means a pair
+// never straddles a row).  The kernel is bound by instruction issue, not by the float32 pipe (profiles/r2_fp32_pipes.txt:
+// a scalar FFMA and a packed FFMA2 both issue once per clock per sub-partition, the packed one doing twice the work), so
+// halving the floating-point instruction count is what moves it.  In this form the points are built from the pixel's ray,
+// x = d (a, b, 1) with a = (u - cu) / fu computed once per pair, and only the depth coordinate is pivoted (the lateral
+// coordinates are centred on the principal point already).
+template <bool VEC, bool GATE, bool HUBER, bool PK>
+__global__ void __launch_bounds__(PM_THREADS, PK ? 3 : 4)
 pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     __shared__ double red[MOM_LEN][PM_THREADS];     // block reduction scratch (25.6 KB)
     __shared__ FrameConst fc;
@@ -432,7 +450,7 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
             float p0, p1;
             cam_fast((float)uc, (float)vc, d, in[0], in[1], in[2], in[3], p0, p1);
             const float v = (t % 3 == 0) ? p0 : ((t % 3 == 1) ? p1 : d);
-            piv[t] = is_finite_f(v) ? v : 0.0f;
+            piv[t] = (is_finite_f(v) && (!PK || t % 3 == 2)) ? v : 0.0f;       // PK: depth coordinate only
         }
     } else if (GATE && threadIdx.x == 32) {
         load_frame_const(fc, pr, frame, a, pair);    // float32 c2w + winning hypothesis for the RANSAC gate
@@ -512,6 +530,74 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
         accumulate(uf, vf, da.w, ca.w, db.w, cb.w);
     };
 
+    // ---- PK: two adjacent pixels per instruction ----
+    float2 m2[PK ? PM_NMOM : 1];
+    float2 r2sum2 = make_float2(0.0f, 0.0f);
+    if (PK) {
+#pragma unroll
+        for (int k = 0; k < (PK ? PM_NMOM : 1); ++k) m2[k] = make_float2(0.0f, 0.0f);
+    }
+    const float2 ds2 = make_float2(ds, ds), pz2x = make_float2(px2, px2), pz2y = make_float2(py2, py2);
+    auto dup = [](float v) { return make_float2(v, v); };
+    auto accumulate2 = [&](float uf, float vf, float2 da, const float2 ca, const float2 db, const float2 cb) {
+        float2 dbs = __fmul2_rn(db, ds2);
+        const bool ok0 = (da.x > eps) & (dbs.x > eps) & is_finite_f(da.x) & is_finite_f(dbs.x);
+        const bool ok1 = (da.y > eps) & (dbs.y > eps) & is_finite_f(da.y) & is_finite_f(dbs.y);
+        bool k0 = (ca.x > thr) & (cb.x > thr) & (ok0 | any_depth);
+        bool k1 = (ca.y > thr) & (cb.y > thr) & (ok1 | any_depth);
+        da = make_float2(k0 ? da.x : 0.0f, k1 ? da.y : 0.0f);
+        dbs = make_float2(k0 ? dbs.x : 0.0f, k1 ? dbs.y : 0.0f);
+        // rays of the two pixels: a = (u - cu) / fu (pixel 2i, 2i + 1), b = (v - cv) / fv (shared)
+        const float aA = (uf - cuA) * ifuA, aB = (uf - cuB) * ifuB;
+        const float2 aA2 = make_float2(aA, aA + ifuA), aB2 = make_float2(aB, aB + ifuB);
+        const float2 bA2 = dup((vf - cvA) * ifvA), bB2 = dup((vf - cvB) * ifvB);
+        const float2 y0 = __fmul2_rn(da, aA2), y1 = __fmul2_rn(da, bA2), x0 = __fmul2_rn(dbs, aB2), x1 = __fmul2_rn(dbs, bB2);
+        if (GATE && gate_on) {                                  // block-uniform; SPEC 4 arithmetic on SPEC 1 points, per pixel
+            float xa[3], ya[3], xs[3], ys[3];
+            cam_fast(uf, vf, da.x, cuA, cvA, ifuA, ifvA, ya[0], ya[1]); ya[2] = da.x;
+            cam_fast(uf, vf, dbs.x, cuB, cvB, ifuB, ifvB, xa[0], xa[1]); xa[2] = dbs.x;
+            ransac_points(fc, a.world, xa, ya, xs, ys);
+            k0 = k0 & (residual2_f32(fc.gate, xs, ys) < a.gate_thr2);
+            cam_fast(uf + 1.0f, vf, da.y, cuA, cvA, ifuA, ifvA, ya[0], ya[1]); ya[2] = da.y;
+            cam_fast(uf + 1.0f, vf, dbs.y, cuB, cvB, ifuB, ifvB, xa[0], xa[1]); xa[2] = dbs.y;
+            ransac_points(fc, a.world, xa, ya, xs, ys);
+            k1 = k1 & (residual2_f32(fc.gate, xs, ys) < a.gate_thr2);
+        }
+        const float2 cc = __fmul2_rn(ca, cb);
+        float2 w = make_float2(sqrt_approx(k0 ? cc.x : 0.0f), sqrt_approx(k1 ? cc.y : 0.0f));   // utils/align.py:166
+        if (HUBER) {
+            const float2 r0 = __ffma2_rn(dup(B[0]), x0, __ffma2_rn(dup(B[1]), x1, __ffma2_rn(dup(B[2]), dbs, __fadd2_rn(y0, dup(c3[0])))));
+            const float2 r1 = __ffma2_rn(dup(B[3]), x0, __ffma2_rn(dup(B[4]), x1, __ffma2_rn(dup(B[5]), dbs, __fadd2_rn(y1, dup(c3[1])))));
+            const float2 r2 = __ffma2_rn(dup(B[6]), x0, __ffma2_rn(dup(B[7]), x1, __ffma2_rn(dup(B[8]), dbs, __fadd2_rn(da, dup(c3[2])))));
+            const float2 rr = __ffma2_rn(r0, r0, __ffma2_rn(r1, r1, __fmul2_rn(r2, r2)));
+            const float2 wh = __fmul2_rn(w, make_float2(a.delta_f * rsqrt_approx(rr.x), a.delta_f * rsqrt_approx(rr.y)));
+            w = make_float2((rr.x > a.delta2_f) ? wh.x : w.x, (rr.y > a.delta2_f) ? wh.y : w.y);         // Huber: delta / r
+            r2sum2 = __fadd2_rn(r2sum2, make_float2(k0 ? rr.x : 0.0f, k1 ? rr.y : 0.0f));
+        }
+        const float2 xc2 = __fadd2_rn(dbs, make_float2(-pz2x.x, -pz2x.y)), yc2 = __fadd2_rn(da, make_float2(-pz2y.x, -pz2y.y));
+        const float2 wx0 = __fmul2_rn(w, x0), wx1 = __fmul2_rn(w, x1), wx2 = __fmul2_rn(w, xc2);
+        m2[0] = __fadd2_rn(m2[0], w);
+        m2[1] = __fadd2_rn(m2[1], wx0); m2[2] = __fadd2_rn(m2[2], wx1); m2[3] = __fadd2_rn(m2[3], wx2);
+        m2[4] = __ffma2_rn(w, y0, m2[4]); m2[5] = __ffma2_rn(w, y1, m2[5]); m2[6] = __ffma2_rn(w, yc2, m2[6]);
+        m2[7] = __ffma2_rn(y0, wx0, m2[7]);    m2[8] = __ffma2_rn(y0, wx1, m2[8]);    m2[9] = __ffma2_rn(y0, wx2, m2[9]);
+        m2[10] = __ffma2_rn(y1, wx0, m2[10]);  m2[11] = __ffma2_rn(y1, wx1, m2[11]);  m2[12] = __ffma2_rn(y1, wx2, m2[12]);
+        m2[13] = __ffma2_rn(yc2, wx0, m2[13]); m2[14] = __ffma2_rn(yc2, wx1, m2[14]); m2[15] = __ffma2_rn(yc2, wx2, m2[15]);
+        m2[16] = __ffma2_rn(wx0, x0, m2[16]);  m2[17] = __ffma2_rn(wx0, x1, m2[17]);  m2[18] = __ffma2_rn(wx0, xc2, m2[18]);
+        m2[19] = __ffma2_rn(wx1, x1, m2[19]);  m2[20] = __ffma2_rn(wx1, xc2, m2[20]); m2[21] = __ffma2_rn(wx2, xc2, m2[21]);
+        wmax = fmaxf(wmax, fmaxf(w.x, w.y));
+        cnt += (k0 ? 1 : 0) + (k1 ? 1 : 0);
+    };
+    auto flush2 = [&]() {
+#pragma unroll
+        for (int k = 0; k < (PK ? PM_NMOM : 1); ++k) { red[k][threadIdx.x] += (double)(m2[k].x + m2[k].y); m2[k] = make_float2(0.0f, 0.0f); }
+        red[MOM_SR][threadIdx.x] += (double)(r2sum2.x + r2sum2.y); r2sum2 = make_float2(0.0f, 0.0f);
+    };
+    auto group2 = [&](float uf, float vf, const float4& da, const float4& ca, const float4& db, const float4& cb) {
+        accumulate2(uf, vf, make_float2(da.x, da.y), make_float2(ca.x, ca.y), make_float2(db.x, db.y), make_float2(cb.x, cb.y));
+        uf += 2.0f; if (uf >= a.W_f) { uf -= a.W_f; vf += 1.0f; }        // W even: a pair never straddles a row
+        accumulate2(uf, vf, make_float2(da.z, da.w), make_float2(ca.z, ca.w), make_float2(db.z, db.w), make_float2(cb.z, cb.w));
+    };
+
     if (VEC) {
         const long long n_groups = a.P >> 2;
         const long long g_begin = (long long)tile * PA_GROUPS_PER_BLOCK;
@@ -524,39 +610,72 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
         const float step_v = (float)step_vi, step_u = (float)(step_px - step_vi * a.W);
         float u0f, v0f;
         { const long long p0 = (g_begin + threadIdx.x) << 2; const int v0 = (int)(p0 / a.W); v0f = (float)v0; u0f = (float)(int)(p0 - (long long)v0 * a.W); }
-        // software pipeline: the 4 loads (64 B) of the thread's NEXT group are in flight while the current
-        // group (4 correspondences) is accumulated; two register buffers alternate (no copies), running
-        // pointers (no per-group address arithmetic); float64 flush every 4 groups (16 correspondences)
         const long long g_first = g_begin + threadIdx.x;
         int left = g_first < g_end ? (int)((g_end - g_first + PM_THREADS - 1) / PM_THREADS) : 0;
         const float4* pdA = dA4 + g_first; const float4* pcA = cA4 + g_first;
         const float4* pdB = dB4 + g_first; const float4* pcB = cB4 + g_first;
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 a0 = z4, a1 = z4, a2 = z4, a3 = z4, b0 = z4, b1 = z4, b2 = z4, b3 = z4;
-        if (left > 0) { a0 = ldg_stream(pdA); a1 = ldg_stream(pcA); a2 = ldg_stream(pdB); a3 = ldg_stream(pcB); }
         auto advance = [&]() {
             u0f += step_u; v0f += step_v;
             if (u0f >= a.W_f) { u0f -= a.W_f; v0f += 1.0f; }
         };
+#if PM_DEPTH > 0
+        // asynchronous copy ring (cp.async, 16 bytes per array and group, straight into shared memory): PM_DEPTH groups
+        // = PM_DEPTH x 64 bytes per thread are in flight while the current group is accumulated, without holding them in
+        // registers.  Measured on loop512 (512 pairs, 2.69 passes): with the scalar inner loop the kernel is issue bound and
+        // the ring changes nothing (IRLS 1.64 ms at depth 0, 2, 3); with the packed inner loop the issue rate drops to 44 %,
+        // global-load latency becomes the first stall, and depth 3 gives 1.50 ms (depth 2: 1.57, 4: 1.53, 6: 1.74).
+        // Every thread reads back only what it copied itself (no block barrier); the slot refilled in an iteration is the one
+        // consumed in the PREVIOUS iteration.  One (possibly empty) commit per iteration keeps wait_group's count uniform.
+        extern __shared__ float4 pm_ring[];                     // [PM_DEPTH + 1][4][PM_THREADS]
+        auto slot_ptr = [&](int sl, int arr) { return pm_ring + ((size_t)(sl * 4 + arr) * PM_THREADS + threadIdx.x); };
+        auto issue = [&](int j) {                                // group j of this thread (j < left) into slot j % (PM_DEPTH + 1)
+            if (j < left) {
+                const int sl = j % (PM_DEPTH + 1);
+                const size_t off = (size_t)j * PM_THREADS;
+                cp_async16(slot_ptr(sl, 0), pdA + off); cp_async16(slot_ptr(sl, 1), pcA + off);
+                cp_async16(slot_ptr(sl, 2), pdB + off); cp_async16(slot_ptr(sl, 3), pcB + off);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int j = 0; j < PM_DEPTH; ++j) issue(j);
+        for (int j = 0; j < left; ++j) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(PM_DEPTH - 1) : "memory");
+            const int sl = j % (PM_DEPTH + 1);
+            const float4 a0 = *slot_ptr(sl, 0), a1 = *slot_ptr(sl, 1), a2 = *slot_ptr(sl, 2), a3 = *slot_ptr(sl, 3);
+            issue(j + PM_DEPTH);
+            if (PK) group2(u0f, v0f, a0, a1, a2, a3); else group(u0f, v0f, a0, a1, a2, a3); advance();
+            if ((j & 3) == 3) { if (PK) flush2(); else flush(); }
+        }
+        if (left & 3) { if (PK) flush2(); else flush(); }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#else
+        // software pipeline: the 4 loads (64 B) of the thread's NEXT group are in flight while the current
+        // group (4 correspondences) is accumulated; two register buffers alternate (no copies), running
+        // pointers (no per-group address arithmetic); float64 flush every 4 groups (16 correspondences)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 a0 = z4, a1 = z4, a2 = z4, a3 = z4, b0 = z4, b1 = z4, b2 = z4, b3 = z4;
+        if (left > 0) { a0 = ldg_stream(pdA); a1 = ldg_stream(pcA); a2 = ldg_stream(pdB); a3 = ldg_stream(pcB); }
         while (left > 0) {                                           // 4 groups per trip
             if (left > 1) { b0 = ldg_stream(pdA + PM_THREADS); b1 = ldg_stream(pcA + PM_THREADS); b2 = ldg_stream(pdB + PM_THREADS); b3 = ldg_stream(pcB + PM_THREADS); }
-            group(u0f, v0f, a0, a1, a2, a3); advance();
+            if (PK) group2(u0f, v0f, a0, a1, a2, a3); else group(u0f, v0f, a0, a1, a2, a3); advance();
             if (left > 1) {
                 if (left > 2) { a0 = ldg_stream(pdA + 2 * PM_THREADS); a1 = ldg_stream(pcA + 2 * PM_THREADS); a2 = ldg_stream(pdB + 2 * PM_THREADS); a3 = ldg_stream(pcB + 2 * PM_THREADS); }
-                group(u0f, v0f, b0, b1, b2, b3); advance();
+                if (PK) group2(u0f, v0f, b0, b1, b2, b3); else group(u0f, v0f, b0, b1, b2, b3); advance();
             }
             if (left > 2) {
                 if (left > 3) { b0 = ldg_stream(pdA + 3 * PM_THREADS); b1 = ldg_stream(pcA + 3 * PM_THREADS); b2 = ldg_stream(pdB + 3 * PM_THREADS); b3 = ldg_stream(pcB + 3 * PM_THREADS); }
-                group(u0f, v0f, a0, a1, a2, a3); advance();
+                if (PK) group2(u0f, v0f, a0, a1, a2, a3); else group(u0f, v0f, a0, a1, a2, a3); advance();
             }
             if (left > 3) {
                 if (left > 4) { a0 = ldg_stream(pdA + 4 * PM_THREADS); a1 = ldg_stream(pcA + 4 * PM_THREADS); a2 = ldg_stream(pdB + 4 * PM_THREADS); a3 = ldg_stream(pcB + 4 * PM_THREADS); }
-                group(u0f, v0f, b0, b1, b2, b3); advance();
+                if (PK) group2(u0f, v0f, b0, b1, b2, b3); else group(u0f, v0f, b0, b1, b2, b3); advance();
             }
-            flush();
+            if (PK) flush2(); else flush();
             pdA += 4 * PM_THREADS; pcA += 4 * PM_THREADS; pdB += 4 * PM_THREADS; pcB += 4 * PM_THREADS;
             left -= 4;
         }
+#endif
     } else {
         int since = 0;
         for (long long pix = p_begin + threadIdx.x; pix < p_end; pix += PM_THREADS) {
@@ -627,7 +746,11 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
             float x[3], y[3], dbs;
             corr_points(g, false, 0.0f, uc, vc, pr.depth_a[pc], 1.0f, pr.depth_b[pc], 1.0f, x, y, dbs);
             double sx[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, sy[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-            for (int k = 0; k < 3; ++k) { sx[4 * k + 3] = is_finite_f(x[k]) ? (double)x[k] : 0.0; sy[4 * k + 3] = is_finite_f(y[k]) ? (double)y[k] : 0.0; }
+            for (int k = 0; k < 3; ++k) {
+                const bool use = !PK || k == 2;                  // the packed kernel pivots the depth coordinate only
+                sx[4 * k + 3] = (use && is_finite_f(x[k])) ? (double)x[k] : 0.0;
+                sy[4 * k + 3] = (use && is_finite_f(y[k])) ? (double)y[k] : 0.0;
+            }
             double mm[MOM_LEN], cam[MOM_LEN];
             for (int k = 0; k < MOM_LEN; ++k) { mm[k] = fmom[k]; cam[k] = 0.0; }
             moments_to_world_add(mm, sx, sy, cam);
@@ -1252,21 +1375,29 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     }
     // persistent cooperative launch: as many blocks as can be co-resident, never more than there are items
     const bool use_gate = a.gate != nullptr;
-    static const void* const table[8] = {
-        (const void*)pair_moments_mixed_kernel<false, false, false>, (const void*)pair_moments_mixed_kernel<false, false, true>,
-        (const void*)pair_moments_mixed_kernel<false, true, false>,  (const void*)pair_moments_mixed_kernel<false, true, true>,
-        (const void*)pair_moments_mixed_kernel<true, false, false>,  (const void*)pair_moments_mixed_kernel<true, false, true>,
-        (const void*)pair_moments_mixed_kernel<true, true, false>,   (const void*)pair_moments_mixed_kernel<true, true, true>};
-    const void* fn = table[(vec ? 4 : 0) | (use_gate ? 2 : 0) | (opts->huber ? 1 : 0)];
+    // PK (packed pixel pairs) needs the float4 path and an even row length; DA3S_IRLS_SCALAR=1 forces the scalar form (A/B runs)
+    static const bool force_scalar = getenv("DA3S_IRLS_SCALAR") && getenv("DA3S_IRLS_SCALAR")[0] == '1';
+    const bool pk = vec && (W % 2 == 0) && !force_scalar;
+    static const void* const table[12] = {
+        (const void*)pair_moments_mixed_kernel<false, false, false, false>, (const void*)pair_moments_mixed_kernel<false, false, true, false>,
+        (const void*)pair_moments_mixed_kernel<false, true, false, false>,  (const void*)pair_moments_mixed_kernel<false, true, true, false>,
+        (const void*)pair_moments_mixed_kernel<true, false, false, false>,  (const void*)pair_moments_mixed_kernel<true, false, true, false>,
+        (const void*)pair_moments_mixed_kernel<true, true, false, false>,   (const void*)pair_moments_mixed_kernel<true, true, true, false>,
+        (const void*)pair_moments_mixed_kernel<true, false, false, true>,   (const void*)pair_moments_mixed_kernel<true, false, true, true>,
+        (const void*)pair_moments_mixed_kernel<true, true, false, true>,    (const void*)pair_moments_mixed_kernel<true, true, true, true>};
+    const void* fn = table[(pk ? 8 : (vec ? 4 : 0)) | (use_gate ? 2 : 0) | (opts->huber ? 1 : 0)];
     int per_sm = 0;
-    DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PM_THREADS, 0));
+    const size_t ring_bytes = vec ? (size_t)PM_RING_BYTES : 0;
+    if (ring_bytes)
+        DA3S_CHECK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+    DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PM_THREADS, ring_bytes));
     if (per_sm < 1) return DA3S_ECUDA;
     long long coop_blocks = (long long)per_sm * ctx->sm_count;
     const long long items = (long long)n_pairs * n_tiles;
     if (coop_blocks > items) coop_blocks = items;
     int max_passes = iters;
     void* kargs[] = {(void*)&a, (void*)&max_passes};
-    DA3S_CHECK_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3((unsigned int)coop_blocks), dim3(PM_THREADS), kargs, 0, st));
+    DA3S_CHECK_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3((unsigned int)coop_blocks), dim3(PM_THREADS), kargs, ring_bytes, st));
     ctx->launches++;
     return DA3S_OK;
 }
