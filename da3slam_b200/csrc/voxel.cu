@@ -31,10 +31,7 @@
 #define VOX_EXP_NOFENCE 0                   // measurement only (NOT correct): publish without release semantics
 #endif
 #ifndef VOX_EXP_NOCOMMIT
-#define VOX_EXP_NOCOMMIT 0                  // measurement only: 1 = no table access at all, 2 = bitmap atomics + key reads only
-#endif
-#ifndef VOX_SPEC_LOAD
-#define VOX_SPEC_LOAD 0
+#define VOX_EXP_NOCOMMIT 0                  // measurement only: 1 = no table access at all (what the kernel costs before the table)
 #endif
 #ifndef VOX_MERGE_PULL
 #define VOX_MERGE_PULL 1                    // 1: leaders pull their peers' 32-bit point values (4 shuffles per round); 0: 64-bit partial sums (10)
@@ -99,23 +96,15 @@ __global__ void voxel_clear_kernel(unsigned long long* acc, long long slots) {
     }
 }
 
-// Add one (already merged) contribution to the voxel `key` (protocol: file header).
-__device__ __forceinline__ bool vox_commit(unsigned long long* __restrict__ acc, long long slots, unsigned long long key,
-                                           unsigned long long sx, unsigned long long sy, unsigned long long sz,
-                                           unsigned long long cr, unsigned long long gb) {
+// Add one (already merged) contribution to the voxel `key` (protocol: file header), probing from `slot`.
+__device__ __forceinline__ bool vox_commit_from(unsigned long long* __restrict__ acc, long long slots, unsigned long long key,
+                                                unsigned long long sx, unsigned long long sy, unsigned long long sz,
+                                                unsigned long long cr, unsigned long long gb, unsigned long long slot) {
     unsigned int* __restrict__ bm = VOX_BITMAP(acc, slots);
-    unsigned long long slot = vox_slot0(key, slots);
     for (int probe = 0; probe < VOX_MAX_PROBE; ++probe) {
         unsigned long long* rec = VOX_REC_PTR(acc, slot);
         const unsigned int bit = 1u << (slot & 31);
-#if VOX_SPEC_LOAD
-        // the key is read in parallel with the arbitration (two independent round trips in flight instead of two in a
-        // row for every contribution that turns out to be an addition); for a claim the value is ignored
-        unsigned long long cur = ld_acquire_u64(rec);
         const unsigned int old = atomicOr(bm + (slot >> 5), bit);
-#else
-        const unsigned int old = atomicOr(bm + (slot >> 5), bit);
-#endif
         if (!(old & bit)) {
             // ours: both sectors as whole 256-bit stores (a full-sector write allocates in L2 without fetching the line
             // from DRAM; a partial one does not) — sector 0 carries the key with VOX_BUSY set — then the key alone with
@@ -129,14 +118,9 @@ __device__ __forceinline__ bool vox_commit(unsigned long long* __restrict__ acc,
 #endif
             return true;
         }
-#if !VOX_SPEC_LOAD
         unsigned long long cur = ld_acquire_u64(rec);
-#endif
         while (cur & VOX_BUSY) { __nanosleep(32); cur = ld_acquire_u64(rec); }       // EMPTY or key | BUSY: claimed, not yet published
         if (cur == key) {
-#if VOX_EXP_NOCOMMIT >= 2
-            return true;
-#endif
             red_add_u64(rec + 1, sx); red_add_u64(rec + 2, sy); red_add_u64(rec + 3, sz);
             red_add_u64(rec + 4, cr);
             if (gb) red_add_u64(rec + 5, gb);
@@ -145,6 +129,11 @@ __device__ __forceinline__ bool vox_commit(unsigned long long* __restrict__ acc,
         slot = (slot + VOX_STEP) & (unsigned long long)(slots - 1);
     }
     return false;
+}
+__device__ __forceinline__ bool vox_commit(unsigned long long* __restrict__ acc, long long slots, unsigned long long key,
+                                           unsigned long long sx, unsigned long long sy, unsigned long long sz,
+                                           unsigned long long cr, unsigned long long gb) {
+    return vox_commit_from(acc, slots, key, sx, sy, sz, cr, gb, vox_slot0(key, slots));
 }
 
 // SPEC 5 quantisation of one coordinate: q = f64(p) / f64(voxel) correctly rounded, k = floor(q), f = llrint((q - k) 2^32).
@@ -177,11 +166,13 @@ static VoxQuant make_quant(float voxel) {
 
 // one batch of up to 32 points held in registers: float64 quantisation, in-warp merge of the lanes that fall
 // in the same voxel, then probe / claim / five additions by the merged lanes.  Every lane of the warp calls it.
-__device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py, float pz, unsigned int rgb, bool has_rgb, const VoxQuant& qz,
-                                                 unsigned long long* __restrict__ acc, long long slots,
-                                                 unsigned long long* __restrict__ counters, uint4* __restrict__ gather /* [32], this warp's */) {
+#define VOX_SCRATCH 32                      // uint4 per warp: one published point per lane (merge)
+// quantise + merge; returns true on the lanes that carry a merged contribution (key, sums) afterwards
+__device__ __forceinline__ bool vox_merge_batch(bool active, float px, float py, float pz, unsigned int rgb, bool has_rgb, const VoxQuant& qz,
+                                                uint4* __restrict__ gather, unsigned long long& key, unsigned long long& sx,
+                                                unsigned long long& sy, unsigned long long& sz, unsigned long long& cr, unsigned long long& gb) {
     const unsigned int lane = threadIdx.x & 31;
-    unsigned long long key = 0, sx = 0, sy = 0, sz = 0, cr = 1ull << 32, gb = 0ull;
+    key = 0; sx = 0; sy = 0; sz = 0; cr = 1ull << 32; gb = 0ull;
     active = active && is_finite_f(px) && is_finite_f(py) && is_finite_f(pz);
     if (active) {
         const double qx = vox_div((double)px, qz), qy = vox_div((double)py, qz), qzz = vox_div((double)pz, qz);
@@ -198,7 +189,7 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
         }
     }
     const unsigned int act = __ballot_sync(0xffffffffu, active);
-    if (!active) return;
+    if (!active) return false;
     // combine the lanes of this warp that hit the same voxel; a lane alone in its voxel skips the exchange
     const unsigned int peers = __match_any_sync(act, key);
     const unsigned int leader = __ffs(peers) - 1;
@@ -220,7 +211,7 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
                 tg = __reduce_add_sync(peers, (unsigned int)(gb >> 32));
                 tb = __reduce_add_sync(peers, (unsigned int)(gb & 0xFFull));
             }
-            if (lane != leader) return;
+            if (lane != leader) return false;
             sx = tx; sy = ty; sz = tz;
             cr = ((unsigned long long)n << 32) | tr;
             gb = (tg << 32) | tb;
@@ -235,7 +226,7 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
         gather[lane] = make_uint4((unsigned int)sx, (unsigned int)sy, (unsigned int)sz,
                                   (rgb & 0xFFFFFFu) | ((unsigned int)(sx >> 32) << 24) | ((unsigned int)(sy >> 32) << 25) | ((unsigned int)(sz >> 32) << 26));
         __syncwarp(peers);
-        if (lane != leader) return;
+        if (lane != leader) return false;
         while (rest) {
             const int src = __ffs(rest) - 1;
             rest &= rest - 1;
@@ -256,8 +247,20 @@ __device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py
             if (lane == leader) { sx += ax; sy += ay; sz += az; cr += ac; gb += ag; }
         }
 #endif
-        if (lane != leader) return;
+        if (lane != leader) return false;
     }
+    return true;
+}
+
+// One batch of up to 32 points: quantise + merge (above), then every carrying lane commits its contribution (vox_commit).
+// Every lane of the warp calls it.  (A warp-cooperative variant — claimers stage their records in shared memory and lane
+// pairs store both halves of a record in one instruction, one 64-byte L2 request instead of two — cut the write requests
+// by 20 % but cost more in extra instructions and warp synchronisation than it saved: profiles/r2_voxel_experiments.md.)
+__device__ __forceinline__ void voxel_insert_xyz(bool active, float px, float py, float pz, unsigned int rgb, bool has_rgb, const VoxQuant& qz,
+                                                 unsigned long long* __restrict__ acc, long long slots,
+                                                 unsigned long long* __restrict__ counters, uint4* __restrict__ gather /* [VOX_SCRATCH], this warp's */) {
+    unsigned long long key, sx, sy, sz, cr, gb;
+    if (!vox_merge_batch(active, px, py, pz, rgb, has_rgb, qz, gather, key, sx, sy, sz, cr, gb)) return;
 #if VOX_EXP_NOCOMMIT == 1
     return;
 #endif
@@ -298,7 +301,7 @@ voxel_insert_kernel(const da3s_voxel_job* __restrict__ jobs, da3s_voxel_job sing
                     int width, VoxQuant qz, unsigned long long* __restrict__ acc,
                     long long slots, unsigned long long* __restrict__ counters /* [0]=voxels (set by finish) [1]=dropped */) {
     __shared__ long long queue[VI_THREADS / 32][VI_QUEUE];
-    __shared__ uint4 gather_sh[VI_THREADS / 32][32];
+    __shared__ uint4 gather_sh[VI_THREADS / 32][VOX_SCRATCH];
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long* q = queue[warp];
     uint4* gather = gather_sh[warp];
@@ -420,7 +423,7 @@ export_voxel_kernel(ExportArgs a) {
     __shared__ unsigned int qd[VI_THREADS / 32][VI_QUEUE];        // depth bits of the queued pixels
     __shared__ unsigned int qp[VI_THREADS / 32][VI_QUEUE];        // (v << 16) | u
     __shared__ float fc_sh[VI_THREADS / 32][EX_CONST];
-    __shared__ uint4 gather_sh[VI_THREADS / 32][32];
+    __shared__ uint4 gather_sh[VI_THREADS / 32][VOX_SCRATCH];
     const VoxQuant qz = a.qz;
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int* qdw = qd[warp];
@@ -438,8 +441,6 @@ export_voxel_kernel(ExportArgs a) {
         __syncwarp();
         const float thr_ge = fc[16], thr_gt = fc[17], d_lo = fc[18], d_hi = fc[19];
         const bool use_conf = fc[20] != 0.0f;
-        // word-wise colour loads need a 4-byte aligned frame whose size is a multiple of 4 (the last pixel's second word)
-        const bool rgb_words = job.rgb && ((reinterpret_cast<uintptr_t>(job.rgb) & 3) == 0) && (((unsigned int)(H * W) * 3u) & 3u) == 0u;
         const int t_begin = (c - f * a.chunks_per_frame) * VI_TILES_PER_BLOCK + (int)warp * VI_TILES_PER_WARP;
         unsigned int head = 0, count = 0;                           // warp-uniform ring state
         auto batch = [&](bool active, unsigned int dbits, unsigned int uv) {
@@ -448,17 +449,8 @@ export_voxel_kernel(ExportArgs a) {
             unsigned int rgb = 0u;
             if (active && job.rgb) {
                 const unsigned int off = 3u * (unsigned int)(v * W + u);
-                if (rgb_words) {
-                    // the pixel's three bytes from one or two aligned 32-bit loads (half the requests of three byte loads)
-                    const unsigned int* wp = reinterpret_cast<const unsigned int*>(job.rgb + (off & ~3u));
-                    const unsigned int sh = (off & 3u) * 8u;
-                    rgb = __ldg(wp) >> sh;
-                    if (sh > 8u) rgb |= __ldg(wp + 1) << (32u - sh);
-                    rgb &= 0xFFFFFFu;
-                } else {
-                    const uint8_t* p = job.rgb + off;
-                    rgb = (unsigned int)p[0] | ((unsigned int)p[1] << 8) | ((unsigned int)p[2] << 16);
-                }
+                const uint8_t* p = job.rgb + off;
+                rgb = (unsigned int)p[0] | ((unsigned int)p[1] << 8) | ((unsigned int)p[2] << 16);
             }
             // K1 fast path (unproject_pixel<DA3S_UNPROJ_FAST> with the composed float32 transform)
             float x, y;
@@ -648,7 +640,13 @@ __device__ __forceinline__ int vox_nth_slot(const unsigned int* s_word, const un
     return w * 32 + (int)pos;
 }
 
-__global__ void __launch_bounds__(VC_THREADS)
+#ifndef VE_Q
+#define VE_Q 4                              // dense rounds (32 records each) a warp has in flight
+#endif
+#ifndef VE_MIN_BLOCKS
+#define VE_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(VC_THREADS, VE_MIN_BLOCKS)
 voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
                   const unsigned long long* __restrict__ warp_offsets, const unsigned int* __restrict__ warp_counts,
                   float voxel, long long max_voxels,
@@ -677,12 +675,12 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
     const unsigned int total = __shfl_sync(0xffffffffu, incl, VC_ROUNDS - 1);
     if (lane < VC_ROUNDS) { s_word[warp][lane] = my_word; s_excl[warp][lane] = incl - my_cnt; bm[lane] = 0u; }
     __syncwarp();
-    for (unsigned int r0 = 0; r0 < total; r0 += 128u) {          // 4 dense rounds at a time: their record loads overlap
-        ulonglong2 r01[4], r23[4], r45[4];                        // (key, sum_x), (sum_y, sum_z), ((n, sum_r), (sum_g, sum_b))
-        unsigned long long* recs[4];
-        bool occ[4];
+    for (unsigned int r0 = 0; r0 < total; r0 += 32u * VE_Q) {     // VE_Q dense rounds at a time: their record loads overlap
+        ulonglong2 r01[VE_Q], r23[VE_Q], r45[VE_Q];                        // (key, sum_x), (sum_y, sum_z), ((n, sum_r), (sum_g, sum_b))
+        unsigned long long* recs[VE_Q];
+        bool occ[VE_Q];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < VE_Q; ++q) {
             const unsigned int rank = r0 + 32u * q + lane;
             occ[q] = rank < total;
             if (occ[q]) {
@@ -694,7 +692,7 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < VE_Q; ++q) {
             if (!occ[q]) continue;
             const unsigned long long o = out0 + r0 + 32u * q + lane;
             if ((long long)o >= max_voxels) continue;
@@ -726,7 +724,7 @@ voxel_emit_kernel(unsigned long long* __restrict__ acc, long long slots,
         // key resets LAST, when the loads above have long returned (a store to a sector whose fill is still in flight
         // stalls behind it); the record itself is rewritten by the next claimer (vox_commit)
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < VE_Q; ++q)
             if (occ[q]) *recs[q] = VOX_EMPTY;
     }
 }
