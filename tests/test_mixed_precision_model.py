@@ -1,13 +1,17 @@
 """Error model of the default (mixed-precision) IRLS kernel, on the CPU.
 
 `pair_moments_mixed_kernel` (da3slam_b200/csrc/pair_align.cu) accumulates the 22 weighted moments of a pair in float32
-FMA arithmetic on points centred at a per-frame pivot, in micro-batches of 16 correspondences per thread that are flushed
-into float64 accumulators; tiles are combined, un-pivoted and moved to world coordinates in float64.  The reference is
-float64 throughout (utils/align.py:14-40, :169-211).  This test restates that arithmetic in numpy — same pivot rule, same
-micro-batch membership (thread t of 128 takes the float4 groups t, t + 128, ... of a 16384-pixel tile, four groups per
-flush), same operation order inside a micro-batch, float32 Huber branch on rr > delta^2 — runs the whole IRLS loop with
-it, and bounds its distance to the float64 oracle: <= 1e-7 relative on (s, R, t) where the contract is 1e-6.  The GPU
-tests (tests/test_gpu_baseline_shapes.py) then check the real kernel against the same oracle at 518^2 and 1036^2."""
+FMA arithmetic, in micro-batches of 16 correspondences per thread that are flushed into float64 accumulators; tiles are
+combined, un-pivoted and moved to world coordinates in float64.  The reference is float64 throughout
+(utils/align.py:14-40, :169-211).  This test restates that arithmetic in numpy in both forms the kernel has —
+  scalar: points by SPEC 1, centred at the frame-centre correspondence (all three coordinates);
+  packed (default for even W): points from the pixel's ray, x = d (a, b, 1) with a = (u - cu) * (1/fu) rounded once,
+          only the depth coordinate pivoted, the even and the odd pixel of a pair in separate float32 accumulators
+          (the two halves of a packed register) that are added just before the float64 flush —
+with the same micro-batch membership (thread t of 128 takes the float4 groups t, t + 128, ... of a 16384-pixel tile,
+four groups per flush), the same operation order inside a micro-batch and the float32 Huber branch on rr > delta^2; it runs
+the whole IRLS loop and bounds its distance to the float64 oracle: <= 1e-7 relative on (s, R, t) where the contract is
+1e-6.  The GPU tests (tests/test_gpu_baseline_shapes.py) check the real kernel against the same oracle at 518^2 and 1036^2."""
 import numpy as np
 import pytest
 
@@ -40,13 +44,22 @@ def microbatch_order(n_pix):
     return pix.reshape(len(grp), 16)
 
 
-def mixed_moments(xf, yf, w32, pivot_x, pivot_y, order):
+def mixed_moments(xf, yf, w32, pivot_x, pivot_y, order, packed=False):
     """Raw float64 camera-frame moments (25) the kernel would produce for one frame."""
     pad_x = np.vstack([xf, np.zeros((1, 3), F32)])
     pad_y = np.vstack([yf, np.zeros((1, 3), F32)])
     pad_w = np.concatenate([w32, np.zeros(1, F32)])
+    if packed:                                                        # even / odd pixel of a pair: separate accumulators
+        halves = [mixed_moments_f32(pad_x, pad_y, pad_w, pivot_x, pivot_y, order[:, par::2]) for par in (0, 1)]
+        acc = (halves[0] + halves[1]).astype(F32)
+    else:
+        acc = mixed_moments_f32(pad_x, pad_y, pad_w, pivot_x, pivot_y, order)
+    return unpivot(acc.astype(np.float64).sum(0), pivot_x, pivot_y)
+
+
+def mixed_moments_f32(pad_x, pad_y, pad_w, pivot_x, pivot_y, order):
     acc = np.zeros((order.shape[0], 22), F32)
-    for i in range(16):
+    for i in range(order.shape[1]):
         idx = order[:, i]                                             # -1 -> the zero-weight pad entry
         wi = pad_w[idx]
         xc = (pad_x[idx] - pivot_x).astype(F32)
@@ -63,7 +76,11 @@ def mixed_moments(xf, yf, w32, pivot_x, pivot_y, order):
         for a in range(3):
             for b in range(a, 3):
                 acc[:, c] = fma32(acc[:, c], wx[:, a], xc[:, b]); c += 1
-    m = acc.astype(np.float64).sum(0)                                 # float64 flush + tile combination
+    return acc
+
+
+def unpivot(m, pivot_x, pivot_y):
+    """float64 flush + tile combination happened in `m`; undo the pivot (exact polynomial identities in float64)."""
     S0, Sx, Sy, Syx, q = m[0], m[1:4], m[4:7], m[7:16].reshape(3, 3), m[16:22]
     Sxx = np.array([[q[0], q[1], q[2]], [q[1], q[3], q[4]], [q[2], q[4], q[5]]])
     px, py = pivot_x.astype(np.float64), pivot_y.astype(np.float64)   # un-pivot: exact polynomial identities in float64
@@ -105,12 +122,26 @@ def solve(m, wscale):
     return s, R, my - s * R @ mx
 
 
-def mixed_irls(corr, H, W, delta=1.0, max_it=20, tol=1e-6):
+def ray_points(sub, frame, H, W):
+    """packed form: x = d * (a, b, 1), a = (u - cu) * (1/fu), b = (v - cv) * (1/fv), every operation rounded once."""
+    K = np.asarray(sub["intrinsics"][frame], F32)
+    d = np.asarray(sub["depth"][frame], F32)
+    a = ((np.arange(W, dtype=F32) - K[0, 2]) * (F32(1) / K[0, 0])).astype(F32)[None, :]
+    b = ((np.arange(H, dtype=F32) - K[1, 2]) * (F32(1) / K[1, 1])).astype(F32)[:, None]
+    return np.stack([(d * a).astype(F32), (d * b).astype(F32), d], axis=-1).reshape(-1, 3)
+
+
+def mixed_irls(corr, H, W, delta=1.0, max_it=20, tol=1e-6, packed_points=None):
     xf, yf, c, mask = corr["xf"], corr["yf"], corr["c"], corr["mask"]
+    packed = packed_points is not None
+    if packed:
+        xf, yf = packed_points
     order = microbatch_order(H * W)
     centre = (H // 2) * W + W // 2                                      # the pivot: the correspondence at the frame's centre pixel
     px = np.where(np.isfinite(xf[centre]), xf[centre], 0).astype(F32)
     py = np.where(np.isfinite(yf[centre]), yf[centre], 0).astype(F32)
+    if packed:
+        px[:2] = 0; py[:2] = 0                                          # depth coordinate only
     Rx, tx = sp.c2w_closed_form(corr["EB"]); Ry, ty = sp.c2w_closed_form(corr["EA"])
     xs = np.where(mask[:, None], xf, F32(0)); ys = np.where(mask[:, None], yf, F32(0))
     s, R, t = 1.0, np.eye(3), np.zeros(3)
@@ -128,7 +159,7 @@ def mixed_irls(corr, H, W, delta=1.0, max_it=20, tol=1e-6):
         big = rr > F32(delta * delta)                                  # the float32 branch of the kernel
         hub = (F32(delta) / np.sqrt(np.maximum(rr, F32(1e-30)))).astype(F32)
         w = np.where(big, (w * hub).astype(F32), w)
-        m = to_world(mixed_moments(xs, ys, w, px, py, order), corr["EB"], corr["EA"])
+        m = to_world(mixed_moments(xs, ys, w, px, py, order, packed), corr["EB"], corr["EA"])
         s_n, R_n, t_n = solve(m, float(w.max()) + 1e-8)
         change = abs(s_n - s) + np.linalg.norm(R_n - R) + np.linalg.norm(t_n - t)
         s, R, t = s_n, R_n, t_n
@@ -142,9 +173,10 @@ def test_mixed_precision_irls_stays_far_inside_the_contract(H, W, seed, outliers
     A, B, _ = synth.make_pair(H, W, frames=2, seed=seed, outlier_ratio=outliers)
     corr = sp.pair_correspondences(A, B, 1, True)
     s0, R0, t0, info = sp.irls_dense(corr["x"], corr["y"], corr["c"], corr["mask"])
-    s, R, t, iters = mixed_irls(corr, H, W)
-    assert iters == info["iters"]
-    assert abs(s - s0) <= 1e-7 * s0 and np.abs(R - R0).max() <= 1e-7 and np.abs(t - t0).max() <= 1e-7 * max(1.0, np.abs(t0).max())
+    for points in (None, (ray_points(B, 0, H, W), ray_points(A, -1, H, W))):     # scalar form, packed form
+        s, R, t, iters = mixed_irls(corr, H, W, packed_points=points)
+        assert iters == info["iters"]
+        assert abs(s - s0) <= 1e-7 * s0 and np.abs(R - R0).max() <= 1e-7 and np.abs(t - t0).max() <= 1e-7 * max(1.0, np.abs(t0).max())
 
 
 def test_microbatch_membership():
