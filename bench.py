@@ -46,20 +46,21 @@ WORKLOADS = {
                     table_slots=1 << 25, max_voxels=1 << 24, voxel=0.02, desc="300 frames, 19 submaps x 16 x 518x518, 18 pairs"),
     # configs[2]: 2000 frames, 32-frame submaps, RANSAC 1024 hypotheses (make_image_chunks -> 65 submaps / 64 pairs)
     "seq2000": dict(n_submaps=65, frames=32, H=518, W=518, overlap=1, n_hyp=1024, outlier=0.3, export=True,
-                    table_slots=1 << 28, max_voxels=1 << 27, voxel=0.02,
+                    table_slots=1 << 27, max_voxels=1 << 26, voxel=0.02,
                     desc="2000 frames, 65 submaps x 32 x 518x518, 64 pairs, RANSAC 1024"),
     # configs[3]: 512 independent loop-candidate pairs (2-frame submaps, so every pair reads distinct frames)
     "loop512": dict(n_submaps=513, frames=2, H=518, W=518, overlap=1, n_hyp=0, outlier=0.0, export=False,
                     table_slots=0, max_voxels=0, voxel=0.02, desc="512 submap pairs, 518x518, 1 overlap frame, alignment only"),
     # configs[4]: 1036x1036, 64-frame submaps + global voxel map
     "hires": dict(n_submaps=8, frames=64, H=1036, W=1036, overlap=1, n_hyp=0, outlier=0.0, export=True,
-                  table_slots=1 << 24, max_voxels=1 << 23, voxel=0.02, desc="8 submaps x 64 x 1036x1036, 7 pairs, voxel map"),
+                  table_slots=1 << 25, max_voxels=1 << 24, voxel=0.02, desc="8 submaps x 64 x 1036x1036, 7 pairs, voxel map"),
     # tiny case for CI / smoke runs of this script
     "tiny": dict(n_submaps=4, frames=4, H=64, W=80, overlap=1, n_hyp=16, outlier=0.1, export=True,
                  table_slots=1 << 16, max_voxels=1 << 16, voxel=0.05, desc="4 submaps x 4 x 64x80"),
 }
 RANSAC_THR = 0.02
 CONF_PERCENTILE = 65.0          # viewer.py:86-88 default slider value
+SUBMAP_SCALE = (0.8, 1.25)      # every synthetic submap's own metric scale (synth.make_sequence_device abs_scale)
 METRIC, UNIT = "submap_pairs_aligned_per_sec", "submap-pairs/s"
 
 
@@ -74,6 +75,7 @@ def config_of(name, w, world, extra=None):
            "conf_percentile": CONF_PERCENTILE if w["export"] else None,
            "irls": "huber delta=1.0, <=20 it, tol 1e-6 (utils/align.py defaults)",
            "seeds": "1234 + 1000 * rank (every rank its own scenes)",
+           "submap_scale": f"every submap at its own scale, uniform in [{SUBMAP_SCALE[0]}, {SUBMAP_SCALE[1]}]",
            "l2": f"inputs {inputs_mb:.0f} MB (depth + conf) per GPU vs 126 MB L2; no explicit flush",
            "parallelism": f"{world} rank(s), one sequence per rank (weak scaling), Sim(3) rows all_gather only"}
     if extra:
@@ -374,13 +376,14 @@ def main_section(args, w, rank, world, dev, local, timer, numa_node):
     """The headline measurement: one full sequence per rank, resident in HBM (value) and from pinned host memory (e2e)."""
     import torch
     import torch.distributed as dist
+    from da3slam_b200 import _lib as L
     from da3slam_b200 import ops, synth
     from da3slam_b200.pipeline import DeviceSubmap, SequencePlan, SequenceStream
     from da3slam_b200.sharding import RowExchange
 
-    seed = 1234 + 1000 * rank
+    seed = 1234 + 1000 * (rank if args.scene_of_rank is None else args.scene_of_rank)
     subs, gt = synth.make_sequence_device(w["n_submaps"], w["frames"], w["H"], w["W"], w["overlap"], seed=seed,
-                                          outlier_ratio=w["outlier"], with_images=w["export"], device=dev)
+                                          outlier_ratio=w["outlier"], with_images=w["export"], device=dev, abs_scale=SUBMAP_SCALE)
     dsubs = [DeviceSubmap.from_prediction(s, dev) for s in subs]
     n_pairs = w["n_submaps"] - 1
     M = w["overlap"] * w["H"] * w["W"]
@@ -417,9 +420,19 @@ def main_section(args, w, rank, world, dev, local, timer, numa_node):
     del check
 
     clocks = ClockSampler(local) if rank == 0 else None
+    for c in plan.contexts():
+        c.kernel_timers(True)                           # event pairs around the four big kernels, read after the timed region
     launches0 = plan.launches
     ms_per_step, stages = timer.run(run_step, args.steps, 0, want_events=True)
     launches = plan.launches - launches0
+    kernel_ms = {}
+    for c in plan.contexts():
+        for which in L.TIMED_NAMES:
+            t_ms, n_t, n_l, wk = c.kernel_time(which)
+            if n_l:
+                a_ms, a_t, a_n, a_w = kernel_ms.get(which, (0.0, 0, 0, 0.0))
+                kernel_ms[which] = (a_ms + t_ms, a_t + n_t, a_n + n_l, a_w + wk)
+        c.kernel_timers(False)
     clock_info = clocks.stop() if clocks else None
     per_rank = None
     if world > 1:
@@ -473,62 +486,76 @@ def main_section(args, w, rank, world, dev, local, timer, numa_node):
     if rank != 0:
         return None
 
-    # ---- roofline of the dominant stage ----
+    # ---- rooflines: every big kernel against the resource that bounds it; `roofline` = the one with the largest share ----
     peak, peak_src = measured_peaks()
     px_export = sum((w["frames"] - (w["overlap"] if k > 0 else 0)) for k in range(w["n_submaps"])) * w["H"] * w["W"] if w["export"] else 0
-    single = {}
-    if w["export"]:
-        single["export_fused"] = ("export_voxel_kernel (unproject + Sim(3) + filter + voxel insert)",
-                                  (8.0 + 3.0 * (1.0 - CONF_PERCENTILE / 100.0)) * px_export, 1,
-                                  "8 B/pixel read (depth + conf) + 3 B rgb per kept point; hash-table traffic is not algorithmic "
-                                  "(see roofline.traffic)")
-        single["voxel_compact"] = ("voxel_count/scan/emit_kernel", (8.0 + 64.0 + 27.0) * n_vox, 3,
-                                   "per voxel: 8 B key + 64 B record read, 27 B written (xyz 12, rgb 3, count 4, key 8)")
     passes = float(np.sum(iters))
-    align_bytes = (passes * 16.0 + 3 * 8.0) * M + (w["n_hyp"] > 0) * n_pairs * 16.0 * M
-    single["align"] = ("select + [ransac_score_kernel] + pair_moments_mixed_kernel", align_bytes, 1,
-                       "16 B/correspondence per IRLS pass x executed passes + 8 B x 3 select passes [+ 16 B RANSAC pass]; "
-                       "with RANSAC the stage is FP32-ALU bound (n_hyp x 15 flop per correspondence), see roofline_fp32")
-    dom = max(single, key=lambda k: stages.get(k, 0.0))
-    kname, bytes_per_step, n_launch, note = single[dom]
-    dur_ms = stages.get(dom, 0.0)
-    achieved = bytes_per_step / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else 0.0
-    traffic, traffic_src = load_traffic(args.workload, dom)
-    roofline = {"bound": "hbm", "kernel": kname, "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_per_step / n_launch, "launches_per_step": n_launch,
-                "avg_launch_ms": dur_ms / n_launch, "stage_share_of_step": dur_ms / ms_per_step, "note": note}
-    per_stage = {}
-    for k, (kn, b, nl, _) in single.items():
-        if stages.get(k, 0) > 0.02:
-            per_stage[k] = {"ms": stages[k], "GB/s": b / (stages[k] * 1e-3) / 1e9, "frac_of_peak": b / (stages[k] * 1e-3) / 1e9 / peak}
-    roofline_fp32 = None
-    if w["n_hyp"] > 0:
-        # RANSAC scoring, oracle/SPEC.md 4: per (correspondence, hypothesis) 12 FMA + 3 add = 27 flop.  `spec` counts every
-        # pair the specification scores; the kernel skips invalid hypotheses and masked correspondences (they score 0 by
-        # definition), so the EXECUTED rate is lower — its pipe utilisation comes from ncu (profiles/r2_traffic.json)
-        flops = 27.0 * M * n_pairs * w["n_hyp"]
-        fp32_peak = ops.fp32_peak_tflops(dev)
-        pipe, pipe_src = load_traffic(args.workload, "ransac_fp32_pipe")
-        roofline_fp32 = {"bound": "fp32", "kernel": "ransac_score_kernel", "spec_flops_per_step": flops, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "peak_source": "measured live: da3s_measure_fp32_peak (packed FFMA2 chains, all SMs)",
-                         "spec_rate_over_align_stage": flops / (stages.get("align", 0.0) * 1e-3) / 1e12 if stages.get("align") else None,
-                         "fma_pipe_busy_frac_ncu": pipe, "fma_pipe_source": pipe_src,
-                         "note": "spec rate = work the specification defines (all hypotheses x all correspondences) / whole align stage; "
-                                 "the kernel executes ~0.66 of it (valid hypotheses x kept correspondences)"}
+    kept = 1.0 - CONF_PERCENTILE / 100.0
+    # algorithmic work PER STEP of each timed kernel: bytes for the HBM-bound ones, flops for the scoring
+    work = {
+        L.TIMED_IRLS: ("hbm", passes * 16.0 * M, "16 B per correspondence (depth + conf of both overlap frames) x executed IRLS passes, summed over the pairs"),
+        L.TIMED_EXPORT_VOXEL: ("hbm", (8.0 + 3.0 * kept) * px_export,
+                               "8 B/pixel read (depth + conf) + 3 B rgb per kept point; hash-table traffic is not algorithmic (see traffic)"),
+        L.TIMED_VOXEL_EMIT: ("hbm", (64.0 + 27.0) * n_vox, "per voxel: 64 B record read, 27 B written (xyz 12, rgb 3, count 4, key 8)"),
+        # oracle/SPEC.md 4: per (correspondence, hypothesis) 12 FMA + 3 add = 27 flop, over EVERY hypothesis and correspondence
+        # the specification scores; the kernel skips invalid hypotheses and masked correspondences (they score 0 by definition)
+        L.TIMED_RANSAC_SCORE: ("fp32", 27.0 * M * n_pairs * w["n_hyp"],
+                               "27 flop per (hypothesis, correspondence) evaluation x the evaluations the kernel EXECUTED (valid hypotheses x "
+                               "correspondences that pass the joint mask, counted on the device); invalid hypotheses and masked "
+                               "correspondences score 0 by definition (oracle/SPEC.md 4) and are not algorithmic work"),
+    }
+    fp32_peak = ops.fp32_peak_tflops(dev) if w["n_hyp"] > 0 else None
+    kernels = {}
+    for which, (bound, amount, note) in work.items():
+        sum_ms, n_t, n_l, executed = kernel_ms.get(which, (0.0, 0, 0, 0.0))
+        if n_t == 0 or amount <= 0:
+            continue
+        if which == L.TIMED_RANSAC_SCORE:
+            spec_flops, amount = amount, 27.0 * executed / args.steps       # what the kernel evaluated, counted on the device
+        per_step = n_l / float(args.steps)
+        avg_ms = sum_ms / n_t
+        name = L.TIMED_NAMES[which]
+        traffic, traffic_src = load_traffic(args.workload, name)
+        if bound == "hbm":
+            ach, pk, unit, pk_src = amount / per_step / (avg_ms * 1e-3) / 1e9, peak, "GB/s", peak_src
+        else:
+            ach, pk, unit = amount / per_step / (avg_ms * 1e-3) / 1e12, fp32_peak, "TFLOP/s"
+            pk_src = "measured live: da3s_measure_fp32_peak (packed FFMA2 chains on all SMs); CUDA-core float32 FMA — the bit-exact fmaf specification has no tensor-core form"
+        kernels[name] = {"bound": bound, "kernel": name, "achieved": ach, "peak": pk, "unit": unit, "frac": ach / pk,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_src,
+                         ("algorithmic_bytes_per_launch" if bound == "hbm" else "algorithmic_flops_per_launch"): amount / per_step,
+                         "launches_per_step": per_step, "avg_launch_ms": avg_ms, "timing": "CUDA event pair around each launch on the "
+                         "launching stream, inside the timed region (da3s_kernel_time), averaged over the timed steps",
+                         "share_of_step": avg_ms * per_step / ms_per_step, "note": note}
+        if which == L.TIMED_RANSAC_SCORE:
+            pipe, pipe_src = load_traffic(args.workload, "ransac_fp32_pipe")
+            kernels[name].update(fma_pipe_busy_frac_ncu=pipe, fma_pipe_source=pipe_src, spec_flops_per_launch=spec_flops / per_step,
+                                 executed_over_spec=amount / spec_flops,
+                                 instruction_mix_ceiling="54 flop per 16 packed FMA-pipe instructions (12 FFMA2/FMUL2 + 4 FADD2) vs 64 for pure "
+                                                         "FFMA2: at most 0.84 of the peak (profiles/r2_fp32_pipes.txt: 52.8 TFLOP/s measured for this mix)")
+    roofline = max(kernels.values(), key=lambda k: k["share_of_step"]) if kernels else None
+    hbm_only = [k for k in kernels.values() if k["bound"] == "hbm"]
+    roofline_hbm = max(hbm_only, key=lambda k: k["share_of_step"]) if hbm_only else None
+    stage_bytes = {"align": (passes * 16.0 + 3 * 8.0) * M + (w["n_hyp"] > 0) * n_pairs * 16.0 * M}
+    if w["export"]:
+        stage_bytes["export_fused"] = work[L.TIMED_EXPORT_VOXEL][1]
+        stage_bytes["voxel_compact"] = (8.0 + 64.0 + 27.0) * n_vox
+    per_stage = {k: {"ms": stages[k], "GB/s": b / (stages[k] * 1e-3) / 1e9, "frac_of_peak": b / (stages[k] * 1e-3) / 1e9 / peak}
+                 for k, b in stage_bytes.items() if stages.get(k, 0) > 0.02}
 
     return {
         "metric": METRIC, "value": world * n_pairs / (ms_per_step * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": config_of(args.workload, w, world, {"numa_node_rank0": numa_node}),
+        "config": config_of(args.workload, w, world), "numa_node_rank0": numa_node,
         "points_per_sec": world * px_export / (ms_per_step * 1e-3) if w["export"] else None,
         "pixels_per_step_per_gpu": px_export, "voxels_out": n_vox,
         "timed_region_s": ms_per_step * args.steps * 1e-3,
         "stages_ms": stages, "per_rank": per_rank, "stage_bandwidth": per_stage,
         "accuracy": {"max_rel_scale_error_vs_ground_truth": err_s, "irls_iterations_mean": float(np.mean(iters)),
                      "pairs_ok": int(ok.sum())},
-        "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_fp32": roofline_fp32,
+        "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm,
+        "kernels": kernels,
     }
 
 
@@ -594,7 +621,8 @@ def global_map_section(args, rank, world, dev, timer):
     a, b = sh["a"], sh["b"]
     # every rank draws the whole sequence (same seed) and keeps its own submaps + the halo submap's overlap frames
     local = []
-    subs, _ = synth.make_sequence_device(n, w["frames"], w["H"], w["W"], w["overlap"], seed=555, with_images=True, device=dev)
+    subs, _ = synth.make_sequence_device(n, w["frames"], w["H"], w["W"], w["overlap"], seed=555, with_images=True, device=dev,
+                                         abs_scale=SUBMAP_SCALE)
     for k in range(a, b + (1 if sh["halo"] else 0)):
         local.append(DeviceSubmap.from_prediction(subs[k], dev))
     del subs
@@ -679,6 +707,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sections", action="store_true", help="skip the loop512_sharded / hires_global_map measurements")
     ap.add_argument("--cpu-workers", type=int, default=None)
+    ap.add_argument("--scene-of-rank", type=int, default=None, help="N=1 only: run rank R's scenes (per-rank load check)")
     ap.add_argument("--table-slots-log2", type=int, default=None, help="override the workload's voxel table size (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -707,7 +736,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT,
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["step_s"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-                "config": config_of(args.workload, w, world, {"numa_node_rank0": None}),
+                "config": config_of(args.workload, w, world),
                 "cpu_baseline": base,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))

@@ -83,6 +83,8 @@ SIGNATURES = {
     "da3s_launch_count": (_ULL, [_P]),
     "da3s_enable_peer_access": (_I, [_P, _I]),
     "da3s_measure_fp32_peak": (_I, [_P, _I, C.POINTER(_D), _P]),
+    "da3s_kernel_timers": (_I, [_P, _I]),
+    "da3s_kernel_time": (_I, [_P, _I, C.POINTER(_D), C.POINTER(_I), C.POINTER(_I), C.POINTER(_D)]),
     "da3s_build_cams": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "da3s_unproject_filter": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _F, _F, _P, _P, _P, _P, _P]),
     "da3s_unproject_filter_jobs": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
@@ -154,3 +156,8 @@ def default_opts(**kw) -> AlignOpts:
 
 
 NAN = math.nan
+
+# da3s_kernel_time ids (include/da3s.h)
+TIMED_RANSAC_SCORE, TIMED_IRLS, TIMED_EXPORT_VOXEL, TIMED_VOXEL_EMIT = 0, 1, 2, 3
+TIMED_NAMES = {TIMED_RANSAC_SCORE: "ransac_score_kernel", TIMED_IRLS: "pair_moments_mixed_kernel",
+               TIMED_EXPORT_VOXEL: "export_voxel_kernel", TIMED_VOXEL_EMIT: "voxel_emit_kernel"}

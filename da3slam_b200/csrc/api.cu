@@ -44,12 +44,56 @@ extern "C" int da3s_destroy(da3s_ctx* ctx) {
     if (!ctx) return DA3S_EINVAL;
     cudaSetDevice(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
+    for (int k = 0; k < DA3S_TIMED_KERNELS; ++k)
+        for (int i = 0; i < DA3S_TIMER_RING; ++i)
+            for (int j = 0; j < 2; ++j) if (ctx->prof_ev[k][i][j]) cudaEventDestroy(ctx->prof_ev[k][i][j]);
+    if (ctx->prof_work) cudaFree(ctx->prof_work);
     delete ctx;
     return DA3S_OK;
 }
 
 extern "C" int da3s_last_cuda_error(const da3s_ctx* ctx) { return ctx ? ctx->last_cuda_error : 0; }
 extern "C" unsigned long long da3s_launch_count(const da3s_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+extern "C" int da3s_kernel_timers(da3s_ctx* ctx, int on) {
+    if (!ctx) return DA3S_EINVAL;
+    cudaSetDevice(ctx->device);
+    if (on && !ctx->prof_ev[0][0][0]) {
+        for (int k = 0; k < DA3S_TIMED_KERNELS; ++k)
+            for (int i = 0; i < DA3S_TIMER_RING; ++i)
+                for (int j = 0; j < 2; ++j) DA3S_CHECK_CUDA(ctx, cudaEventCreate(&ctx->prof_ev[k][i][j]));
+        DA3S_CHECK_CUDA(ctx, cudaMalloc((void**)&ctx->prof_work, sizeof(unsigned long long) * DA3S_TIMED_KERNELS));
+    }
+    if (ctx->prof_work) DA3S_CHECK_CUDA(ctx, cudaMemset(ctx->prof_work, 0, sizeof(unsigned long long) * DA3S_TIMED_KERNELS));
+    for (int k = 0; k < DA3S_TIMED_KERNELS; ++k) ctx->prof_n[k] = 0;
+    ctx->prof_on = on != 0;
+    return DA3S_OK;
+}
+
+extern "C" int da3s_kernel_time(da3s_ctx* ctx, int which, double* sum_ms_out, int* timed_out, int* launches_out, double* work_out) {
+    if (!ctx || which < 0 || which >= DA3S_TIMED_KERNELS || !sum_ms_out || !timed_out || !launches_out) return DA3S_EINVAL;
+    *sum_ms_out = 0.0; *timed_out = 0; *launches_out = 0;
+    if (work_out) *work_out = 0.0;
+    if (!ctx->prof_ev[0][0][0]) return DA3S_OK;
+    const unsigned int n = ctx->prof_n[which], kept = n < DA3S_TIMER_RING ? n : DA3S_TIMER_RING;
+    for (unsigned int i = 0; i < kept; ++i) {
+        const unsigned int e = (n - 1 - i) % DA3S_TIMER_RING;
+        if (i == 0) DA3S_CHECK_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[which][e][1]));
+        float ms = 0.f;
+        DA3S_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[which][e][0], ctx->prof_ev[which][e][1]));
+        *sum_ms_out += ms;
+    }
+    *timed_out = (int)kept;
+    *launches_out = (int)n;
+    if (work_out && ctx->prof_work && n) {      // the last launch has completed (event synchronised above)
+        unsigned long long w = 0;
+        DA3S_CHECK_CUDA(ctx, cudaMemcpy(&w, ctx->prof_work + which, sizeof(w), cudaMemcpyDeviceToHost));
+        DA3S_CHECK_CUDA(ctx, cudaMemset(ctx->prof_work + which, 0, sizeof(w)));
+        *work_out = (double)w;
+    }
+    ctx->prof_n[which] = 0;
+    return DA3S_OK;
+}
 
 extern "C" int da3s_enable_peer_access(da3s_ctx* ctx, int peer_device) {
     if (!ctx || peer_device < 0) return DA3S_EINVAL;

@@ -27,7 +27,20 @@ struct da3s_ctx {
     unsigned int* vox_groups;           // per 512-slot group: occupied count [n] u32, then output offset [n] u64
     size_t vox_bytes;
     bool vox_clean, vox_active;
+    // per-kernel timers (da3s_kernel_timers / da3s_kernel_time): event pairs around the named launches, a ring per kernel
+    bool prof_on;
+    cudaEvent_t prof_ev[DA3S_TIMED_KERNELS][DA3S_TIMER_RING][2];
+    unsigned int prof_n[DA3S_TIMED_KERNELS];
+    unsigned long long* prof_work;      // device [DA3S_TIMED_KERNELS]: work units the timed kernels report (RANSAC: evaluations)
 };
+
+// Event pair around one launch of a timed kernel (no-ops unless da3s_kernel_timers(ctx, 1) was called)
+static inline void prof_begin(da3s_ctx* c, int which, cudaStream_t st) {
+    if (c->prof_on) cudaEventRecord(c->prof_ev[which][c->prof_n[which] % DA3S_TIMER_RING][0], st);
+}
+static inline void prof_end(da3s_ctx* c, int which, cudaStream_t st) {
+    if (c->prof_on) { cudaEventRecord(c->prof_ev[which][c->prof_n[which] % DA3S_TIMER_RING][1], st); c->prof_n[which]++; }
+}
 
 #define DA3S_CHECK_CUDA(ctx, expr)                                   \
     do {                                                             \

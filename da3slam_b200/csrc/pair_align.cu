@@ -48,7 +48,10 @@ struct PairArgs {
     unsigned int* tickets;                  // [n_pairs]
     int* n_active;                          // pairs active when the IRLS kernel starts (constant while it runs)
     int* done_count;                        // [max_iterations] pairs finished during pass p (persistent kernel's exit test)
-    unsigned long long* work_counter;       // [max_iterations] next (pair, tile) item of pass p
+    unsigned long long* work_counter;       // [max_iterations] next (pair, tile) item of pass p ([0]: the queue's item ticket)
+    int* q_pair;                            // [q_cap] IRLS work queue: entry e = a pair whose next pass may run (-1: not yet published)
+    unsigned int* q_reserve;                // next free queue entry
+    int q_cap;
     double huber_delta, tol;
     float delta_f, delta2_f, W_f;           // float32 copies read straight from the constant bank in the inner loop
     int max_iterations, min_points, precise;
@@ -364,6 +367,52 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+#ifndef PM_QUEUE
+#define PM_QUEUE 1                          // 1: per-pair dependencies through a work queue (below); 0: grid-wide barrier between passes
+#endif
+
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// IRLS work queue.  An ENTRY is a pair whose next pass may run (its residual map is published); entry e stands for the
+// items e * n_tiles .. (e + 1) * n_tiles - 1 of the global item ticket.  The pairs active at the start fill the first
+// entries (this kernel, pair order); the block that solves a pair appends it again unless the pair has finished.
+__global__ void __launch_bounds__(1024)
+pm_queue_init_kernel(PairArgs a) {
+    __shared__ int base_sh;
+    if (threadIdx.x == 0) base_sh = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int base = 0;
+        for (int p0 = 0; p0 < a.n_pairs; p0 += 32) {
+            const int p = p0 + (int)threadIdx.x;
+            const bool act = p < a.n_pairs && a.state[p].done == 0;
+            const unsigned int m = __ballot_sync(0xffffffffu, act);
+            if (act) a.q_pair[base + __popc(m & ((1u << threadIdx.x) - 1u))] = p;
+            base += __popc(m);
+        }
+        if (threadIdx.x == 0) { base_sh = base; *a.q_reserve = (unsigned int)base; *a.n_active = base; a.done_count[0] = 0; a.work_counter[0] = 0ull; }
+    }
+    __syncthreads();
+    for (int e = base_sh + (int)threadIdx.x; e < a.q_cap; e += 1024) a.q_pair[e] = -1;
+}
+
+// thread 0 of a block: the pair of queue entry e, waiting until the entry is published; -1 once every pair has finished
+__device__ __forceinline__ int pm_wait_entry(const PairArgs& a, long long e) {
+    for (;;) {
+        if (e < (long long)a.q_cap) {
+            const int p = ld_acquire_s32(a.q_pair + e);
+            if (p >= 0) return p;
+        }
+        if (*((volatile int*)&a.done_count[0]) >= *((volatile int*)a.n_active)) return -1;      // nothing will be appended any more
+        __nanosleep(200);
+    }
+}
+
 // PERSISTENT: one cooperative launch runs every IRLS iteration.  Blocks stride over the
 // (pair, tile) work items of the pairs that have not converged, the last block of a pair
 // (ticket) solves it, a grid-wide barrier separates iterations, and the kernel ends as soon as
@@ -388,12 +437,36 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     __shared__ bool is_last;
     __shared__ int pair_done;
     __shared__ long long cur_item;
+#if !PM_QUEUE
     cooperative_groups::grid_group grid_g = cooperative_groups::this_grid();
+#endif
     const int n_tiles_all = a.overlap * a.tiles_per_frame;
     const long long n_items = (long long)a.n_pairs * n_tiles_all;
   __shared__ float fcm[32];                         // per-item constants, filled by warp 0 (one value per lane)
   // with few items per block an early request would take work away from idle blocks
   const bool prefetch = n_items >= 4ll * gridDim.x;
+#if PM_QUEUE
+  const int pass = 0;
+  {
+   // dynamic work distribution over the queue's items: the block that happens to solve a pair (serial epilogue) simply
+   // takes fewer tiles.  The NEXT ticket is requested while the current item is processed (the atomic's round trip is
+   // never waited for); a ticket whose entry is not published yet is waited for by thread 0 (pm_wait_entry).
+   __syncthreads();
+   if (threadIdx.x == 0) {
+       const long long it = (long long)atomicAdd(&a.work_counter[0], 1ull);
+       cur_item = it;
+       pair_done = pm_wait_entry(a, it / n_tiles_all);         // here: the item's pair, or -1 (all pairs finished)
+   }
+   __syncthreads();
+   for (;;) {
+    const long long item = cur_item;
+    const int pair = pair_done;
+    if (pair < 0) break;
+    long long next_item = 0;
+    if (prefetch && threadIdx.x == 0) next_item = (long long)atomicAdd(&a.work_counter[0], 1ull);
+   do {
+    const int item_tile = (int)(item % n_tiles_all);
+#else
   for (int pass = 0; pass < max_passes; ++pass) {
    // dynamic work distribution: the block that happens to solve a pair (serial epilogue) simply
    // takes fewer tiles, instead of delaying a fixed share of them.  The NEXT item is requested
@@ -415,6 +488,7 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     const int pair = (int)(item / n_tiles_all);
     const int item_tile = (int)(item - (long long)pair * n_tiles_all);
     if (skip) continue;                             // block-uniform: converged pairs cost nothing
+#endif
     const da3s_pair pr = a.pairs[pair];
     const int frame = item_tile / a.tiles_per_frame;
     const int tile = item_tile - frame * a.tiles_per_frame;
@@ -769,11 +843,29 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     if (threadIdx.x == 0) {
         double mm[MOM_LEN];
         for (int k = 0; k < MOM_LEN; ++k) mm[k] = wmom[k];
-        solve_pair(a, pair, mm, pass);
         a.tickets[pair] = 0;
+        solve_pair(a, pair, mm, pass);              // ends with: fence, state, done_count
+#if PM_QUEUE
+        if (!*((volatile int*)&a.state[pair].done)) {
+            // the pair's next pass may start: its residual map, state and ticket are written; publish the entry
+            __threadfence();
+            const unsigned int e = atomicAdd(a.q_reserve, 1u);
+            if (e < (unsigned int)a.q_cap) st_release_s32(a.q_pair + e, pair);
+        }
+#endif
     }
    } while (0);
     __syncthreads();                                // everyone is done with cur_item and the shared scratch
+#if PM_QUEUE
+    if (threadIdx.x == 0) {
+        if (!prefetch) next_item = (long long)atomicAdd(&a.work_counter[0], 1ull);
+        cur_item = next_item;
+        pair_done = pm_wait_entry(a, next_item / n_tiles_all);
+    }
+    __syncthreads();
+   }   // items
+  }
+#else
     if (threadIdx.x == 0) {
         if (!prefetch) next_item = (long long)atomicAdd(&a.work_counter[pass], 1ull);
         cur_item = next_item;
@@ -789,6 +881,7 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
    for (int q = 0; q <= pass; ++q) active -= *((volatile int*)&a.done_count[q]);
    if (active <= 0) break;
   }    // passes
+#endif
 }
 
 // ---------------------------------------------------------------------------------
@@ -868,6 +961,7 @@ struct RansacArgs {
     const int32_t* sample_idx;
     float* hyp_A; float* hyp_t; uint8_t* hyp_ok; double* hyp_sim3;
     int32_t* counts;
+    unsigned long long* work;       // optional (kernel timers on): += (hypothesis, correspondence) evaluations executed
 };
 
 __device__ __forceinline__ void frame_const_basic(FrameConst& fc, const da3s_pair& pr, int frame, const float* thr,
@@ -1048,6 +1142,7 @@ ransac_score_kernel(RansacArgs a, const float* __restrict__ chyp, const int32_t*
     long long p_end = p_begin + (long long)PA_GROUPS_PER_BLOCK * 4;
     if (p_end > a.P) p_end = a.P;
     const float2 thr2 = make_float2(a.thr2, a.thr2);
+    int n_staged = 0;
     for (long long sb = p_begin; sb < p_end; sb += RS_SUB) {
         // stage the KEPT correspondences of this sub-tile (RS_SUB / RS_THREADS per thread), compacted
 #pragma unroll 2
@@ -1076,6 +1171,7 @@ ransac_score_kernel(RansacArgs a, const float* __restrict__ chyp, const int32_t*
         }
         __syncthreads();
         const int n_here = n_sh;
+        n_staged += n_here;
         if (warp_live) {
 #pragma unroll 8
             for (int i = 0; i < n_here; ++i) {
@@ -1098,6 +1194,8 @@ ransac_score_kernel(RansacArgs a, const float* __restrict__ chyp, const int32_t*
         __syncthreads();
     }
     if (!warp_live) return;
+    if (a.work && threadIdx.x == 0)
+        atomicAdd(a.work, (unsigned long long)n_staged * (unsigned long long)min(RS_HYP_PER_BLOCK, nv - hyp0));
 #pragma unroll
     for (int m = 0; m < RS_HPT; ++m) {
         const int c = (int)((m & 1) ? cnt[m >> 1].y : cnt[m >> 1].x);
@@ -1237,7 +1335,7 @@ static void fill_ransac_args(RansacArgs& r, const da3s_pair* pairs, int n_pairs,
     r.world = world; r.valid_depth = valid_depth; r.n_hyp = n_hyp; r.hyp_base = 0; r.depth_eps = depth_eps;
     r.thr2 = (float)((double)ransac_thr * (double)ransac_thr);
     r.thr = thr; r.dscale = dscale; r.sample_idx = nullptr; r.hyp_A = nullptr; r.hyp_t = nullptr; r.hyp_ok = nullptr;
-    r.hyp_sim3 = nullptr; r.counts = nullptr;
+    r.hyp_sim3 = nullptr; r.counts = nullptr; r.work = nullptr;
 }
 
 extern "C" int da3s_ransac_hypotheses(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
@@ -1269,6 +1367,7 @@ extern "C" int da3s_ransac_score(da3s_ctx* ctx, const da3s_pair* pairs, int n_pa
     RansacArgs r;
     fill_ransac_args(r, pairs, n_pairs, overlap, H, W, P, tpf, world, valid_depth, depth_eps, conf_thr, depth_scale, n_hyp, ransac_thr);
     r.hyp_A = const_cast<float*>(hyp_A); r.hyp_t = const_cast<float*>(hyp_t); r.hyp_ok = const_cast<uint8_t*>(hyp_ok); r.counts = counts;
+    r.work = ctx->prof_on ? ctx->prof_work + DA3S_TIMED_RANSAC_SCORE : nullptr;
     DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_pairs * n_hyp, st));
     size_t save_top = ctx->ws_top;
     WS_ALLOC(ctx, float, chyp, (size_t)n_pairs * n_hyp * 12);
@@ -1279,7 +1378,9 @@ extern "C" int da3s_ransac_score(da3s_ctx* ctx, const da3s_pair* pairs, int n_pa
     const int zs = (n_hyp + RS_HYP_PER_BLOCK - 1) / RS_HYP_PER_BLOCK;
     if (zs > 65535) return DA3S_EINVAL;
     dim3 grid(tpf * overlap, n_pairs, zs);
+    prof_begin(ctx, DA3S_TIMED_RANSAC_SCORE, st);
     ransac_score_kernel<<<grid, RS_THREADS, 0, st>>>(r, chyp, cidx, n_valid);
+    prof_end(ctx, DA3S_TIMED_RANSAC_SCORE, st);
     DA3S_LAUNCH_CHECK(ctx);
     ctx->ws_top = save_top;     // consumed in stream order
     return DA3S_OK;
@@ -1325,6 +1426,9 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     WS_ALLOC(ctx, int, n_active, 1);
     WS_ALLOC(ctx, int, done_count, opts->max_iterations);
     WS_ALLOC(ctx, unsigned long long, work_counter, opts->max_iterations);
+    const int q_cap = n_pairs * (opts->max_iterations + 1);
+    WS_ALLOC(ctx, int, q_pair, (size_t)q_cap);
+    WS_ALLOC(ctx, unsigned int, q_reserve, 1);
 
     int rc = thresholds_impl(ctx, pairs, n_pairs, overlap, H, W, opts, thr, dscale, aux, st);
     if (rc != DA3S_OK) return rc;
@@ -1339,6 +1443,7 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     a.delta_f = (float)opts->huber_delta; a.delta2_f = a.delta_f * a.delta_f; a.W_f = (float)W;
     a.max_iterations = opts->max_iterations; a.min_points = opts->min_points; a.precise = opts->precise;
     a.rows = sim3_rows; a.aux = aux;
+    a.q_pair = q_pair; a.q_reserve = q_reserve; a.q_cap = q_cap;
 
     int threads = 128, blocks = (n_pairs + threads - 1) / threads;
     pair_state_init_kernel<<<blocks, threads, 0, st>>>(a);
@@ -1397,7 +1502,18 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
     if (coop_blocks > items) coop_blocks = items;
     int max_passes = iters;
     void* kargs[] = {(void*)&a, (void*)&max_passes};
+#if PM_QUEUE
+    pm_queue_init_kernel<<<1, 1024, 0, st>>>(a);
+    DA3S_LAUNCH_CHECK(ctx);
+    // no grid-wide barrier inside: an ordinary launch (a block only ever waits for entries that running blocks produce)
+    prof_begin(ctx, DA3S_TIMED_IRLS, st);
+    DA3S_CHECK_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned int)coop_blocks), dim3(PM_THREADS), kargs, ring_bytes, st));
+    prof_end(ctx, DA3S_TIMED_IRLS, st);
+#else
+    prof_begin(ctx, DA3S_TIMED_IRLS, st);
     DA3S_CHECK_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3((unsigned int)coop_blocks), dim3(PM_THREADS), kargs, ring_bytes, st));
+    prof_end(ctx, DA3S_TIMED_IRLS, st);
+#endif
     ctx->launches++;
     return DA3S_OK;
 }
@@ -1569,7 +1685,7 @@ static int points_common(da3s_ctx* ctx, PointsArgs& a, long long count, int hube
     pa.pairs = nullptr; pa.n_pairs = 1; pa.overlap = 1; pa.H = 1; pa.W = 1; pa.P = 1; pa.tiles_per_frame = (int)nb;
     pa.world = 0; pa.valid_depth = 0; pa.huber = huber; pa.variant = variant; pa.depth_eps = 0; pa.thr = nullptr;
     pa.dscale = nullptr; pa.state = state; pa.eff = eff; pa.gate = nullptr; pa.gate_thr2 = 0; pa.partials = partials;
-    pa.tickets = tickets; pa.n_active = nullptr; pa.done_count = nullptr; pa.work_counter = nullptr; pa.huber_delta = delta; pa.tol = tol; pa.max_iterations = max_it; pa.min_points = min_points;
+    pa.tickets = tickets; pa.n_active = nullptr; pa.done_count = nullptr; pa.work_counter = nullptr; pa.q_pair = nullptr; pa.q_reserve = nullptr; pa.q_cap = 0; pa.huber_delta = delta; pa.tol = tol; pa.max_iterations = max_it; pa.min_points = min_points;
     pa.precise = 1;
     pa.rows = row; pa.aux = nullptr;
     a.count = count;

@@ -166,15 +166,14 @@ static VoxQuant make_quant(float voxel) {
 
 // one batch of up to 32 points held in registers: float64 quantisation, in-warp merge of the lanes that fall
 // in the same voxel, then probe / claim / five additions by the merged lanes.  Every lane of the warp calls it.
-#define VOX_SCRATCH 32                      // uint4 per warp: one published point per lane (merge)
+#define VOX_SCRATCH 48                      // uint4 per warp: one published point per lane, 24 bytes each (merge)
 // quantise + merge; returns true on the lanes that carry a merged contribution (key, sums) afterwards
 __device__ __forceinline__ bool vox_merge_batch(bool active, float px, float py, float pz, unsigned int rgb, bool has_rgb, const VoxQuant& qz,
                                                 uint4* __restrict__ gather, unsigned long long& key, unsigned long long& sx,
                                                 unsigned long long& sy, unsigned long long& sz, unsigned long long& cr, unsigned long long& gb) {
     const unsigned int lane = threadIdx.x & 31;
     key = 0; sx = 0; sy = 0; sz = 0; cr = 1ull << 32; gb = 0ull;
-    active = active && is_finite_f(px) && is_finite_f(py) && is_finite_f(pz);
-    if (active) {
+    if (active) {                                                   // NaN / infinite coordinates fail the range test below
         const double qx = vox_div((double)px, qz), qy = vox_div((double)py, qz), qzz = vox_div((double)pz, qz);
         const double kx = floor(qx), ky = floor(qy), kz = floor(qzz);
         active = (fabs(kx) < (double)VOX_BIAS) && (fabs(ky) < (double)VOX_BIAS) && (fabs(kz) < (double)VOX_BIAS);
@@ -219,23 +218,35 @@ __device__ __forceinline__ bool vox_merge_batch(bool active, float px, float py,
     } else if (peers != (1u << lane)) {
         unsigned int rest = peers & ~(1u << leader);                // identical for every lane of the group
 #if VOX_MERGE_PULL
-        // every lane still holds ONE point: its three fractions are <= 2^32 (llrint of a fraction just below 1 gives 2^32:
-        // bit 32 travels in the colour word's top byte) and its colour is 24 bits.  Every lane of a multi-point group
-        // publishes its point as one 128-bit word in the warp's scratch; the leader then reads one LDS.128 per peer and
-        // accumulates in 64 bits (the peers never accumulate, and leave).
-        gather[lane] = make_uint4((unsigned int)sx, (unsigned int)sy, (unsigned int)sz,
-                                  (rgb & 0xFFFFFFu) | ((unsigned int)(sx >> 32) << 24) | ((unsigned int)(sy >> 32) << 25) | ((unsigned int)(sz >> 32) << 26));
-        __syncwarp(peers);
-        if (lane != leader) return false;
-        while (rest) {
-            const int src = __ffs(rest) - 1;
-            rest &= rest - 1;
-            const uint4 g = gather[src];
-            sx += (unsigned long long)g.x + ((unsigned long long)((g.w >> 24) & 1u) << 32);
-            sy += (unsigned long long)g.y + ((unsigned long long)((g.w >> 25) & 1u) << 32);
-            sz += (unsigned long long)g.z + ((unsigned long long)((g.w >> 26) & 1u) << 32);
-            cr += (1ull << 32) | (unsigned long long)(g.w & 0xFFu);
-            gb += ((unsigned long long)((g.w >> 8) & 0xFFu) << 32) | (unsigned long long)((g.w >> 16) & 0xFFu);
+        // every lane still holds ONE point: its three fractions are <= 2^32 (llrint of a fraction just below 1 gives 2^32)
+        // and its colour is 24 bits.  Every lane of a multi-point group publishes its point as three 64-bit words in the
+        // warp's scratch, fraction in bits 0..39 and one colour channel in bits 40..: a group has at most 32 lanes, so the
+        // fraction sums stay below 2^38 and the channel sums below 2^13 — plain 64-bit additions accumulate both without
+        // a carry between the fields.  The leader reads one LDS.128 + one LDS.64 per peer and adds three words (the peers
+        // never accumulate, and leave); the count is the group's population.
+        {
+            const unsigned long long wa = sx | ((unsigned long long)(rgb & 0xFFu) << 40);
+            const unsigned long long wb = sy | ((unsigned long long)((rgb >> 8) & 0xFFu) << 40);
+            const unsigned long long wc = sz | ((unsigned long long)((rgb >> 16) & 0xFFu) << 40);
+            uint2* gather2 = reinterpret_cast<uint2*>(gather + 32);
+            gather[lane] = make_uint4((unsigned int)wa, (unsigned int)(wa >> 32), (unsigned int)wb, (unsigned int)(wb >> 32));
+            gather2[lane] = make_uint2((unsigned int)wc, (unsigned int)(wc >> 32));
+            __syncwarp(peers);
+            if (lane != leader) return false;
+            unsigned long long ta = wa, tb = wb, tc = wc;
+            while (rest) {
+                const int src = __ffs(rest) - 1;
+                rest &= rest - 1;
+                const uint4 g = gather[src];
+                const uint2 h = gather2[src];
+                ta += ((unsigned long long)g.y << 32) | g.x;
+                tb += ((unsigned long long)g.w << 32) | g.z;
+                tc += ((unsigned long long)h.y << 32) | h.x;
+            }
+            const unsigned long long fmask = (1ull << 40) - 1ull;
+            sx = ta & fmask; sy = tb & fmask; sz = tc & fmask;
+            cr = ((unsigned long long)__popc(peers) << 32) | (ta >> 40);
+            gb = ((tb >> 40) << 32) | (tc >> 40);
         }
 #else
         while (rest) {
@@ -555,7 +566,9 @@ extern "C" int da3s_unproject_voxel_jobs(da3s_ctx* ctx, const da3s_export_job* j
     DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, export_voxel_kernel, VI_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     const long long total = (long long)a.chunks_per_frame * n_frames, cap = (long long)ctx->sm_count * per_sm;
+    prof_begin(ctx, DA3S_TIMED_EXPORT_VOXEL, st);
     export_voxel_kernel<<<(unsigned int)(total > cap ? cap : total), VI_THREADS, 0, st>>>(a);
+    prof_end(ctx, DA3S_TIMED_EXPORT_VOXEL, st);
     DA3S_LAUNCH_CHECK(ctx);
     ctx->ws_top = save_top;     // the constants are consumed in stream order
     return DA3S_OK;
@@ -1082,8 +1095,10 @@ extern "C" int da3s_voxel_finish(da3s_ctx* ctx, float voxel, long long max_voxel
     DA3S_LAUNCH_CHECK(ctx);
     voxel_scan_top_kernel<<<1, 1024, 0, st>>>(chunk_offsets, n_chunks, ctx->vox_counters);
     DA3S_LAUNCH_CHECK(ctx);
+    prof_begin(ctx, DA3S_TIMED_VOXEL_EMIT, st);
     voxel_emit_kernel<<<n_cblocks, VC_THREADS, 0, st>>>(ctx->vox_acc, ctx->vox_slots, warp_offsets, chunk_offsets, warp_counts, voxel, max_voxels,
                                                        xyz_out, rgb_out, count_out, key_out);
+    prof_end(ctx, DA3S_TIMED_VOXEL_EMIT, st);
     DA3S_LAUNCH_CHECK(ctx);
     DA3S_CHECK_CUDA(ctx, cudaMemcpyAsync(n_voxels, ctx->vox_counters, 8, cudaMemcpyDeviceToDevice, st));
     if (n_dropped)

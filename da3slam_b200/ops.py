@@ -38,6 +38,17 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.da3s_launch_count(self.h))
 
+    def kernel_timers(self, on: bool = True) -> None:
+        """Event pairs around the library's four big kernels (include/da3s.h: da3s_kernel_timers)."""
+        L.check(self.lib.da3s_kernel_timers(self.h, int(bool(on))), "da3s_kernel_timers")
+
+    def kernel_time(self, which: int):
+        """(sum in ms of the `timed` most recent launch durations, timed, launches since the last read, work units all
+        those launches executed — RANSAC scoring only); synchronises with the last launch."""
+        ms, timed, n, work = C.c_double(0.0), C.c_int(0), C.c_int(0), C.c_double(0.0)
+        L.check(self.lib.da3s_kernel_time(self.h, int(which), C.byref(ms), C.byref(timed), C.byref(n), C.byref(work)), "da3s_kernel_time")
+        return float(ms.value), int(timed.value), int(n.value), float(work.value)
+
 
 def context(device=None, workspace_bytes: int | None = None) -> Context:
     if not torch.cuda.is_available():

@@ -325,13 +325,17 @@ class SequencePlan:
                 self.grid.finish(self.voxel)
                 mark("voxel_compact")
 
-    @property
-    def launches(self) -> int:
-        """Kernel launches so far by every da3s_ctx this plan enqueues on (the device context the alignment and the grid
-        share, plus the private one of the export percentiles)."""
+    def contexts(self):
+        """Every da3s_ctx this plan enqueues on: the device context the alignment and the grid share, plus the private one
+        of the export percentiles."""
         ctxs = {id(c): c for c in (ops.context(self.dev), getattr(getattr(self, "grid", None), "ctx", None),
                                     getattr(getattr(self, "percentiles", None), "ctx", None)) if c is not None}
-        return sum(c.launches for c in ctxs.values())
+        return list(ctxs.values())
+
+    @property
+    def launches(self) -> int:
+        """Kernel launches so far by every da3s_ctx of contexts()."""
+        return sum(c.launches for c in self.contexts())
 
     def read(self, sort=False):
         out = {"rows": self.rows.cpu().numpy(), "cum": self.cum.cpu().numpy()}

@@ -154,8 +154,13 @@ def to_device(sub, device="cuda"):
 # 10^8 pixels would take minutes with numpy.  Extrinsics / ground truth are drawn on the host.
 # ------------------------------------------------------------------------------------------
 def make_sequence_device(n_submaps, frames, H, W, overlap=1, seed=1234, outlier_ratio=0.0, depth_noise=0.002,
-                         with_images=True, device="cuda", conf_offset=0.0):
-    """Returns (submaps, gt): submaps are dicts of CUDA tensors with the Prediction fields."""
+                         with_images=True, device="cuda", conf_offset=0.0, abs_scale=None):
+    """Returns (submaps, gt): submaps are dicts of CUDA tensors with the Prediction fields.
+
+    abs_scale=(lo, hi): every submap draws its OWN metric scale sigma_k in [lo, hi] (sigma_0 = 1) and the pair scale is
+    sigma_k / sigma_{k-1} — what a network that predicts each chunk at an arbitrary scale produces.  Without it the pair
+    scales are independent draws, so the accumulated scale is a random walk over the sequence (after 64 pairs anything
+    from 0.2 to 5: map extent and voxel count then vary 20x between seeds)."""
     import torch
     rng = np.random.default_rng(seed)
     g = torch.Generator(device=device)
@@ -172,6 +177,7 @@ def make_sequence_device(n_submaps, frames, H, W, overlap=1, seed=1234, outlier_
         band[:, :b] = True
         band[:, -b:] = True
     subs, gt, prev = [], [], None
+    sigma_prev = 1.0
     for k in range(n_submaps):
         E = trajectory_w2c(rng, frames)
         p = {name: torch.from_numpy(rng.uniform(lo, hi, size=(frames, 1, 1)).astype(np.float32)).to(dev)
@@ -183,6 +189,9 @@ def make_sequence_device(n_submaps, frames, H, W, overlap=1, seed=1234, outlier_
         conf[:, band] = conf_offset + 0.01 * torch.rand((frames, int(band.sum())), device=dev, generator=g)
         if prev is not None:
             s, R, t = random_sim3(rng)
+            if abs_scale is not None:
+                sigma = float(rng.uniform(*abs_scale))
+                s, sigma_prev = sigma / sigma_prev, sigma
             gt.append((s, R, t))
             Ep = prev["extrinsics"][-overlap:].double().cpu().numpy()
             Rp, tp = c2w_of(Ep)

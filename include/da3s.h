@@ -58,6 +58,23 @@ int da3s_enable_peer_access(da3s_ctx* ctx, int peer_device);
  * Synchronises `stream`.  bench.py uses it as the denominator for the ALU-bound RANSAC scoring kernel. */
 int da3s_measure_fp32_peak(da3s_ctx* ctx, int iters, double* tflops_out, void* stream);
 
+/* Per-kernel device timers: with timers on, the library records a CUDA event pair on the caller's stream around every
+ * launch of the kernels below (nothing else changes; the records cost no device time).  da3s_kernel_time synchronises
+ * with the last recorded pair and returns the SUM of the durations of the `timed` most recent launches (all launches
+ * since the previous read, at most DA3S_TIMER_RING), `timed`, the number of launches since the previous read and, where the
+ * kernel counts it, the work ALL those launches executed (ransac_score_kernel: (hypothesis, correspondence) evaluations,
+ * 27 flop each — invalid hypotheses and masked correspondences are skipped, so this is below n_hyp x pixels; else 0);
+ * then it resets the ring.  work_out may be NULL.  bench.py's roofline lines divide
+ * algorithmic bytes / flops by these. */
+#define DA3S_TIMED_RANSAC_SCORE 0   /* ransac_score_kernel          */
+#define DA3S_TIMED_IRLS         1   /* pair_moments_mixed_kernel    */
+#define DA3S_TIMED_EXPORT_VOXEL 2   /* export_voxel_kernel          */
+#define DA3S_TIMED_VOXEL_EMIT   3   /* voxel_emit_kernel            */
+#define DA3S_TIMED_KERNELS      4
+#define DA3S_TIMER_RING         64
+int da3s_kernel_timers(da3s_ctx* ctx, int on);
+int da3s_kernel_time(da3s_ctx* ctx, int which, double* sum_ms_out, int* timed_out, int* launches_out, double* work_out);
+
 /* ---- camera table ------------------------------------------------------------- */
 /* One entry per frame, device resident.  Built by da3s_build_cams from the network's
  * float32 intrinsics [n,3,3] and world-to-camera extrinsics [n,3,4]

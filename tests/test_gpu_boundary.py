@@ -110,3 +110,43 @@ def test_sequence_plan_validates_its_arguments(cuda):
         SequencePlan(dsubs, overlap=1, export=False, world=1, n_hyp=16)                     # RANSAC without sample_idx
     with pytest.raises(ValueError):
         SequencePlan(dsubs, overlap=1, export=False, world=1, n_hyp=16, sample_idx=torch.zeros((2, 8, 3), dtype=torch.int32))
+
+
+def test_sharded_sequence_plans_equal_the_whole(cuda):
+    """One sequence spread over two (virtual) ranks the way bench.py's hires_global_map section does it
+    (sharding.shard_sequence + SequencePlan(pairs=, export_submaps=, chain_index=, n_chain=, rows_hook=)): every rank's rows are
+    bit-identical to the same rows of the single-rank plan, the chain is identical, and the ranks' exports partition the
+    whole export (every kept point lands in exactly one rank's grid; per key the counts add up to the whole map's)."""
+    from da3slam_b200.pipeline import SequencePlan
+    from da3slam_b200.sharding import shard_sequence
+    H, W, F, n, world = 48, 64, 3, 5, 2
+    subs, _ = synth.make_sequence(n, F, H, W, overlap=1, seed=91, with_images=True)
+    dsubs = [DeviceSubmap.from_prediction(s, cuda) for s in subs]
+    kw = dict(overlap=1, voxel=0.05, conf_percentile=65.0, table_slots=1 << 16, world=1)
+    whole = SequencePlan(dsubs, **kw)
+    whole.run()
+    ref = whole.read(sort=True)
+    rows_full = torch.from_numpy(ref["rows"]).to(cuda)
+    merged = {}
+    for r in range(world):
+        sh = shard_sequence(n, r, world)
+        a, b = sh["a"], sh["b"]
+        local = dsubs[a:b + (1 if sh["halo"] else 0)]
+        n_local_pairs = sh["pair_sizes"][r]
+        first_pair = sum(sh["pair_sizes"][:r])
+        seen = {}
+
+        def hook(rows_local, first_pair=first_pair, n_local_pairs=n_local_pairs, seen=seen):
+            seen["rows"] = rows_local.clone()
+            return rows_full                                   # what RowExchange would hand back on every rank
+        plan = SequencePlan(local, pairs=[(i, i + 1) for i in range(n_local_pairs)], export_submaps=list(range(b - a)),
+                            chain_index=[a + i for i in range(len(local))], n_chain=n, rows_hook=hook, **kw)
+        plan.run()
+        out = plan.read(sort=True)
+        assert np.array_equal(seen["rows"].cpu().numpy(), ref["rows"][first_pair:first_pair + n_local_pairs])
+        assert np.array_equal(out["cum"], ref["cum"])
+        for k_, c_ in zip(out["voxel_key"].cpu().numpy(), out["voxel_count"].cpu().numpy()):
+            merged[int(k_)] = merged.get(int(k_), 0) + int(c_)
+    keys = np.array(sorted(merged))
+    assert np.array_equal(keys, ref["voxel_key"].cpu().numpy())
+    assert np.array_equal(np.array([merged[int(k_)] for k_ in keys]), ref["voxel_count"].cpu().numpy())
