@@ -357,6 +357,9 @@ pair_moments_kernel(PairArgs a) {
 #ifndef PM_DEPTH
 #define PM_DEPTH 3                          // groups (64 B each) a thread keeps in flight through cp.async; 0 = two register buffers
 #endif
+#ifndef PM_PK_BLOCKS
+#define PM_PK_BLOCKS 3                      // resident blocks per SM the packed kernel is compiled for (registers)
+#endif
 #define PM_RING_BYTES ((PM_DEPTH > 0 ? (PM_DEPTH + 1) : 0) * 4 * PM_THREADS * 16)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -426,7 +429,7 @@ __device__ __forceinline__ int pm_wait_entry(const PairArgs& a, long long e) {
 // x = d (a, b, 1) with a = (u - cu) / fu computed once per pair, and only the depth coordinate is pivoted (the lateral
 // coordinates are centred on the principal point already).
 template <bool VEC, bool GATE, bool HUBER, bool PK>
-__global__ void __launch_bounds__(PM_THREADS, PK ? 3 : 4)
+__global__ void __launch_bounds__(PM_THREADS, PK ? PM_PK_BLOCKS : 4)
 pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     __shared__ double red[MOM_LEN][PM_THREADS];     // block reduction scratch (25.6 KB)
     __shared__ FrameConst fc;
@@ -962,6 +965,10 @@ struct RansacArgs {
     float* hyp_A; float* hyp_t; uint8_t* hyp_ok; double* hyp_sim3;
     int32_t* counts;
     unsigned long long* work;       // optional (kernel timers on): += (hypothesis, correspondence) evaluations executed
+    int round_mask, n_sel;          // tiles scored by this launch: those whose rs_round_of() bit is set; n_sel of them per frame
+    int list_stride;                // hypotheses per pair in the (chyp, cidx) list handed to the scoring kernel
+    int split;                      // blocks per tile (a block scores 1 / split of a tile's correspondences); divides PA_GROUPS_PER_BLOCK
+    int32_t* kept_tile;             // optional [n_pairs][overlap * tiles_per_frame]: correspondences that pass the mask, per tile
 };
 
 __device__ __forceinline__ void frame_const_basic(FrameConst& fc, const da3s_pair& pr, int frame, const float* thr,
@@ -1052,6 +1059,117 @@ __global__ void ransac_hyp_kernel(RansacArgs a) {
 #define RS_HPT 4                            // hypotheses per thread (even: two share every packed instruction)
 #endif
 #define RS_HYP_PER_BLOCK (RS_THREADS * RS_HPT)
+#ifndef RS_SPLIT
+#define RS_SPLIT 8                          // blocks per tile in the round launches (PA_GROUPS_PER_BLOCK * 4 / RS_SPLIT correspondences each)
+#endif
+
+// Scoring in ROUNDS with exact pruning (da3s_align_pairs needs the winner, not every count).  The tiles of a frame are
+// dealt into RS_ROUNDS = 3 rounds, interleaved over the image: round 0 takes the middle tile and 5 of every 16 others
+// (35 % of a 518 x 518 frame), round 1 another 4 of 16 (59 % seen), round 2 the rest.  After round 0 the hypothesis with
+// the most inliers so far (the LEADER) is scored on all other tiles at once, which also counts the correspondences every
+// tile keeps.  Its complete count L bounds the winner from below, so after each round a hypothesis whose count so far
+// plus ALL correspondences of the tiles it has not seen yet stays below L can neither win nor tie and is dropped from the
+// list (ransac_prune_kernel); the survivors' counts are complete at the end and the winner (most inliers, ties to the
+// lowest index) is the one full scoring finds.  With a leader at 70 % inliers, round 0 drops everything below 14 % of
+// the leader's count; round 1 catches up to 32 % when the leader itself is weaker.  Few, large launches: every launch
+// pays a ramp (coefficients, first staging) and a tail, which is why the rounds are not finer.
+#define RS_ROUNDS 3
+__host__ __device__ __forceinline__ int rs_round_of(int tile, int tiles_per_frame) {
+    if (tile == tiles_per_frame / 2) return 0;
+    return (int)((0x2102201201202102ull >> (4 * (tile & 15))) & 15ull);
+}
+static int rs_round_tiles(int tiles_per_frame, int mask) {
+    int n = 0;
+    for (int t = 0; t < tiles_per_frame; ++t) n += (mask >> rs_round_of(t, tiles_per_frame)) & 1;
+    return n;
+}
+
+// ordered compaction of the entries i of a list for which keep(i) holds (block per pair, 256 threads)
+template <typename Keep>
+__device__ __forceinline__ void rs_filter_list(const float* __restrict__ chyp_in, const int32_t* __restrict__ cidx_in, int n_in, int stride,
+                                               int pair, float* __restrict__ chyp_out, int32_t* __restrict__ cidx_out,
+                                               int32_t* __restrict__ n_out, int* wsum, int* base_sh, Keep keep) {
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) *base_sh = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_in; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        const int h = i < n_in ? cidx_in[(size_t)pair * stride + i] : -1;
+        const bool ok = h >= 0 && keep(h);
+        const unsigned int m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int before = *base_sh;
+        for (unsigned int w = 0; w < warp; ++w) before += wsum[w];
+        if (ok) {
+            const int pos = before + __popc(m & ((1u << lane) - 1u));
+            const float* src = chyp_in + ((size_t)pair * stride + i) * 12;
+            float* dst = chyp_out + ((size_t)pair * stride + pos) * 12;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) dst[k] = src[k];
+            cidx_out[(size_t)pair * stride + pos] = h;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += wsum[w]; *base_sh += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_out[pair] = *base_sh;
+}
+
+// leader after round 0 (most inliers so far, ties to the lowest index) as a one-entry list, and the list without it
+__global__ void __launch_bounds__(256)
+ransac_lead_kernel(const int32_t* __restrict__ counts, int n_hyp, const float* __restrict__ chyp_in, const int32_t* __restrict__ cidx_in,
+                   const int32_t* __restrict__ n_in, float* __restrict__ chyp_lead, int32_t* __restrict__ cidx_lead, int32_t* __restrict__ n_lead,
+                   float* __restrict__ chyp_out, int32_t* __restrict__ cidx_out, int32_t* __restrict__ n_out) {
+    __shared__ unsigned long long best[256];
+    __shared__ int wsum[8];
+    __shared__ int base_sh;
+    const int pair = blockIdx.x, n = n_in[pair];
+    unsigned long long b = 0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int h = cidx_in[(size_t)pair * n_hyp + i];
+        const unsigned long long key = ((unsigned long long)(unsigned int)(counts[(size_t)pair * n_hyp + h] + 1) << 32) | (unsigned int)(0x7fffffff - h);
+        if (key > b) b = key;
+    }
+    best[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s && best[threadIdx.x + s] > best[threadIdx.x]) best[threadIdx.x] = best[threadIdx.x + s];
+        __syncthreads();
+    }
+    const int lead = best[0] ? (int)(0x7fffffff - (unsigned int)(best[0] & 0xffffffffu)) : -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256)
+        if (cidx_in[(size_t)pair * n_hyp + i] == lead) {
+            for (int k = 0; k < 12; ++k) chyp_lead[(size_t)pair * 12 + k] = chyp_in[((size_t)pair * n_hyp + i) * 12 + k];
+        }
+    if (threadIdx.x == 0) { cidx_lead[pair] = lead; n_lead[pair] = lead >= 0 ? 1 : 0; }
+    rs_filter_list(chyp_in, cidx_in, n, n_hyp, pair, chyp_out, cidx_out, n_out, wsum, &base_sh, [&](int h) { return h != lead; });
+}
+
+// after round `after_round`: keep the hypotheses that can still reach the leader's complete count
+__global__ void __launch_bounds__(256)
+ransac_prune_kernel(const int32_t* __restrict__ counts, int n_hyp, const int32_t* __restrict__ cidx_lead, const int32_t* __restrict__ kept_tile,
+                    int overlap, int tiles_per_frame, int after_round, const float* __restrict__ chyp_in, const int32_t* __restrict__ cidx_in,
+                    const int32_t* __restrict__ n_in, float* __restrict__ chyp_out, int32_t* __restrict__ cidx_out, int32_t* __restrict__ n_out) {
+    __shared__ int wsum[8];
+    __shared__ int base_sh;
+    __shared__ long long rem_sh;
+    const int pair = blockIdx.x;
+    if (threadIdx.x == 0) rem_sh = 0;
+    __syncthreads();
+    long long rem = 0;                      // correspondences of the tiles the list has not been scored on yet
+    for (int i = threadIdx.x; i < overlap * tiles_per_frame; i += 256)
+        if (rs_round_of(i % tiles_per_frame, tiles_per_frame) > after_round) rem += kept_tile[(size_t)pair * overlap * tiles_per_frame + i];
+    for (int o = 16; o > 0; o >>= 1) rem += __shfl_down_sync(0xffffffffu, rem, o);
+    if ((threadIdx.x & 31) == 0 && rem) atomicAdd((unsigned long long*)&rem_sh, (unsigned long long)rem);
+    __syncthreads();
+    const long long remaining = rem_sh;
+    const int lead = cidx_lead[pair];
+    const long long target = lead >= 0 ? (long long)counts[(size_t)pair * n_hyp + lead] : 0;
+    rs_filter_list(chyp_in, cidx_in, n_in[pair], n_hyp, pair, chyp_out, cidx_out, n_out, wsum, &base_sh,
+                   [&](int h) { return (long long)counts[(size_t)pair * n_hyp + h] + remaining >= target; });
+}
 
 // Valid hypotheses of every pair, compacted (stable): coefficient rows [n_pairs][n_hyp][12] (A row-major, then t), their
 // original indices, and the count.  About a third of uniformly drawn 3-pixel samples touch a masked pixel (SPEC 4: such a
@@ -1093,6 +1211,7 @@ ransac_compact_kernel(const float* __restrict__ hyp_A, const float* __restrict__
 // counts at most 16384 correspondences), which replaces compare + predicated integer add per hypothesis by 1.5 instructions
 __device__ __forceinline__ float set_lt(float a, float b) { float r; asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
+
 // Threads own hypotheses (coefficients in registers), points are broadcast from shared
 // memory.  Two hypotheses share every arithmetic instruction: sm_100's packed float32 pipe
 // (FFMA2 / FADD2 / FMUL2 on register pairs, each half an ordinary IEEE operation, so SPEC 4's
@@ -1111,10 +1230,22 @@ ransac_score_kernel(RansacArgs a, const float* __restrict__ chyp, const int32_t*
     const int hyp0 = blockIdx.z * RS_HYP_PER_BLOCK;
     if (hyp0 >= nv) return;                 // block-uniform
     const da3s_pair pr = a.pairs[pair];
-    const int frame = blockIdx.x / a.tiles_per_frame;
-    const int tile = blockIdx.x - frame * a.tiles_per_frame;
-    if (threadIdx.x == 0) { frame_const_basic(fc, pr, frame, a.thr, a.dscale, pair); n_sh = 0; }
+    __shared__ int tile_sh;
+    const int bx = blockIdx.x / a.split, part = blockIdx.x - bx * a.split;
+    const int frame = bx / a.n_sel;
+    if (threadIdx.x == 0) {
+        frame_const_basic(fc, pr, frame, a.thr, a.dscale, pair); n_sh = 0;
+        const int j = bx - frame * a.n_sel;             // the j-th tile of this launch's rounds
+        int t = j;
+        if (a.n_sel != a.tiles_per_frame) {
+            int c = 0;
+            for (t = 0; t < a.tiles_per_frame; ++t)
+                if ((a.round_mask >> rs_round_of(t, a.tiles_per_frame)) & 1) { if (c == j) break; ++c; }
+        }
+        tile_sh = t;
+    }
     __syncthreads();
+    const int tile = tile_sh;
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // this warp's hypotheses: lane-interleaved inside the warp so that a warp covers 32 * RS_HPT consecutive valid ones
     const int wbase = hyp0 + (int)warp * 32 * RS_HPT;
@@ -1127,7 +1258,7 @@ ransac_score_kernel(RansacArgs a, const float* __restrict__ chyp, const int32_t*
     for (int m = 0; m < RS_HPT; ++m) {
         const int j = wbase + m * 32 + (int)lane;
         hid[m] = j < nv ? j : -1;
-        const float* hc = chyp + ((size_t)pair * a.n_hyp + (j < nv ? j : 0)) * 12;
+        const float* hc = chyp + ((size_t)pair * a.list_stride + (j < nv ? j : 0)) * 12;
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             const float c = warp_live ? hc[k] : 0.0f;
@@ -1138,8 +1269,9 @@ ransac_score_kernel(RansacArgs a, const float* __restrict__ chyp, const int32_t*
     for (int q = 0; q < RS_HPT / 2; ++q) cnt[q] = make_float2(0.0f, 0.0f);
 
     const size_t foff = (size_t)frame * (size_t)a.P;
-    const long long p_begin = (long long)tile * PA_GROUPS_PER_BLOCK * 4;
-    long long p_end = p_begin + (long long)PA_GROUPS_PER_BLOCK * 4;
+    const long long part_len = (long long)(PA_GROUPS_PER_BLOCK * 4) / a.split;
+    const long long p_begin = (long long)tile * PA_GROUPS_PER_BLOCK * 4 + part * part_len;
+    long long p_end = p_begin + part_len;
     if (p_end > a.P) p_end = a.P;
     const float2 thr2 = make_float2(a.thr2, a.thr2);
     int n_staged = 0;
@@ -1194,12 +1326,15 @@ ransac_score_kernel(RansacArgs a, const float* __restrict__ chyp, const int32_t*
         __syncthreads();
     }
     if (!warp_live) return;
-    if (a.work && threadIdx.x == 0)
-        atomicAdd(a.work, (unsigned long long)n_staged * (unsigned long long)min(RS_HYP_PER_BLOCK, nv - hyp0));
+    if (threadIdx.x == 0) {
+        if (a.work) atomicAdd(a.work, (unsigned long long)n_staged * (unsigned long long)min(RS_HYP_PER_BLOCK, nv - hyp0));
+        if (a.kept_tile && blockIdx.z == 0 && n_staged)
+            atomicAdd(&a.kept_tile[((size_t)pair * a.overlap + frame) * a.tiles_per_frame + tile], n_staged);
+    }
 #pragma unroll
     for (int m = 0; m < RS_HPT; ++m) {
         const int c = (int)((m & 1) ? cnt[m >> 1].y : cnt[m >> 1].x);
-        if (hid[m] >= 0 && c) atomicAdd(&a.counts[(size_t)pair * a.n_hyp + cidx[(size_t)pair * a.n_hyp + hid[m]]], c);
+        if (hid[m] >= 0 && c) atomicAdd(&a.counts[(size_t)pair * a.n_hyp + cidx[(size_t)pair * a.list_stride + hid[m]]], c);
     }
 }
 
@@ -1280,6 +1415,60 @@ ransac_mask_kernel(RansacArgs a, const float* best_A, const float* best_t, const
     }
 }
 
+// The leader on the tiles of the rounds in a.round_mask, point-parallel (threads own correspondences, the one hypothesis is
+// block-uniform): its inlier count (same float32 chain as the scoring kernel: residual2_f32) and, per tile, the number of
+// correspondences that pass the mask.  A scoring-kernel warp evaluates 128 hypothesis slots whatever the list length, so a
+// one-entry list would cost a fifth of full scoring; this pass is a plain 16 B / correspondence stream.
+__global__ void __launch_bounds__(256)
+ransac_leader_kernel(RansacArgs a, const float* __restrict__ chyp_lead, const int32_t* __restrict__ cidx_lead) {
+    __shared__ FrameConst fc;
+    __shared__ float g[12];
+    __shared__ int tile_sh;
+    __shared__ int red[2][8];
+    const int pair = blockIdx.y;
+    const int lead = cidx_lead[pair];
+    if (lead < 0) return;                   // block-uniform
+    const da3s_pair pr = a.pairs[pair];
+    const int frame = blockIdx.x / a.n_sel;
+    if (threadIdx.x == 0) {
+        frame_const_basic(fc, pr, frame, a.thr, a.dscale, pair);
+        for (int k = 0; k < 12; ++k) g[k] = chyp_lead[(size_t)pair * 12 + k];
+        const int j = blockIdx.x - frame * a.n_sel;
+        int c = 0, t;
+        for (t = 0; t < a.tiles_per_frame; ++t)
+            if ((a.round_mask >> rs_round_of(t, a.tiles_per_frame)) & 1) { if (c == j) break; ++c; }
+        tile_sh = t;
+    }
+    __syncthreads();
+    const int tile = tile_sh;
+    const size_t foff = (size_t)frame * (size_t)a.P;
+    const long long p_begin = (long long)tile * PA_GROUPS_PER_BLOCK * 4;
+    long long p_end = p_begin + (long long)PA_GROUPS_PER_BLOCK * 4;
+    if (p_end > a.P) p_end = a.P;
+    int kept = 0, inl = 0;
+    for (long long pix = p_begin + threadIdx.x; pix < p_end; pix += 256) {
+        const int v = (int)(pix / a.W), u = (int)(pix - (long long)v * a.W);
+        float x[3], y[3], xs[3], ys[3], dbs;
+        const bool keep = corr_points(fc, a.valid_depth, a.depth_eps, u, v, ldg_stream1(pr.depth_a + foff + pix), ldg_stream1(pr.conf_a + foff + pix),
+                                      ldg_stream1(pr.depth_b + foff + pix), ldg_stream1(pr.conf_b + foff + pix), x, y, dbs);
+        if (keep) {
+            ransac_points(fc, a.world, x, y, xs, ys);
+            ++kept;
+            inl += residual2_f32(g, xs, ys) < a.thr2 ? 1 : 0;
+        }
+    }
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    inl = __reduce_add_sync(0xffffffffu, inl);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = kept; red[1][threadIdx.x >> 5] = inl; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int k = 0, n = 0;
+        for (int w = 0; w < 8; ++w) { k += red[0][w]; n += red[1][w]; }
+        if (a.kept_tile) a.kept_tile[((size_t)pair * a.overlap + frame) * a.tiles_per_frame + tile] = k;
+        if (n) atomicAdd(&a.counts[(size_t)pair * a.n_hyp + lead], n);
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // host-side orchestration
 // ---------------------------------------------------------------------------------
@@ -1336,6 +1525,7 @@ static void fill_ransac_args(RansacArgs& r, const da3s_pair* pairs, int n_pairs,
     r.thr2 = (float)((double)ransac_thr * (double)ransac_thr);
     r.thr = thr; r.dscale = dscale; r.sample_idx = nullptr; r.hyp_A = nullptr; r.hyp_t = nullptr; r.hyp_ok = nullptr;
     r.hyp_sim3 = nullptr; r.counts = nullptr; r.work = nullptr;
+    r.round_mask = (1 << RS_ROUNDS) - 1; r.n_sel = tpf; r.list_stride = n_hyp; r.split = 1; r.kept_tile = nullptr;
 }
 
 extern "C" int da3s_ransac_hypotheses(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, int overlap, int H, int W,
@@ -1382,6 +1572,72 @@ extern "C" int da3s_ransac_score(da3s_ctx* ctx, const da3s_pair* pairs, int n_pa
     ransac_score_kernel<<<grid, RS_THREADS, 0, st>>>(r, chyp, cidx, n_valid);
     prof_end(ctx, DA3S_TIMED_RANSAC_SCORE, st);
     DA3S_LAUNCH_CHECK(ctx);
+    ctx->ws_top = save_top;     // consumed in stream order
+    return DA3S_OK;
+}
+
+// Scoring for da3s_align_pairs: rounds with exact pruning (comment above rs_round_of).  Same winner as da3s_ransac_score;
+// the counts of dropped hypotheses stay partial (below the winner's), so this path is not used when the caller asks for
+// the count table.
+static int ransac_score_rounds(da3s_ctx* ctx, RansacArgs r, const float* hyp_A, const float* hyp_t, const uint8_t* hyp_ok,
+                               int32_t* counts, cudaStream_t st) {
+    const int n_pairs = r.n_pairs, n_hyp = r.n_hyp, tpf = r.tiles_per_frame, overlap = r.overlap;
+    r.counts = counts;
+    r.work = ctx->prof_on ? ctx->prof_work + DA3S_TIMED_RANSAC_SCORE : nullptr;
+    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_pairs * n_hyp, st));
+    size_t save_top = ctx->ws_top;
+    float* chyp[2]; int32_t* cidx[2]; int32_t* n_list[2];
+    for (int k = 0; k < 2; ++k) {
+        WS_ALLOC(ctx, float, c, (size_t)n_pairs * n_hyp * 12);
+        WS_ALLOC(ctx, int32_t, i, (size_t)n_pairs * n_hyp);
+        WS_ALLOC(ctx, int32_t, n, n_pairs);
+        chyp[k] = c; cidx[k] = i; n_list[k] = n;
+    }
+    WS_ALLOC(ctx, float, chyp_lead, (size_t)n_pairs * 12);
+    WS_ALLOC(ctx, int32_t, cidx_lead, n_pairs);
+    WS_ALLOC(ctx, int32_t, n_lead, n_pairs);
+    WS_ALLOC(ctx, int32_t, kept_tile, (size_t)n_pairs * overlap * tpf);
+    DA3S_CHECK_CUDA(ctx, cudaMemsetAsync(kept_tile, 0, sizeof(int32_t) * (size_t)n_pairs * overlap * tpf, st));
+    const int zs = (n_hyp + RS_HYP_PER_BLOCK - 1) / RS_HYP_PER_BLOCK;
+    if (zs > 65535) return DA3S_EINVAL;
+    // a round has few tiles: every tile is cut into RS_SPLIT blocks so that one launch still fills the device
+    auto score = [&](int mask, const float* ch, const int32_t* ci, const int32_t* nl, int stride, int z, bool count_kept) -> int {
+        RansacArgs q = r;
+        q.round_mask = mask; q.n_sel = rs_round_tiles(tpf, mask); q.list_stride = stride; q.split = RS_SPLIT;
+        q.kept_tile = count_kept ? kept_tile : nullptr;
+        if (q.n_sel == 0) return DA3S_OK;
+        prof_begin(ctx, DA3S_TIMED_RANSAC_SCORE, st);
+        ransac_score_kernel<<<dim3(q.n_sel * overlap * RS_SPLIT, n_pairs, z), RS_THREADS, 0, st>>>(q, ch, ci, nl);
+        prof_end(ctx, DA3S_TIMED_RANSAC_SCORE, st);
+        DA3S_LAUNCH_CHECK(ctx);
+        return DA3S_OK;
+    };
+    ransac_compact_kernel<<<n_pairs, 256, 0, st>>>(hyp_A, hyp_t, hyp_ok, n_hyp, chyp[0], cidx[0], n_list[0]);
+    DA3S_LAUNCH_CHECK(ctx);
+    const int all_rounds = (1 << RS_ROUNDS) - 1;
+    int rc = score(1 << 0, chyp[0], cidx[0], n_list[0], n_hyp, zs, true);                   // round 0, every valid hypothesis
+    if (rc != DA3S_OK) return rc;
+    ransac_lead_kernel<<<n_pairs, 256, 0, st>>>(counts, n_hyp, chyp[0], cidx[0], n_list[0], chyp_lead, cidx_lead, n_lead,
+                                                chyp[1], cidx[1], n_list[1]);
+    DA3S_LAUNCH_CHECK(ctx);
+    {                                                                                       // the leader on every other tile
+        RansacArgs q = r;
+        q.round_mask = all_rounds & ~1; q.n_sel = rs_round_tiles(tpf, q.round_mask); q.kept_tile = kept_tile;
+        if (q.n_sel > 0) {
+            ransac_leader_kernel<<<dim3(q.n_sel * overlap, n_pairs), 256, 0, st>>>(q, chyp_lead, cidx_lead);
+            DA3S_LAUNCH_CHECK(ctx);
+        }
+    }
+    int cur = 1;
+    for (int round = 1; round < RS_ROUNDS; ++round) {
+        if (rs_round_tiles(tpf, 1 << round) == 0) continue;
+        ransac_prune_kernel<<<n_pairs, 256, 0, st>>>(counts, n_hyp, cidx_lead, kept_tile, overlap, tpf, round - 1, chyp[cur], cidx[cur],
+                                                     n_list[cur], chyp[cur ^ 1], cidx[cur ^ 1], n_list[cur ^ 1]);
+        DA3S_LAUNCH_CHECK(ctx);
+        cur ^= 1;
+        rc = score(1 << round, chyp[cur], cidx[cur], n_list[cur], n_hyp, zs, false);
+        if (rc != DA3S_OK) return rc;
+    }
     ctx->ws_top = save_top;     // consumed in stream order
     return DA3S_OK;
 }
@@ -1459,8 +1715,17 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
         rc = da3s_ransac_hypotheses(ctx, pairs, n_pairs, overlap, H, W, opts->world, opts->valid_depth, opts->depth_eps,
                                     thr, dscale, sample_idx, nh, hyp_A, hyp_t, hyp_ok, nullptr, stream);
         if (rc != DA3S_OK) return rc;
-        rc = da3s_ransac_score(ctx, pairs, n_pairs, overlap, H, W, opts->world, opts->valid_depth, opts->depth_eps,
-                               thr, dscale, hyp_A, hyp_t, hyp_ok, nh, opts->ransac_thr, counts, stream);
+        // the winner is all that is needed unless the caller asked for the count table: rounds with exact pruning
+        static const bool no_rounds = getenv("DA3S_RANSAC_FULL") && getenv("DA3S_RANSAC_FULL")[0] == '1';
+        if (!hyp_counts_out && tpf >= 8 && !no_rounds) {
+            RansacArgs r;
+            fill_ransac_args(r, pairs, n_pairs, overlap, H, W, P, tpf, opts->world, opts->valid_depth, opts->depth_eps, thr, dscale, nh,
+                             opts->ransac_thr);
+            rc = ransac_score_rounds(ctx, r, hyp_A, hyp_t, hyp_ok, counts, st);
+        } else {
+            rc = da3s_ransac_score(ctx, pairs, n_pairs, overlap, H, W, opts->world, opts->valid_depth, opts->depth_eps,
+                                   thr, dscale, hyp_A, hyp_t, hyp_ok, nh, opts->ransac_thr, counts, stream);
+        }
         if (rc != DA3S_OK) return rc;
         ransac_best_kernel<<<n_pairs, 256, 0, st>>>(counts, hyp_ok, hyp_A, hyp_t, nh, opts->ransac_min_inliers, state, gate,
                                                     sim3_rows, aux, n_active);

@@ -71,7 +71,7 @@ int da3s_measure_fp32_peak(da3s_ctx* ctx, int iters, double* tflops_out, void* s
 #define DA3S_TIMED_EXPORT_VOXEL 2   /* export_voxel_kernel          */
 #define DA3S_TIMED_VOXEL_EMIT   3   /* voxel_emit_kernel            */
 #define DA3S_TIMED_KERNELS      4
-#define DA3S_TIMER_RING         64
+#define DA3S_TIMER_RING         256
 int da3s_kernel_timers(da3s_ctx* ctx, int on);
 int da3s_kernel_time(da3s_ctx* ctx, int which, double* sum_ms_out, int* timed_out, int* launches_out, double* work_out);
 
@@ -251,7 +251,8 @@ typedef struct da3s_pair_aux {  /* optional per-pair diagnostics, float64[8] per
  * utils/align_geometry_single.py:31-49,105-122 and the per-pair body of
  * utils/da3_streaming.py:322-363.
  * sample_idx: device int32 [n_pairs, n_hyp, 3] pixel indices in [0, overlap*H*W) (null if n_hyp==0).
- * hyp_counts_out: device int32 [n_pairs, n_hyp] (nullable). */
+ * hyp_counts_out: device int32 [n_pairs, n_hyp] (nullable).  Without it the hypotheses are scored in rounds and those
+ * that can no longer reach the leader's count are dropped (exact: same winner, same count, same rows). */
 int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs /* device */, int n_pairs,
                      int overlap, int H, int W, const da3s_align_opts* opts,
                      const int32_t* sample_idx, double* sim3_rows /* [n_pairs,16] */,

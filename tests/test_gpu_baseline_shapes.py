@@ -124,6 +124,10 @@ def test_ransac_1024_hypotheses_64_pairs(cuda):
     opts = L.default_opts(world=1, n_hyp=n_hyp, ransac_thr=thr)
     rows, aux, counts = ops.align_pairs(ops.make_pairs(entries, cuda), n, 1, H, W, opts, torch.from_numpy(si).to(cuda),
                                         want_aux=True, want_counts=True)
+    # the same call without the count table scores in rounds and drops hypotheses that can no longer win (pair_align.cu,
+    # rs_round_of): winner, its count and every row must come out bit for bit the same
+    rows_r, aux_r, _ = ops.align_pairs(ops.make_pairs(entries, cuda), n, 1, H, W, opts, torch.from_numpy(si).to(cuda), want_aux=True)
+    assert torch.equal(rows_r, rows) and torch.equal(aux_r, aux)
     rows, aux, counts = rows.cpu().numpy(), aux.cpu().numpy(), counts.cpu().numpy()
     for k in range(n):
         assert rows[k, 15] == 0 and abs(rows[k, 0] - gt[k][0]) < 5e-3 * gt[k][0], k
