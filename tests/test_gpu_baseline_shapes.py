@@ -147,3 +147,31 @@ def test_ransac_1024_hypotheses_64_pairs(cuda):
         mask = sp.ransac_inlier_mask_c(A, T, best, xs, ys, corr["mask"], thr)
         s, R, t, info = sp.irls_dense(corr["x"], corr["y"], corr["c"], mask)
         check_row(rows[k], dict(s=s, R=R, t=t, iters=info["iters"], n_valid=info["n_valid"], status=info["status"]), f"pair {k}")
+
+
+@pytest.mark.parametrize("outlier", [0.1, 0.45])
+def test_ransac_rounds_two_overlap_frames(cuda, outlier):
+    """The round scoring (pair_align.cu: rs_round_of, leader pass, pruning) on a second geometry: 384 x 384 (9 tiles per
+    frame), TWO overlap frames, 10 % outliers (almost every valid hypothesis survives) and 45 % (the leader's ratio is
+    below what round 0 can prune on: round 1 is the first to drop anything).  With and without the count table the rows,
+    the winner and its count must be identical; the winner of every pair is checked against the oracle's table."""
+    H = W = 384
+    n_sub, n_hyp, thr, ov = 4, 192, 0.02, 2
+    subs, gt = synth.make_sequence_device(n_sub, 3, H, W, overlap=ov, seed=31, outlier_ratio=outlier, with_images=False, device=cuda)
+    dsubs, table, n = dev_pairs(subs, cuda, ov)
+    rng = np.random.default_rng(17)
+    si = rng.integers(0, ov * H * W, size=(n, n_hyp, 3)).astype(np.int32)
+    opts = L.default_opts(world=1, n_hyp=n_hyp, ransac_thr=thr)
+    rows_f, aux_f, counts = ops.align_pairs(table, n, ov, H, W, opts, torch.from_numpy(si).to(cuda), want_aux=True, want_counts=True)
+    rows_r, aux_r, _ = ops.align_pairs(table, n, ov, H, W, opts, torch.from_numpy(si).to(cuda), want_aux=True)
+    assert torch.equal(rows_r, rows_f) and torch.equal(aux_r, aux_f)
+    aux, counts = aux_r.cpu().numpy(), counts.cpu().numpy()
+    for k in range(n):
+        prev, cur = synth.submap_to_host(subs[k]), synth.submap_to_host(subs[k + 1])
+        corr = sp.pair_correspondences(prev, cur, ov, True)
+        xs, ys = sp.ransac_points(corr, True)
+        A, T, ok, _ = sp.ransac_hypotheses(xs, ys, corr["mask"], si[k])
+        ref_counts = sp.ransac_score_c(A, T, ok, xs, ys, corr["mask"], thr)
+        best, nbest = sp.ransac_best(ref_counts, ok)
+        assert int(aux[k, 4]) == best and abs(int(aux[k, 5]) - nbest) <= 2, (k, aux[k, 4:6], best, nbest)
+        assert int(aux[k, 5]) == int(counts[k].max())
