@@ -16,7 +16,6 @@
 // moments — so world mode costs nothing per pixel.
 #include "common.cuh"
 #include "sim3_math.cuh"
-#include <cooperative_groups.h>
 #include <cstdlib>
 
 int da3s_select_impl(da3s_ctx* ctx, const da3s_select_seg* segs, int n_segs, long long max_n,
@@ -370,9 +369,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-#ifndef PM_QUEUE
-#define PM_QUEUE 1                          // 1: per-pair dependencies through a work queue (below); 0: grid-wide barrier between passes
-#endif
 
 __device__ __forceinline__ int ld_acquire_s32(const int* p) {
     int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
@@ -416,10 +412,10 @@ __device__ __forceinline__ int pm_wait_entry(const PairArgs& a, long long e) {
     }
 }
 
-// PERSISTENT: one cooperative launch runs every IRLS iteration.  Blocks stride over the
-// (pair, tile) work items of the pairs that have not converged, the last block of a pair
-// (ticket) solves it, a grid-wide barrier separates iterations, and the kernel ends as soon as
-// no pair is active — no empty launches, no host involvement between iterations.
+// PERSISTENT: one launch runs every IRLS iteration of every pair.  Blocks draw (queue entry, tile) items from one global
+// ticket; the block that finishes the last tile of a pair's pass (per-pair ticket) solves the pair and, unless it has
+// finished, appends it to the queue again — pairs iterate independently, there is no barrier between passes — and the
+// kernel ends when every active pair has finished: no empty launches, no host involvement between iterations.
 //
 // PK (default whenever W is even): the two horizontally adjacent pixels of a float4 half share every float32
 // instruction — packed FFMA2 / FMUL2 / FADD2 on register pairs (.x = pixel 2i, .y = pixel 2i + 1; W even means a pair
@@ -430,7 +426,7 @@ __device__ __forceinline__ int pm_wait_entry(const PairArgs& a, long long e) {
 // coordinates are centred on the principal point already).
 template <bool VEC, bool GATE, bool HUBER, bool PK>
 __global__ void __launch_bounds__(PM_THREADS, PK ? PM_PK_BLOCKS : 4)
-pair_moments_mixed_kernel(PairArgs a, int max_passes) {
+pair_moments_mixed_kernel(PairArgs a) {
     __shared__ double red[MOM_LEN][PM_THREADS];     // block reduction scratch (25.6 KB)
     __shared__ FrameConst fc;
     __shared__ float piv[6];                        // pivot: x (source) then y (target), float32 camera-frame point
@@ -438,17 +434,13 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
     __shared__ double wmom[MOM_LEN];
     __shared__ double part[MOM_LEN][PM_THREADS / 32];
     __shared__ bool is_last;
-    __shared__ int pair_done;
+    __shared__ int cur_pair;                       // the current item's pair, -1 once every pair has finished
     __shared__ long long cur_item;
-#if !PM_QUEUE
-    cooperative_groups::grid_group grid_g = cooperative_groups::this_grid();
-#endif
     const int n_tiles_all = a.overlap * a.tiles_per_frame;
     const long long n_items = (long long)a.n_pairs * n_tiles_all;
   __shared__ float fcm[32];                         // per-item constants, filled by warp 0 (one value per lane)
   // with few items per block an early request would take work away from idle blocks
   const bool prefetch = n_items >= 4ll * gridDim.x;
-#if PM_QUEUE
   const int pass = 0;
   {
    // dynamic work distribution over the queue's items: the block that happens to solve a pair (serial epilogue) simply
@@ -458,40 +450,17 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
    if (threadIdx.x == 0) {
        const long long it = (long long)atomicAdd(&a.work_counter[0], 1ull);
        cur_item = it;
-       pair_done = pm_wait_entry(a, it / n_tiles_all);         // here: the item's pair, or -1 (all pairs finished)
+       cur_pair = pm_wait_entry(a, it / n_tiles_all);
    }
    __syncthreads();
    for (;;) {
     const long long item = cur_item;
-    const int pair = pair_done;
+    const int pair = cur_pair;
     if (pair < 0) break;
     long long next_item = 0;
     if (prefetch && threadIdx.x == 0) next_item = (long long)atomicAdd(&a.work_counter[0], 1ull);
    do {
     const int item_tile = (int)(item % n_tiles_all);
-#else
-  for (int pass = 0; pass < max_passes; ++pass) {
-   // dynamic work distribution: the block that happens to solve a pair (serial epilogue) simply
-   // takes fewer tiles, instead of delaying a fixed share of them.  The NEXT item is requested
-   // while the current one is processed, so the atomic's round trip is never waited for.
-   __syncthreads();
-   if (threadIdx.x == 0) {
-       const long long it = (long long)atomicAdd(&a.work_counter[pass], 1ull);
-       cur_item = it;
-       pair_done = (it < n_items) ? *((volatile int*)&a.state[(int)(it / n_tiles_all)].done) : 1;
-   }
-   __syncthreads();
-   for (;;) {
-    const long long item = cur_item;
-    const bool skip = pair_done != 0;
-    if (item >= n_items) break;
-    long long next_item = 0;
-    if (prefetch && threadIdx.x == 0) next_item = (long long)atomicAdd(&a.work_counter[pass], 1ull);
-   do {
-    const int pair = (int)(item / n_tiles_all);
-    const int item_tile = (int)(item - (long long)pair * n_tiles_all);
-    if (skip) continue;                             // block-uniform: converged pairs cost nothing
-#endif
     const da3s_pair pr = a.pairs[pair];
     const int frame = item_tile / a.tiles_per_frame;
     const int tile = item_tile - frame * a.tiles_per_frame;
@@ -848,43 +817,23 @@ pair_moments_mixed_kernel(PairArgs a, int max_passes) {
         for (int k = 0; k < MOM_LEN; ++k) mm[k] = wmom[k];
         a.tickets[pair] = 0;
         solve_pair(a, pair, mm, pass);              // ends with: fence, state, done_count
-#if PM_QUEUE
         if (!*((volatile int*)&a.state[pair].done)) {
             // the pair's next pass may start: its residual map, state and ticket are written; publish the entry
             __threadfence();
             const unsigned int e = atomicAdd(a.q_reserve, 1u);
             if (e < (unsigned int)a.q_cap) st_release_s32(a.q_pair + e, pair);
         }
-#endif
     }
    } while (0);
     __syncthreads();                                // everyone is done with cur_item and the shared scratch
-#if PM_QUEUE
     if (threadIdx.x == 0) {
         if (!prefetch) next_item = (long long)atomicAdd(&a.work_counter[0], 1ull);
         cur_item = next_item;
-        pair_done = pm_wait_entry(a, next_item / n_tiles_all);
+        cur_pair = pm_wait_entry(a, next_item / n_tiles_all);
     }
     __syncthreads();
    }   // items
   }
-#else
-    if (threadIdx.x == 0) {
-        if (!prefetch) next_item = (long long)atomicAdd(&a.work_counter[pass], 1ull);
-        cur_item = next_item;
-        pair_done = (next_item < n_items) ? *((volatile int*)&a.state[(int)(next_item / n_tiles_all)].done) : 1;
-    }
-    __syncthreads();
-   }   // items
-   grid_g.sync();                                   // every solve of this pass is visible everywhere
-   // pairs still active = active at start - finished in passes <= this one.  Only counters of
-   // completed passes are read, so every block takes the same decision (a fast block already
-   // working on the next pass writes done_count[pass + 1]).
-   int active = *((volatile int*)a.n_active);
-   for (int q = 0; q <= pass; ++q) active -= *((volatile int*)&a.done_count[q]);
-   if (active <= 0) break;
-  }    // passes
-#endif
 }
 
 // ---------------------------------------------------------------------------------
@@ -1743,7 +1692,7 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
         }
         return DA3S_OK;
     }
-    // persistent cooperative launch: as many blocks as can be co-resident, never more than there are items
+    // persistent launch: as many blocks as can be resident, never more than there are items
     const bool use_gate = a.gate != nullptr;
     // PK (packed pixel pairs) needs the float4 path and an even row length; DA3S_IRLS_SCALAR=1 forces the scalar form (A/B runs)
     static const bool force_scalar = getenv("DA3S_IRLS_SCALAR") && getenv("DA3S_IRLS_SCALAR")[0] == '1';
@@ -1762,23 +1711,16 @@ extern "C" int da3s_align_pairs(da3s_ctx* ctx, const da3s_pair* pairs, int n_pai
         DA3S_CHECK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
     DA3S_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PM_THREADS, ring_bytes));
     if (per_sm < 1) return DA3S_ECUDA;
-    long long coop_blocks = (long long)per_sm * ctx->sm_count;
+    long long n_blocks = (long long)per_sm * ctx->sm_count;
     const long long items = (long long)n_pairs * n_tiles;
-    if (coop_blocks > items) coop_blocks = items;
-    int max_passes = iters;
-    void* kargs[] = {(void*)&a, (void*)&max_passes};
-#if PM_QUEUE
+    if (n_blocks > items) n_blocks = items;
+    void* kargs[] = {(void*)&a};
     pm_queue_init_kernel<<<1, 1024, 0, st>>>(a);
     DA3S_LAUNCH_CHECK(ctx);
     // no grid-wide barrier inside: an ordinary launch (a block only ever waits for entries that running blocks produce)
     prof_begin(ctx, DA3S_TIMED_IRLS, st);
-    DA3S_CHECK_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned int)coop_blocks), dim3(PM_THREADS), kargs, ring_bytes, st));
+    DA3S_CHECK_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned int)n_blocks), dim3(PM_THREADS), kargs, ring_bytes, st));
     prof_end(ctx, DA3S_TIMED_IRLS, st);
-#else
-    prof_begin(ctx, DA3S_TIMED_IRLS, st);
-    DA3S_CHECK_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3((unsigned int)coop_blocks), dim3(PM_THREADS), kargs, ring_bytes, st));
-    prof_end(ctx, DA3S_TIMED_IRLS, st);
-#endif
     ctx->launches++;
     return DA3S_OK;
 }
