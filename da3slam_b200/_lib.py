@@ -83,6 +83,7 @@ SIGNATURES = {
     "da3s_launch_count": (_ULL, [_P]),
     "da3s_enable_peer_access": (_I, [_P, _I]),
     "da3s_measure_fp32_peak": (_I, [_P, _I, C.POINTER(_D), _P]),
+    "da3s_ransac_round_of": (_I, [_I, _I]),
     "da3s_kernel_timers": (_I, [_P, _I]),
     "da3s_kernel_time": (_I, [_P, _I, C.POINTER(_D), C.POINTER(_I), C.POINTER(_I), C.POINTER(_D)]),
     "da3s_build_cams": (_I, [_P, _P, _P, _I, _I, _P, _P]),

@@ -1027,6 +1027,11 @@ __host__ __device__ __forceinline__ int rs_round_of(int tile, int tiles_per_fram
     if (tile == tiles_per_frame / 2) return 0;
     return (int)((0x2102201201202102ull >> (4 * (tile & 15))) & 15ull);
 }
+static_assert(RS_ROUNDS == DA3S_RANSAC_ROUNDS && PA_GROUPS_PER_BLOCK * 4 == DA3S_RANSAC_TILE, "include/da3s.h documents the rounds");
+extern "C" int da3s_ransac_round_of(int tile, int tiles_per_frame) {
+    if (tile < 0 || tiles_per_frame <= 0 || tile >= tiles_per_frame) return DA3S_EINVAL;
+    return rs_round_of(tile, tiles_per_frame);
+}
 static int rs_round_tiles(int tiles_per_frame, int mask) {
     int n = 0;
     for (int t = 0; t < tiles_per_frame; ++t) n += (mask >> rs_round_of(t, tiles_per_frame)) & 1;

@@ -288,6 +288,16 @@ int da3s_ransac_inlier_mask(da3s_ctx* ctx, const da3s_pair* pairs, int n_pairs, 
                             const float* best_A /* [n_pairs,9] */, const float* best_t /* [n_pairs,3] */,
                             const uint8_t* best_ok /* [n_pairs] */, float ransac_thr, uint8_t* mask_out, void* stream);
 
+/* How da3s_align_pairs scores when no count table is asked for (no reference counterpart; oracle/SPEC.md 4): the
+ * correspondence tiles of a frame (DA3S_RANSAC_TILE pixels each, row-major) are dealt into DA3S_RANSAC_ROUNDS rounds;
+ * after round 0 the hypothesis with the most inliers so far is counted on every other tile, and before each later round
+ * a hypothesis is dropped when its count so far plus ALL correspondences of the tiles it has not seen is below that
+ * complete count.  da3s_ransac_round_of is the dealing rule (host function, no device needed): the round of `tile`
+ * in a frame of `tiles_per_frame` tiles. */
+#define DA3S_RANSAC_ROUNDS 3
+#define DA3S_RANSAC_TILE   16384
+int da3s_ransac_round_of(int tile, int tiles_per_frame);
+
 /* ---- Umeyama on materialised correspondences ----------------------------------------------
  * Replaces utils/align.py:14-40 (weighted_umeyama_alignment; variant 0),
  * align_geometry.py:59-82 (_umeyama_sim3; variant 1) and utils/align.py:224-276
